@@ -1,0 +1,1026 @@
+// libbpgpu.so — C-ABI implementation (see include/bp_gpu.h).  Host side of the B200-native trainer object that
+// replaces the reference's BP_GPU class (BP_GPU.h:40-88, BP_GPU.cu).  One `Rank` == one GPU == one NCCL rank.
+//
+// Data layout in HBM (all fp32):
+//   parameter arena   per weight layer l (fan-in K, fan-out N):  (K+1) rows x ldN floats, row k<K = w[k*N + out]
+//                     (the reference's own index convention, BP_GPU.cu:188), row K = bias; ldN = roundup(N,32).
+//                     Three identical arenas: weights, momentum deltas, gradients (flat, one SGD launch, one
+//                     all-reduce region per layer).
+//   chunk buffers     x: rows x ldx (ldx = roundup(K0+1,32)), column K0 holds 1.0f;  targets: rows x Nout packed.
+//                     Double-buffered so the next chunk's H2D overlaps the current chunk's compute.
+//   activations       Y_l: bunch x ldy_l (ldy = roundup(N_l+1,32)), column N_l holds 1.0f (bias-gradient trick);
+//                     D_l (= dE/dX_l): bunch x ldd_l (ldd = roundup(N_l,32)).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bp_gpu.h"
+#include "bp_elementwise.cuh"
+#include "bp_gemm.cuh"
+
+namespace {
+
+using namespace bp;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(BP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define BP_TRY(expr)            \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != BP_OK) return r__; \
+  } while (0)
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ driver entry
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+int get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (!g_encode) return fail(BP_ECUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  return BP_OK;
+}
+
+// 2-D fp32 tensor {inner (contiguous), outer (stride ld floats)}; box {32, box_outer}; OOB -> 0.
+// mn_major = false: operand whose reduction dim is contiguous (K-major)  -> SWIZZLE_128B, box {32 k, rows}.
+// mn_major = true : operand whose M/N dim is contiguous (MN-major)       -> SWIZZLE_128B_ATOM_32B, box {32 mn, 32 k}
+//                   (tcgen05 accepts only the 32-B-atom swizzle for MN-major 32-bit operands).
+int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
+             bool mn_major) {
+  BP_TRY(get_encode());
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0)
+    return fail(BP_EINVAL, "tensor map: base/stride not 16-byte aligned (ld=%lld)", ld);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(BP_ECUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%d", (int)r, inner,
+                outer, ld, box_outer);
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+constexpr int kBlockN = 128;
+constexpr int kStages = 6;
+
+template <bool kAMN, bool kBMN, int kEpi>
+int launch_gemm(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, kBlockN, kStages>;
+  constexpr size_t smem = gemm_smem_bytes<kBlockN, kStages>();
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev;
+  }
+  const int mt = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int nt = (p.N + kBlockN - 1) / kBlockN;
+  const int tiles = mt * nt;
+  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  const int grid = std::min(tiles, num_sms);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(a, b, p);
+  CU_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL (lazy dlopen)
+struct NcclId128 { char b[128]; };  // layout of ncclUniqueId (passed by value to ncclCommInitRank)
+struct NcclApi {
+  using Id128 = NcclId128;
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+int load_nccl() {
+  std::call_once(g_nccl_once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return;
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.lib, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+    g_nccl.GetErrorString =
+        reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+  });
+  if (!g_nccl.lib || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(BP_ECOMM, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "missing symbols");
+  return BP_OK;
+}
+#define NCCL_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    int r__ = (expr);                                                                                   \
+    if (r__ != 0)                                                                                       \
+      return fail(BP_ECOMM, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+  } while (0)
+constexpr int kNcclFloat32 = 7;  // ncclFloat32
+constexpr int kNcclSum = 0;      // ncclSum
+
+// ------------------------------------------------------------------------------------------------ per-rank state
+struct LayerState {
+  int K = 0, N = 0;        // fan-in, fan-out
+  long long ldN = 0;       // arena row stride
+  long long off = 0;       // arena offset (floats) of row 0
+  long long size = 0;      // (K+1)*ldN rounded up to 64 floats
+  float* y = nullptr;      // activation output Y_l (hidden layers only): rows x ldy
+  long long ldy = 0;
+  float* d = nullptr;      // dE/dX_l: rows x ldd
+  long long ldd = 0;
+  // tensor maps that do not depend on the chunk
+  CUtensorMap w_fwd;       // W^T as MN-major A: {N, K}, box {32,32}
+  CUtensorMap w_dx;        // W as K-major A:    {N, K}, box {32,128}
+  CUtensorMap yprev_fwd;   // Y_{l-1} as K-major B (l >= 2): {K, rows}, box {32,kBlockN}
+  CUtensorMap yprev_dw;    // Y_{l-1}^T as MN-major B (l >= 2): {K+1, bunch}, box {32,32}
+  CUtensorMap d_dx;        // D_l as K-major B: {N, bunch}, box {32,kBlockN}
+  CUtensorMap d_dw;        // D_l^T as MN-major A: {N, bunch}, box {32,32}
+};
+
+struct ChunkBuf {
+  float* x = nullptr;
+  float* t = nullptr;
+  long long cap_rows = 0;
+  int rows = 0;            // rows currently resident
+  bool has_targ = false;
+  cudaEvent_t uploaded = nullptr;  // recorded on the copy stream after the H2D
+  cudaEvent_t consumed = nullptr;  // recorded on the compute stream after the last kernel that reads the buffer
+  bool consumed_valid = false;
+};
+
+struct Rank {
+  bp_config cfg{};
+  int L = 0;               // weight layers
+  int local_bunch = 0;
+  int num_sms = 0;
+  cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr;
+  float *w = nullptr, *dw = nullptr, *g = nullptr;
+  long long arena_floats = 0;
+  LayerState layer[BP_MAXLAYER];
+  long long ldx = 0;
+  ChunkBuf chunk[2];
+  int cur = 0;             // chunk buffer the resident calls operate on
+  float* out_dev = nullptr;
+  long long out_cap_rows = 0;
+  double* sqerr_dev = nullptr;
+  void* nccl_comm = nullptr;
+  uint64_t launches = 0, bunches = 0;
+  uint32_t step = 0;
+  bool profiling = false;
+  cudaEvent_t pev[16] = {};
+  float prof_ms[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t prof_n = 0;
+  SgdBiasRanges bias_ranges{};
+
+  int Nout() const { return cfg.layersizes[L]; }
+  int K0() const { return cfg.layersizes[0]; }
+};
+
+int ensure_chunk(Rank* r, ChunkBuf& c, long long rows) {
+  if (rows <= c.cap_rows) return BP_OK;
+  if (c.x) {
+    CU_TRY(cudaStreamSynchronize(r->compute));
+    CU_TRY(cudaStreamSynchronize(r->copy));
+    CU_TRY(cudaFree(c.x));
+    CU_TRY(cudaFree(c.t));
+    c.x = c.t = nullptr;
+  }
+  const long long cap = std::max<long long>(rows, r->cfg.bunchsize);
+  CU_TRY(cudaMalloc(&c.x, sizeof(float) * cap * r->ldx));
+  CU_TRY(cudaMalloc(&c.t, sizeof(float) * cap * r->Nout()));
+  CU_TRY(cudaMemsetAsync(c.x, 0, sizeof(float) * cap * r->ldx, r->copy));
+  bp_fill_col_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, r->copy>>>(c.x, r->ldx, cap, r->K0(), 1.0f);
+  CU_TRY(cudaGetLastError());
+  r->launches++;
+  c.cap_rows = cap;
+  c.rows = 0;
+  c.consumed_valid = false;
+  return BP_OK;
+}
+
+int rank_destroy(Rank* r) {
+  if (!r) return BP_OK;
+  cudaSetDevice(r->cfg.device);
+  cudaDeviceSynchronize();
+  if (r->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(r->nccl_comm);
+  for (auto& c : r->chunk) {
+    cudaFree(c.x);
+    cudaFree(c.t);
+    if (c.uploaded) cudaEventDestroy(c.uploaded);
+    if (c.consumed) cudaEventDestroy(c.consumed);
+  }
+  for (int l = 1; l <= r->L; ++l) {
+    cudaFree(r->layer[l].y);
+    cudaFree(r->layer[l].d);
+  }
+  cudaFree(r->w);
+  cudaFree(r->dw);
+  cudaFree(r->g);
+  cudaFree(r->out_dev);
+  cudaFree(r->sqerr_dev);
+  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm})
+    if (e) cudaEventDestroy(e);
+  for (auto e : r->pev)
+    if (e) cudaEventDestroy(e);
+  for (auto s : {r->compute, r->copy, r->comm_stream})
+    if (s) cudaStreamDestroy(s);
+  delete r;
+  return BP_OK;
+}
+
+int upload_params(Rank* r, float* const* weights, float* const* bias) {
+  for (int l = 1; l <= r->L; ++l) {
+    LayerState& ls = r->layer[l];
+    CU_TRY(cudaMemcpy2DAsync(r->w + ls.off, ls.ldN * 4, weights[l], size_t(ls.N) * 4, size_t(ls.N) * 4, ls.K,
+                             cudaMemcpyHostToDevice, r->compute));
+    CU_TRY(cudaMemcpyAsync(r->w + ls.off + (long long)ls.K * ls.ldN, bias[l], size_t(ls.N) * 4,
+                           cudaMemcpyHostToDevice, r->compute));
+  }
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  return BP_OK;
+}
+
+int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* const* bias) {
+  if (!cfg || !weights || !bias) return fail(BP_EINVAL, "bp_create: null argument");
+  if (cfg->numlayers < 2 || cfg->numlayers > BP_MAXLAYER)
+    return fail(BP_EINVAL, "bp_create: numlayers=%d out of range [2,%d]", cfg->numlayers, BP_MAXLAYER);
+  for (int i = 0; i < cfg->numlayers; ++i)
+    if (cfg->layersizes[i] <= 0) return fail(BP_EINVAL, "bp_create: layersizes[%d]=%d", i, cfg->layersizes[i]);
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return fail(BP_EINVAL, "bp_create: rank %d / world %d", cfg->rank, cfg->world_size);
+  if (cfg->bunchsize <= 0 || cfg->bunchsize % cfg->world_size != 0)
+    return fail(BP_EINVAL, "bp_create: bunchsize %d must be a positive multiple of world_size %d", cfg->bunchsize,
+                cfg->world_size);
+  if ((cfg->bunchsize / cfg->world_size) % 4 != 0 && cfg->dropoutflag == 1)
+    return fail(BP_EINVAL, "bp_create: per-rank bunch (%d) must be a multiple of 4 when dropout is on",
+                cfg->bunchsize / cfg->world_size);
+  if (cfg->math_mode != BP_MATH_TF32) return fail(BP_EINVAL, "bp_create: math_mode %d not built", cfg->math_mode);
+  if (cfg->activation != BP_ACT_RELU && cfg->activation != BP_ACT_SIGMOID)
+    return fail(BP_EINVAL, "bp_create: activation %d", cfg->activation);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(BP_ENODEV, "no CUDA device (this library has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(BP_ENODEV, "device %d of %d", cfg->device, ndev);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(BP_ENODEV, "device %d is sm_%d%d; libbpgpu is built for sm_100a only", cfg->device, prop.major,
+                prop.minor);
+  CU_TRY(cudaSetDevice(cfg->device));
+
+  Rank* r = new Rank();
+  r->cfg = *cfg;
+  r->L = cfg->numlayers - 1;
+  r->local_bunch = cfg->bunchsize / cfg->world_size;
+  r->num_sms = prop.multiProcessorCount;
+  int rc = [&]() -> int {
+    CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&r->ev_t0));
+    CU_TRY(cudaEventCreate(&r->ev_t1));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_grad, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_comm, cudaEventDisableTiming));
+    for (auto& c : r->chunk) {
+      CU_TRY(cudaEventCreateWithFlags(&c.uploaded, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&c.consumed, cudaEventDisableTiming));
+    }
+    for (auto& e : r->pev) CU_TRY(cudaEventCreate(&e));
+
+    long long off = 0;
+    r->bias_ranges.n = 0;
+    for (int l = 1; l <= r->L; ++l) {
+      LayerState& ls = r->layer[l];
+      ls.K = cfg->layersizes[l - 1];
+      ls.N = cfg->layersizes[l];
+      ls.ldN = round_up(ls.N, 32);
+      ls.off = off;
+      ls.size = round_up((long long)(ls.K + 1) * ls.ldN, 64);
+      r->bias_ranges.begin4[r->bias_ranges.n] = (off + (long long)ls.K * ls.ldN) / 4;
+      r->bias_ranges.end4[r->bias_ranges.n] = (off + (long long)(ls.K + 1) * ls.ldN) / 4;
+      r->bias_ranges.n++;
+      off += ls.size;
+    }
+    r->arena_floats = off;
+    CU_TRY(cudaMalloc(&r->w, off * 4));
+    CU_TRY(cudaMalloc(&r->dw, off * 4));
+    CU_TRY(cudaMalloc(&r->g, off * 4));
+    CU_TRY(cudaMemsetAsync(r->w, 0, off * 4, r->compute));
+    CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
+    CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
+    CU_TRY(cudaMalloc(&r->sqerr_dev, sizeof(double)));
+
+    r->ldx = round_up(r->K0() + 1, 32);
+    const long long rows = cfg->bunchsize;  // activation buffers hold a full (global) bunch so CV can use it
+    for (int l = 1; l <= r->L; ++l) {
+      LayerState& ls = r->layer[l];
+      ls.ldd = round_up(ls.N, 32);
+      CU_TRY(cudaMalloc(&ls.d, rows * ls.ldd * 4));
+      CU_TRY(cudaMemsetAsync(ls.d, 0, rows * ls.ldd * 4, r->compute));
+      if (l < r->L) {
+        ls.ldy = round_up(ls.N + 1, 32);
+        CU_TRY(cudaMalloc(&ls.y, rows * ls.ldy * 4));
+        CU_TRY(cudaMemsetAsync(ls.y, 0, rows * ls.ldy * 4, r->compute));
+        bp_fill_col_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, r->compute>>>(ls.y, ls.ldy, rows, ls.N, 1.0f);
+        CU_TRY(cudaGetLastError());
+        r->launches++;
+      }
+    }
+    for (int l = 1; l <= r->L; ++l) {
+      LayerState& ls = r->layer[l];
+      const float* wl = r->w + ls.off;
+      BP_TRY(make_map(&ls.w_fwd, wl, ls.N, ls.K, ls.ldN, 32, true));
+      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
+      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
+      BP_TRY(make_map(&ls.d_dw, ls.d, ls.N, r->local_bunch, ls.ldd, 32, true));
+      if (l >= 2) {
+        LayerState& lp = r->layer[l - 1];
+        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, kBlockN, false));
+        BP_TRY(make_map(&ls.yprev_dw, lp.y, ls.K + 1, r->local_bunch, lp.ldy, 32, true));
+      }
+    }
+    BP_TRY(upload_params(r, weights, bias));
+    return BP_OK;
+  }();
+  if (rc != BP_OK) {
+    std::string keep = g_err;
+    rank_destroy(r);
+    g_err = keep;
+    return rc;
+  }
+  *out = r;
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ chunk upload
+int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
+  if (n_frames <= 0 || !in) return fail(BP_EINVAL, "upload: n_frames=%d in=%p", n_frames, (const void*)in);
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  const int nb = r->cur ^ 1;
+  ChunkBuf& c = r->chunk[nb];
+  BP_TRY(ensure_chunk(r, c, n_frames));
+  if (c.consumed_valid) CU_TRY(cudaStreamWaitEvent(r->copy, c.consumed, 0));
+  const size_t rowb = size_t(r->K0()) * 4;
+  CU_TRY(cudaMemcpy2DAsync(c.x, r->ldx * 4, in, rowb, rowb, n_frames, cudaMemcpyHostToDevice, r->copy));
+  if (targ)
+    CU_TRY(cudaMemcpyAsync(c.t, targ, size_t(n_frames) * r->Nout() * 4, cudaMemcpyHostToDevice, r->copy));
+  CU_TRY(cudaEventRecord(c.uploaded, r->copy));
+  c.rows = n_frames;
+  c.has_targ = targ != nullptr;
+  r->cur = nb;
+  CU_TRY(cudaStreamWaitEvent(r->compute, c.uploaded, 0));
+  // The caller may overwrite its buffers as soon as we return (BP_GPU::train semantics): wait for the DMA only.
+  CU_TRY(cudaEventSynchronize(c.uploaded));
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// Forward over rows [f0, f0+n) of the resident chunk.  train=true: masks + D_L; train=false: keep-scaling (CV).
+int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, long long ldo2, double* sqerr) {
+  const bp_config& cf = r->cfg;
+  const bool drop = cf.dropoutflag == 1;
+  const uint32_t seed_lo = (uint32_t)cf.seed, seed_hi = (uint32_t)(cf.seed >> 32);
+  const int frame0 = cf.rank * r->local_bunch;
+  float* xb = c.x + (long long)f0 * r->ldx;
+
+  if (train && drop && cf.visible_omit > 0.0f) {
+    dim3 grid((r->K0() + 255) / 256, (n + 3) / 4);
+    bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(xb, r->ldx, n, r->K0(), cf.visible_omit, seed_lo, seed_hi,
+                                                          r->step, frame0);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+  }
+  for (int l = 1; l <= r->L; ++l) {
+    LayerState& ls = r->layer[l];
+    GemmParams p{};
+    p.M = ls.N;
+    p.N = n;
+    p.K = ls.K;
+    p.bias = r->w + ls.off + (long long)ls.K * ls.ldN;
+    p.act = cf.activation;
+    p.scale = 1.0f;
+    if (!train && drop) p.scale = 1.0f - (l == 1 ? cf.visible_omit : cf.hid_omit);
+    p.seed_lo = seed_lo;
+    p.seed_hi = seed_hi;
+    p.step = r->step;
+    p.layer = (uint32_t)l;
+    p.frame0 = frame0;
+    CUtensorMap xmap;
+    const CUtensorMap* bmap = &ls.yprev_fwd;
+    if (l == 1) {
+      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, kBlockN, false));
+      bmap = &xmap;
+    }
+    if (l < r->L) {
+      p.out = ls.y;
+      p.ldo = ls.ldy;
+      p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
+      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->num_sms, ls.w_fwd, *bmap, p)));
+    } else {
+      if (train) {
+        p.out = ls.d;
+        p.ldo = ls.ldd;
+        p.aux = c.t + (long long)f0 * ls.N;
+        p.ldaux = ls.N;
+        p.gscale = 2.0f / (float)cf.bunchsize;  // (2.0f/rows), rows = GLOBAL bunch (DevFunc.cu:263)
+      } else {
+        p.out = nullptr;
+        p.out2 = out2;
+        p.ldo2 = ldo2;
+        if (sqerr) {
+          p.aux = c.t + (long long)f0 * ls.N;
+          p.ldaux = ls.N;
+          p.sqerr = sqerr;
+        }
+      }
+      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->num_sms, ls.w_fwd, *bmap, p)));
+    }
+    r->launches++;
+  }
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one train bunch
+int train_bunch(Rank* r, ChunkBuf& c, int f0) {
+  const bp_config& cf = r->cfg;
+  const int n = r->local_bunch;
+  const bool prof = r->profiling;
+  int pe = 0;
+  auto mark = [&]() { if (prof) cudaEventRecord(r->pev[pe++], r->compute); };
+  mark();                                               // 0
+  BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, nullptr));
+  mark();                                               // 1: fwd done
+  float* xb = c.x + (long long)f0 * r->ldx;
+  // dX chain first (it only needs W, which the deferred update has not touched yet) ...
+  for (int l = r->L; l >= 2; --l) {
+    LayerState& ls = r->layer[l];
+    LayerState& lp = r->layer[l - 1];
+    GemmParams p{};
+    p.M = ls.K;  // units of layer l-1
+    p.N = n;
+    p.K = ls.N;
+    p.out = lp.d;
+    p.ldo = lp.ldd;
+    p.aux = lp.y;
+    p.ldaux = lp.ldy;
+    p.act = cf.activation;
+    BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->num_sms, ls.w_dx, ls.d_dx, p)));
+    r->launches++;
+  }
+  mark();                                               // 2: dX done
+  // ... then the weight (+bias) gradients, last layer first so its all-reduce starts earliest.
+  for (int l = r->L; l >= 1; --l) {
+    LayerState& ls = r->layer[l];
+    GemmParams p{};
+    p.M = ls.N;
+    p.N = ls.K + 1;  // + the all-ones column -> row K of the gradient block = bias gradient
+    p.K = n;
+    p.out = r->g + ls.off;
+    p.ldo = ls.ldN;
+    CUtensorMap xmap;
+    const CUtensorMap* bmap = &ls.yprev_dw;
+    if (l == 1) {
+      BP_TRY(make_map(&xmap, xb, ls.K + 1, n, r->ldx, 32, true));
+      bmap = &xmap;
+    }
+    BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->compute, r->num_sms, ls.d_dw, *bmap, p)));
+    r->launches++;
+    if (r->nccl_comm) {
+      CU_TRY(cudaEventRecord(r->ev_grad, r->compute));
+      CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_grad, 0));
+      NCCL_TRY(g_nccl.AllReduce(r->g + ls.off, r->g + ls.off, (size_t)ls.size, kNcclFloat32, kNcclSum, r->nccl_comm,
+                                r->comm_stream));
+    }
+  }
+  mark();                                               // 3: dW done
+  if (r->nccl_comm) {
+    CU_TRY(cudaEventRecord(r->ev_comm, r->comm_stream));
+    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
+  }
+  mark();                                               // 4: all-reduce waited
+  {
+    const long long n4 = r->arena_floats / 4;
+    const int grid = r->num_sms * 8;
+    const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
+    const float c1 = (1 - cf.momentum) * cf.lrate;
+    if (cf.weightcost != 0.0f)
+      bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
+                                                        cf.momentum, c1, cf.weightcost, r->bias_ranges);
+    else
+      bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
+                                                         cf.momentum, c1, 0.0f, r->bias_ranges);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+  }
+  mark();                                               // 5: sgd done
+  r->step++;
+  r->bunches++;
+  if (prof) {
+    CU_TRY(cudaEventSynchronize(r->pev[5]));
+    float ms;
+    // fwd (incl. input dropout), dX, dW, sgd, allreduce wait
+    cudaEventElapsedTime(&ms, r->pev[0], r->pev[1]); r->prof_ms[0] += ms;
+    cudaEventElapsedTime(&ms, r->pev[1], r->pev[2]); r->prof_ms[1] += ms;
+    cudaEventElapsedTime(&ms, r->pev[2], r->pev[3]); r->prof_ms[2] += ms;
+    cudaEventElapsedTime(&ms, r->pev[4], r->pev[5]); r->prof_ms[3] += ms;
+    cudaEventElapsedTime(&ms, r->pev[3], r->pev[4]); r->prof_ms[4] += ms;
+    r->prof_n++;
+  }
+  return BP_OK;
+}
+
+int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  ChunkBuf& c = r->chunk[r->cur];
+  if (!c.x || !c.has_targ) return fail(BP_EINVAL, "train_resident: no resident chunk with targets");
+  if (first_bunch < 0 || n_bunches < 0 || (long long)(first_bunch + n_bunches) * r->local_bunch > c.rows)
+    return fail(BP_EINVAL, "train_resident: bunches [%d,%d) exceed resident rows %d (bunch %d)", first_bunch,
+                first_bunch + n_bunches, c.rows, r->local_bunch);
+  for (int b = 0; b < n_bunches; ++b) BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch));
+  CU_TRY(cudaEventRecord(c.consumed, r->compute));
+  c.consumed_valid = true;
+  return BP_OK;
+}
+
+int rank_forward_resident(Rank* r, int first_frame, int n_frames, float* out_host, double* sum_sq) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  ChunkBuf& c = r->chunk[r->cur];
+  if (!c.x) return fail(BP_EINVAL, "forward_resident: no resident chunk");
+  if (first_frame < 0 || n_frames <= 0 || first_frame + n_frames > c.rows)
+    return fail(BP_EINVAL, "forward_resident: rows [%d,%d) exceed resident rows %d", first_frame,
+                first_frame + n_frames, c.rows);
+  if (sum_sq && !c.has_targ) return fail(BP_EINVAL, "forward_resident: squared error needs resident targets");
+  const int no = r->Nout();
+  if (out_host && n_frames > r->out_cap_rows) {
+    CU_TRY(cudaStreamSynchronize(r->compute));
+    if (r->out_dev) CU_TRY(cudaFree(r->out_dev));
+    r->out_dev = nullptr;
+    CU_TRY(cudaMalloc(&r->out_dev, size_t(n_frames) * no * 4));
+    r->out_cap_rows = n_frames;
+  }
+  if (sum_sq) CU_TRY(cudaMemsetAsync(r->sqerr_dev, 0, sizeof(double), r->compute));
+  const int B = r->cfg.bunchsize;
+  for (int i = 0; i < n_frames; i += B) {
+    const int n = std::min(B, n_frames - i);
+    BP_TRY(forward_rows(r, c, first_frame + i, n, false, out_host ? r->out_dev + (long long)i * no : nullptr, no,
+                        sum_sq ? r->sqerr_dev : nullptr));
+  }
+  CU_TRY(cudaEventRecord(c.consumed, r->compute));
+  c.consumed_valid = true;
+  if (out_host)
+    CU_TRY(cudaMemcpyAsync(out_host, r->out_dev, size_t(n_frames) * no * 4, cudaMemcpyDeviceToHost, r->compute));
+  if (sum_sq) CU_TRY(cudaMemcpyAsync(sum_sq, r->sqerr_dev, sizeof(double), cudaMemcpyDeviceToHost, r->compute));
+  if (out_host || sum_sq) CU_TRY(cudaStreamSynchronize(r->compute));
+  return BP_OK;
+}
+
+int rank_return_weights(Rank* r, float* const* weights, float* const* bias) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  for (int l = 1; l <= r->L; ++l) {
+    LayerState& ls = r->layer[l];
+    CU_TRY(cudaMemcpy2DAsync(weights[l], size_t(ls.N) * 4, r->w + ls.off, ls.ldN * 4, size_t(ls.N) * 4, ls.K,
+                             cudaMemcpyDeviceToHost, r->compute));
+    CU_TRY(cudaMemcpyAsync(bias[l], r->w + ls.off + (long long)ls.K * ls.ldN, size_t(ls.N) * 4,
+                           cudaMemcpyDeviceToHost, r->compute));
+  }
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  return BP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+struct bp_handle {
+  std::vector<Rank*> ranks;  // 1 entry for a rank handle; gpu_used entries for an in-process group
+};
+
+namespace {
+
+// Run fn(rank_index) on every rank of a group, one host thread per GPU; returns the first failure.
+template <class F>
+int for_each_rank(bp_handle* h, F fn) {
+  if (h->ranks.size() == 1) return fn(0);
+  std::vector<int> rc(h->ranks.size(), BP_OK);
+  std::vector<std::string> msg(h->ranks.size());
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < h->ranks.size(); ++i)
+    th.emplace_back([&, i] {
+      rc[i] = fn((int)i);
+      if (rc[i] != BP_OK) msg[i] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < rc.size(); ++i)
+    if (rc[i] != BP_OK) {
+      g_err = msg[i];
+      return rc[i];
+    }
+  return BP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bp_last_error(void) { return g_err.c_str(); }
+int bp_version(void) { return 100; }
+
+int bp_create_ex(bp_handle** h, const bp_config* cfg, float* const* weights, float* const* bias) {
+  if (!h) return fail(BP_EINVAL, "bp_create_ex: null handle pointer");
+  *h = nullptr;
+  Rank* r = nullptr;
+  BP_TRY(rank_create(&r, cfg, weights, bias));
+  bp_handle* hh = new bp_handle();
+  hh->ranks.push_back(r);
+  *h = hh;
+  return BP_OK;
+}
+
+int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes, int bunchsize, float lrate,
+              float momentum, float weightcost, float* const* weights, float* const* bias, int dropoutflag,
+              float visible_omit, float hid_omit) {
+  if (!h || !layersizes) return fail(BP_EINVAL, "bp_create: null argument");
+  *h = nullptr;
+  if (numlayers < 2 || numlayers > BP_MAXLAYER) return fail(BP_EINVAL, "bp_create: numlayers=%d", numlayers);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(BP_ENODEV, "no CUDA device (this library has no CPU fallback)");
+  }
+  if (gpu_used < 1 || gpu_used > ndev)  // BP_GPU.cu:20-24 "GPU selected out of range"
+    return fail(BP_ENODEV, "gpu_used=%d out of range [1,%d]", gpu_used, ndev);
+  bp_config cfg{};
+  cfg.world_size = gpu_used;
+  cfg.numlayers = numlayers;
+  for (int i = 0; i < numlayers; ++i) cfg.layersizes[i] = layersizes[i];
+  cfg.bunchsize = bunchsize;
+  cfg.lrate = lrate;
+  cfg.momentum = momentum;
+  cfg.weightcost = weightcost;
+  cfg.dropoutflag = dropoutflag;
+  cfg.visible_omit = visible_omit;
+  cfg.hid_omit = hid_omit;
+  cfg.activation = BP_ACT_RELU;
+  cfg.math_mode = BP_MATH_TF32;
+  cfg.seed = 0x5eed5eedULL;
+  if (const char* e = getenv("BP_ACTIVATION")) cfg.activation = (strcmp(e, "sigmoid") == 0) ? BP_ACT_SIGMOID : 0;
+  if (const char* e = getenv("BP_SEED")) cfg.seed = strtoull(e, nullptr, 0);
+
+  bp_handle* hh = new bp_handle();
+  hh->ranks.assign(gpu_used, nullptr);
+  char id[128];
+  if (gpu_used > 1) {
+    int rc = bp_comm_unique_id(id);
+    if (rc != BP_OK) { delete hh; return rc; }
+  }
+  int rc = for_each_rank(hh, [&](int i) -> int {
+    bp_config c = cfg;
+    c.rank = i;
+    c.device = i;
+    BP_TRY(rank_create(&hh->ranks[i], &c, weights, bias));
+    if (gpu_used > 1) {
+      NcclApi::Id128 uid;
+      memcpy(uid.b, id, 128);
+      NCCL_TRY(g_nccl.CommInitRank(&hh->ranks[i]->nccl_comm, gpu_used, uid, i));
+    }
+    return BP_OK;
+  });
+  if (rc != BP_OK) {
+    std::string keep = g_err;
+    bp_destroy(hh);
+    g_err = keep;
+    return rc;
+  }
+  *h = hh;
+  return BP_OK;
+}
+
+void bp_destroy(bp_handle* h) {
+  if (!h) return;
+  for (Rank* r : h->ranks) rank_destroy(r);
+  delete h;
+}
+
+int bp_upload_chunk(bp_handle* h, int n_frames, const float* in, const float* targ) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  if (h->ranks.size() == 1) return rank_upload(h->ranks[0], n_frames, in, targ);
+  // In-process group: rank r owns rows [r*lb, (r+1)*lb) of every global bunch.  Re-pack per rank, bunch by bunch.
+  const int G = (int)h->ranks.size();
+  const int B = h->ranks[0]->cfg.bunchsize, lb = B / G;
+  const int nb = n_frames / B;
+  if (nb == 0) return fail(BP_EINVAL, "upload: chunk of %d frames has no full bunch of %d", n_frames, B);
+  return for_each_rank(h, [&](int i) -> int {
+    Rank* r = h->ranks[i];
+    const int k0 = r->K0(), no = r->Nout();
+    std::vector<float> xin((size_t)nb * lb * k0), tin(targ ? (size_t)nb * lb * no : 0);
+    for (int b = 0; b < nb; ++b) {
+      memcpy(&xin[(size_t)b * lb * k0], in + ((size_t)b * B + (size_t)i * lb) * k0, sizeof(float) * lb * k0);
+      if (targ)
+        memcpy(&tin[(size_t)b * lb * no], targ + ((size_t)b * B + (size_t)i * lb) * no, sizeof(float) * lb * no);
+    }
+    return rank_upload(r, nb * lb, xin.data(), targ ? tin.data() : nullptr);
+  });
+}
+
+int bp_train_resident(bp_handle* h, int first_bunch, int n_bunches) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  return for_each_rank(h, [&](int i) { return rank_train_resident(h->ranks[i], first_bunch, n_bunches); });
+}
+
+int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
+  if (!h || !in || !targ) return fail(BP_EINVAL, "bp_train: null argument");
+  Rank* r0 = h->ranks[0];
+  const int per_call_bunch = (h->ranks.size() == 1) ? r0->local_bunch : r0->cfg.bunchsize;
+  const int nb = n_frames / per_call_bunch;
+  if (n_frames % per_call_bunch)
+    printf("this bunch has only %d samples and is ignored.\n", n_frames % per_call_bunch);  // BP_GPU.cu:317
+  if (nb == 0) return BP_OK;
+  BP_TRY(bp_upload_chunk(h, n_frames, in, targ));
+  return bp_train_resident(h, 0, nb);
+}
+
+int bp_forward_resident(bp_handle* h, int first_frame, int n_frames, float* out_host, double* sum_sq_err) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  return rank_forward_resident(h->ranks[0], first_frame, n_frames, out_host, sum_sq_err);
+}
+
+int bp_crossvalid(bp_handle* h, int n_frames, const float* in, const float* targ, float* sum_sq_err) {
+  if (!h || !in || !targ || !sum_sq_err) return fail(BP_EINVAL, "bp_crossvalid: null argument");
+  if (n_frames <= 0) { *sum_sq_err = 0.0f; return BP_OK; }
+  Rank* r = h->ranks[0];  // CV runs on device 0 only, like the reference (BP_GPU.cu:440-441)
+  BP_TRY(rank_upload(r, n_frames, in, targ));
+  double s = 0.0;
+  BP_TRY(rank_forward_resident(r, 0, n_frames, nullptr, &s));
+  *sum_sq_err = (float)s;
+  return BP_OK;
+}
+
+int bp_forward(bp_handle* h, int n_frames, const float* in, float* out) {
+  if (!h || !in || !out) return fail(BP_EINVAL, "bp_forward: null argument");
+  Rank* r = h->ranks[0];
+  BP_TRY(rank_upload(r, n_frames, in, nullptr));
+  return rank_forward_resident(r, 0, n_frames, out, nullptr);
+}
+
+int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias) {
+  if (!h || !weights || !bias) return fail(BP_EINVAL, "bp_return_weights: null argument");
+  return rank_return_weights(h->ranks[0], weights, bias);  // device 0, BP_GPU.cu:915
+}
+
+int bp_sync(bp_handle* h) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  return for_each_rank(h, [&](int i) -> int {
+    Rank* r = h->ranks[i];
+    CU_TRY(cudaSetDevice(r->cfg.device));
+    CU_TRY(cudaStreamSynchronize(r->copy));
+    CU_TRY(cudaStreamSynchronize(r->comm_stream));
+    CU_TRY(cudaStreamSynchronize(r->compute));
+    return BP_OK;
+  });
+}
+
+void* bp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void bp_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int bp_timer_start(bp_handle* h) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  CU_TRY(cudaEventRecord(r->ev_t0, r->compute));
+  return BP_OK;
+}
+int bp_timer_stop(bp_handle* h, float* elapsed_ms) {
+  if (!h || !elapsed_ms) return fail(BP_EINVAL, "null argument");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  CU_TRY(cudaEventRecord(r->ev_t1, r->compute));
+  CU_TRY(cudaEventSynchronize(r->ev_t1));
+  CU_TRY(cudaEventElapsedTime(elapsed_ms, r->ev_t0, r->ev_t1));
+  return BP_OK;
+}
+
+int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bunches) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  uint64_t l = 0;
+  for (Rank* r : h->ranks) l += r->launches;
+  if (kernel_launches) *kernel_launches = l;
+  if (train_bunches) *train_bunches = h->ranks[0]->bunches;
+  return BP_OK;
+}
+
+int bp_set_profiling(bp_handle* h, int on) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  for (Rank* r : h->ranks) {
+    r->profiling = on != 0;
+    for (float& m : r->prof_ms) m = 0.0f;
+    r->prof_n = 0;
+  }
+  return BP_OK;
+}
+int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled) {
+  if (!h || !ms) return fail(BP_EINVAL, "null argument");
+  Rank* r = h->ranks[0];
+  for (int i = 0; i < 6; ++i) ms[i] = r->prof_ms[i];
+  if (bunches_profiled) *bunches_profiled = r->prof_n;
+  return BP_OK;
+}
+
+int bp_comm_unique_id(char id128[128]) {
+  if (!id128) return fail(BP_EINVAL, "null id");
+  BP_TRY(load_nccl());
+  NCCL_TRY(g_nccl.GetUniqueId(id128));
+  return BP_OK;
+}
+int bp_comm_init(bp_handle* h, const char id128[128]) {
+  if (!h || !id128 || h->ranks.size() != 1) return fail(BP_EINVAL, "bp_comm_init: needs a rank handle");
+  Rank* r = h->ranks[0];
+  if (r->cfg.world_size == 1) return BP_OK;
+  BP_TRY(load_nccl());
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  NcclApi::Id128 uid;
+  memcpy(uid.b, id128, 128);
+  NCCL_TRY(g_nccl.CommInitRank(&r->nccl_comm, r->cfg.world_size, uid, r->cfg.rank));
+  return BP_OK;
+}
+
+int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame, uint32_t unit, float p) {
+  float u[4];
+  philox_uniform4((uint32_t)seed, (uint32_t)(seed >> 32), frame >> 2, unit, layer, step, u);
+  return u[frame & 3] < p ? 1 : 0;
+}
+
+int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* out,
+                  int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
+                  float* elapsed_ms) {
+  if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return fail(BP_EINVAL, "bp_debug_gemm: bad argument");
+  if (math_mode != BP_MATH_TF32) return fail(BP_EINVAL, "bp_debug_gemm: math_mode %d not built", math_mode);
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(BP_ENODEV, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
+  // operand shapes (rows x cols as stored on the host, row-major with the given ld)
+  long long a_rows, a_cols, b_rows, b_cols;
+  bool amn, bmn;
+  switch (kind) {
+    case 0: case 3: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
+    case 1: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
+    case 2: a_rows = K; a_cols = M; b_rows = K; b_cols = N; amn = true; bmn = true; break;
+    default: return fail(BP_EINVAL, "bp_debug_gemm: kind %d", kind);
+  }
+  const long long dlda = round_up(a_cols, 32), dldb = round_up(b_cols, 32), dldo = round_up(M, 32),
+                  dldaux = round_up(M, 32);
+  float *dA = nullptr, *dB = nullptr, *dO = nullptr, *dBias = nullptr, *dAux = nullptr;
+  cudaStream_t st;
+  cudaEvent_t e0, e1;
+  int rc = [&]() -> int {
+    CU_TRY(cudaStreamCreate(&st));
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    CU_TRY(cudaMalloc(&dA, a_rows * dlda * 4));
+    CU_TRY(cudaMalloc(&dB, b_rows * dldb * 4));
+    CU_TRY(cudaMalloc(&dO, (long long)N * dldo * 4));
+    CU_TRY(cudaMemset(dA, 0, a_rows * dlda * 4));
+    CU_TRY(cudaMemset(dB, 0, b_rows * dldb * 4));
+    CU_TRY(cudaMemset(dO, 0, (long long)N * dldo * 4));
+    CU_TRY(cudaMemcpy2D(dA, dlda * 4, A, size_t(lda) * 4, a_cols * 4, a_rows, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy2D(dB, dldb * 4, B, size_t(ldb) * 4, b_cols * 4, b_rows, cudaMemcpyHostToDevice));
+    if (bias) {
+      CU_TRY(cudaMalloc(&dBias, size_t(M) * 4));
+      CU_TRY(cudaMemcpy(dBias, bias, size_t(M) * 4, cudaMemcpyHostToDevice));
+    }
+    if (aux) {
+      CU_TRY(cudaMalloc(&dAux, (long long)N * dldaux * 4));
+      CU_TRY(cudaMemcpy2D(dAux, dldaux * 4, aux, size_t(ldaux) * 4, size_t(M) * 4, N, cudaMemcpyHostToDevice));
+    }
+    CUtensorMap ma, mb;
+    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, amn ? 32 : GEMM_BLOCK_M, amn));
+    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, bmn ? 32 : kBlockN, bmn));
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.out = dO; p.ldo = dldo;
+    p.bias = dBias;
+    p.aux = dAux; p.ldaux = dldaux;
+    p.scale = scale;
+    p.act = act < 0 ? 0 : act;
+    if (const char* e = getenv("BP_DBG_MN_LBO")) p.dbg_mn_lbo = (uint32_t)atoi(e);
+    if (const char* e = getenv("BP_DBG_MN_SBO")) p.dbg_mn_sbo = (uint32_t)atoi(e);
+    const int sms = prop.multiProcessorCount;
+    CU_TRY(cudaEventRecord(e0, st));
+    if (kind == 0) {
+      if (!bias) return fail(BP_EINVAL, "kind 0 needs bias");
+      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p)));
+    } else if (kind == 3) {
+      BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p)));
+    } else if (kind == 1) {
+      if (!aux) return fail(BP_EINVAL, "kind 1 needs aux (Y)");
+      BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p)));
+    } else {
+      BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p)));
+    }
+    CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (elapsed_ms) CU_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
+    return BP_OK;
+  }();
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux);
+  return rc;
+}
+
+int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bunch, float momentum, float lrate,
+                 float weightcost) {
+  if (n <= 0 || !delta || !weights || !grad) return fail(BP_EINVAL, "bp_debug_sgd: bad argument");
+  const long long n4 = (n + 3) / 4;
+  float *d = nullptr, *w = nullptr, *g = nullptr;
+  int rc = [&]() -> int {
+    CU_TRY(cudaMalloc(&d, n4 * 16));
+    CU_TRY(cudaMalloc(&w, n4 * 16));
+    CU_TRY(cudaMalloc(&g, n4 * 16));
+    CU_TRY(cudaMemset(d, 0, n4 * 16));
+    CU_TRY(cudaMemset(w, 0, n4 * 16));
+    CU_TRY(cudaMemset(g, 0, n4 * 16));
+    CU_TRY(cudaMemcpy(d, delta, size_t(n) * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(w, weights, size_t(n) * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g, grad, size_t(n) * 4, cudaMemcpyHostToDevice));
+    SgdBiasRanges br{};
+    const float c1 = (1 - momentum) * lrate;
+    if (weightcost != 0.0f)
+      bp_sgd_kernel<true><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum, c1,
+                                            weightcost, br);
+    else
+      bp_sgd_kernel<false><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum,
+                                             c1, 0.0f, br);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(delta, d, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(weights, w, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    return BP_OK;
+  }();
+  cudaFree(d); cudaFree(w); cudaFree(g);
+  return rc;
+}
+
+}  // extern "C"

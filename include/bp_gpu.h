@@ -1,0 +1,144 @@
+/* bp_gpu.h — C-ABI of libbpgpu.so: the B200-native (sm_100a) replacement for the reference's trainer object.
+ *
+ * The reference's drop-in seam is the C++ class BP_GPU (reference BP_GPU.h:40-88) used by main() at exactly four
+ * sites: constructor BPtrain.cc:31-32, train :53, returnWeights :57, CrossValid :77, destructor :96.
+ * Each entry point below names the reference member it replaces.  Plain pointers and sizes only; all `float*`
+ * arguments are HOST memory owned by the caller unless stated otherwise.
+ *
+ * Error convention: the reference prints and exit(0)s (BP_GPU.cu:20-24, 929-933).  Here every call returns
+ * BP_OK (0) or a negative BP_E* code and bp_last_error() gives the message; the CLI maps that to "log + exit(0)".
+ * There is NO CPU fallback: without a usable sm_100 device bp_create fails with BP_ENODEV.
+ */
+#ifndef BP_GPU_H_
+#define BP_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_MAXLAYER 10 /* reference BP_GPU.h:13 */
+
+#define BP_OK 0
+#define BP_EINVAL (-1)  /* bad argument */
+#define BP_ENODEV (-2)  /* no sm_100 CUDA device / gpu_used out of range (reference BP_GPU.cu:17-25) */
+#define BP_ECUDA (-3)   /* CUDA runtime / driver error */
+#define BP_ENOMEM (-4)
+#define BP_ECOMM (-5)   /* NCCL error */
+
+#define BP_ACT_RELU 0    /* HEAD: DevFunc.cu:67-97 */
+#define BP_ACT_SIGMOID 1 /* commented variant: DevFunc.cu:48-64 */
+
+#define BP_MATH_TF32 0   /* single-pass TF32 tensor-core products, fp32 accumulate (throughput mode) */
+#define BP_MATH_3XTF32 1 /* hi/lo split, three TF32 products per term: ~fp32 accuracy (parity mode) */
+
+typedef struct bp_handle bp_handle;
+
+/* Extended construction parameters (everything the reference fixes at compile time or leaves to the wall clock). */
+typedef struct bp_config {
+  int device;       /* CUDA device ordinal for this rank */
+  int world_size;   /* data-parallel ranks (1 = single GPU) */
+  int rank;         /* this rank, 0..world_size-1 */
+  int numlayers;    /* number of layer SIZES (weight layers = numlayers-1), <= BP_MAXLAYER */
+  int layersizes[BP_MAXLAYER];
+  int bunchsize;    /* GLOBAL minibatch rows per step; each rank processes bunchsize/world_size rows */
+  float lrate, momentum, weightcost;
+  int dropoutflag;
+  float visible_omit, hid_omit;
+  int activation;   /* BP_ACT_* */
+  int math_mode;    /* BP_MATH_* */
+  uint64_t seed;    /* dropout RNG seed (reference: time(NULL), BP_GPU.cu:77-78) */
+} bp_config;
+
+/* BP_GPU::BP_GPU (BP_GPU.cu:10-197).  weights[i], bias[i] valid for i = 1..numlayers-1 (index 0 unused, as in the
+ * reference); weights[i] = float[layersizes[i-1]*layersizes[i]] laid out w[in*n_out + out].  Copied, not retained.
+ * gpu_used > 1 runs gpu_used data-parallel ranks (one host thread + NCCL rank per GPU) inside this process. */
+int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes, int bunchsize, float lrate,
+              float momentum, float weightcost, float* const* weights, float* const* bias, int dropoutflag,
+              float visible_omit, float hid_omit);
+
+/* Same, with the extended configuration; one handle == one rank (one process per GPU under torchrun). */
+int bp_create_ex(bp_handle** h, const bp_config* cfg, float* const* weights, float* const* bias);
+
+/* BP_GPU::~BP_GPU (BP_GPU.cu:199-238). */
+void bp_destroy(bp_handle* h);
+
+/* BP_GPU::train (BP_GPU.cu:241-331): in = n_frames x layersizes[0], targ = n_frames x layersizes[last], row-major.
+ * Uploads the chunk and runs floor(n_frames/bunch) full bunches of forward + back-prop + SGD update; a trailing
+ * partial bunch is skipped exactly like the reference (:297-318).  The host buffers are not read after return.
+ * For a rank handle (world_size > 1) n_frames/in/targ are this rank's shard: local bunch = bunchsize/world_size. */
+int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ);
+
+/* BP_GPU::CrossValid (BP_GPU.cu:408-479): forward only (partial last bunch included, :450); *sum_sq_err receives
+ * sum over frames and output dims of (out - targ)^2.  With dropoutflag the keep probability scales the products
+ * (:705-746).  Weights are not modified (the reference's in-place rescale drift, :726-746, is not replicated). */
+int bp_crossvalid(bp_handle* h, int n_frames, const float* in, const float* targ, float* sum_sq_err);
+
+/* Decode extension of cv_bunch_single (BP_GPU.cu:676-773): writes the enhanced frames, out = n_frames x
+ * layersizes[last] (the reference computes them and throws them away, :445-473). */
+int bp_forward(bp_handle* h, int n_frames, const float* in, float* out);
+
+/* BP_GPU::returnWeights (BP_GPU.cu:910-923): fills caller-owned arrays, same indexing as bp_create. */
+int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias);
+
+/* Last error message of the calling thread ("" if none). */
+const char* bp_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device-resident control (measurement and pipelining): the same work as bp_train / bp_crossvalid split into
+ * "upload a chunk" and "run bunches on the resident chunk" so that a benchmark can time the kernels with inputs
+ * already in HBM, and a reader thread can overlap the next upload.
+ * ------------------------------------------------------------------------------------------------------------- */
+int bp_upload_chunk(bp_handle* h, int n_frames, const float* in, const float* targ /* may be NULL */);
+int bp_train_resident(bp_handle* h, int first_bunch, int n_bunches);
+int bp_forward_resident(bp_handle* h, int first_frame, int n_frames, float* out_host /* may be NULL */,
+                        double* sum_sq_err /* may be NULL; needs resident targets */);
+int bp_sync(bp_handle* h);
+
+/* Pinned host memory for true asynchronous DMA of chunks (the reference uses pageable new[] buffers). */
+void* bp_host_alloc(size_t bytes);
+void bp_host_free(void* p);
+
+/* CUDA-event stopwatch on the handle's compute stream. */
+int bp_timer_start(bp_handle* h);
+int bp_timer_stop(bp_handle* h, float* elapsed_ms);
+
+/* Counters since creation: kernels launched by this library on this handle; train bunches executed. */
+int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bunches);
+
+/* Per-kernel device time of the most recent bunch when profiling is on (CUDA events around each launch class):
+ * ms[0] = forward GEMMs, ms[1] = dX GEMMs, ms[2] = dW GEMMs, ms[3] = SGD update, ms[4] = all-reduce wait,
+ * ms[5] = input dropout.  Enabling it serialises nothing but adds event records. */
+int bp_set_profiling(bp_handle* h, int on);
+int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled);
+
+/* Data-parallel communicator (NCCL over NVLink): rank 0 obtains an id, every rank passes the same 128 bytes. */
+int bp_comm_unique_id(char id128[128]);
+int bp_comm_init(bp_handle* h, const char id128[128]);
+
+/* Mask that the fused dropout draws for (activation tensor `layer`, global frame, unit) at bunch `step`;
+ * exposed so tests can replay masks against the oracle.  Returns 1 = dropped, 0 = kept. */
+int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame, uint32_t unit, float p);
+
+/* Stand-alone launch of one fused GEMM (host operands, testing only).
+ *  kind 0: fwd  out[n*ldo+m] = act(scale * sum_k W[k*ldw+m] * X[n*ldx+k] + bias[m])     A=W (K x M), B=X (N x K)
+ *  kind 1: dX   out[n*ldo+m] = act'(Y[n*ldy+m]) * sum_k W[m*ldw+k] * D[n*ldd+k]         A=W (M x K), B=D (N x K)
+ *  kind 2: dW   out[n*ldo+m] = sum_k D[k*ldd+m] * X[k*ldx+n]                            A=D (K x M), B=X (K x N)
+ *  kind 3: plain fwd (no bias/activation).   act < 0 means "no activation" for kind 0. */
+int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* out,
+                  int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
+                  float* elapsed_ms);
+
+/* Stand-alone fused SGD update on host arrays of length n (testing only): kernUpdatedelta + kernAccSum
+ * (DevFunc.cu:313-318, 270-277). */
+int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bunch, float momentum, float lrate,
+                 float weightcost);
+
+int bp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP_GPU_H_ */
