@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the frame-wise DNN hot path (BASELINE.json metric) on N B200s.
+
+A "step" is one bunch (minibatch) of spliced LPS frames through forward + back-prop + SGD update on the C2 workload of
+BASELINE.json: 2827 -> 2048x3 (ReLU) -> 257, bunch 1024 per GPU (weak scaling: global bunch = 1024 * N), synthetic
+frames, Glorot-initialised weights (Gen_rand_net scheme), lrate 1 (reference script), momentum 0.9.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C5]
+  N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...` (one rank/GPU).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs in HBM before the timed region, CUDA
+events on the library's compute stream, max over ranks); `e2e` = the same work through the reference-facing C-ABI
+call bp_train() with PINNED HOST buffers (H2D of every step's inputs inside the timed region, D2H of every step's loss).
+`--impl reference` times the CPU restatement of the reference path (oracle/, the reference has no CPU implementation of
+its own — SURVEY.md §8c) on the host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (layersizes, local bunch, dropoutflag, visible_omit, hid_omit, train?)
+    "C2": ([2827, 2048, 2048, 2048, 257], 1024, 0, 0.0, 0.0, True),
+    "C3": ([3084, 2048, 2048, 2048, 257], 2048, 1, 0.2, 0.2, True),
+    "C4": ([2827, 2048, 2048, 2048, 2048, 2048, 257], 512, 0, 0.0, 0.0, True),
+    "C5": ([2827, 2048, 2048, 2048, 257], 8192, 0, 0.0, 0.0, False),
+}
+
+
+def flops_per_frame(sizes, train):
+    P = sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))
+    return 2.0 * (3 * P - sizes[0] * sizes[1]) if train else 2.0 * P
+
+
+def n_params(sizes):
+    return sum((sizes[i] + 1) * sizes[i + 1] for i in range(len(sizes) - 1))
+
+
+def glorot(sizes, seed=3, beta=0.5):
+    rng = np.random.default_rng(seed)
+    L = len(sizes)
+    w, b = [None] * L, [None] * L
+    for i in range(1, L):
+        r = beta * np.sqrt(6.0) / np.sqrt(sizes[i - 1] + sizes[i])
+        w[i] = rng.uniform(-r, r, size=(sizes[i - 1], sizes[i])).astype(np.float32)
+        b[i] = np.zeros(sizes[i], dtype=np.float32)
+    return w, b
+
+
+def synth(n, k0, nout, seed, out_x=None, out_t=None):
+    rng = np.random.default_rng(seed)
+    x = out_x if out_x is not None else np.empty((n, k0), np.float32)
+    t = out_t if out_t is not None else np.empty((n, nout), np.float32)
+    rng.standard_normal((n, k0), dtype=np.float32, out=x)
+    rng.standard_normal((n, nout), dtype=np.float32, out=t)
+    t *= 0.5
+    return x, t
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop_flag, self.th = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_port_run(sizes, bunch, train, n_samples_bunches, dropout=(0, 0.0, 0.0)):
+    """Times the CPU restatement (oracle port) on all host cores: returns (frames/s, cores, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py as O
+    w, b = glorot(sizes)
+    x, t = synth(bunch * n_samples_bunches, sizes[0], sizes[-1], seed=1)
+    net = O.Net(sizes, bunch, lrate=1.0, momentum=0.9, dropoutflag=dropout[0], visible_omit=dropout[1],
+                hid_omit=dropout[2], weights=w, bias=b)
+    t0 = time.perf_counter()
+    if train:
+        net.train(x.shape[0], x, t)
+    else:
+        net.forward(x)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    what = f"{n_samples_bunches} bunch(es) of {bunch} frames, {'train step' if train else 'forward'}, oracle port (OpenMP)"
+    return x.shape[0] / dt, cores, what, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chunk-bunches", type=int, default=32, help="bunches resident per chunk (inputs > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU)", file=sys.stderr)
+        return 2
+    sizes, lb, dflag, vo, ho, train = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+    gb = lb * world
+    metric = "frames_per_sec"
+    cfg = {"workload": f"{args.workload}: {'-'.join(map(str, sizes))} {'train (fwd+bwd+SGD)' if train else 'forward decode'}",
+           "bunch_per_gpu": lb, "global_bunch": gb, "parallelism": f"dp{world}",
+           "dropout": [dflag, vo, ho], "l2_policy": "inputs larger than L2 (resident chunk cycles)",
+           "math": "tf32 tensor-core products (fp32 storage, fp32 accumulate)"}
+
+    # ------------------------------------------------------------------ reference arm: CPU restatement
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        nb = 1 if train else 1
+        best = None
+        for _ in range(max(1, min(K, 2))):
+            fps, cores, what, dt = cpu_port_run(sizes, lb if lb <= 1024 else 1024, train, nb, (dflag, vo, ho))
+            best = fps if best is None else max(best, fps)
+        line = {"impl": "reference", "metric": metric, "value": best, "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": K, "warmup": W, "ms_per_step": 1e3 * (lb if lb <= 1024 else 1024) / best,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg,
+                "cpu_baseline": {"value": best, "unit": "frames/s", "cores": cores, "kind": "port", "sample": what},
+                "e2e": {"value": best, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "the reference has no CPU implementation of this path (CUDA+cuBLAS only); this is the literal "
+                        "fp32 CPU restatement oracle/bp_oracle.c timed on the host cores"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w, b = glorot(sizes)
+    g = bp.BP_GPU(1, len(sizes), sizes, gb, 1.0, 0.9, 0.0, w, b, dflag, vo, ho, seed=12345, device=local_rank,
+                  world_size=world, rank=rank)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(bp.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        g.comm_init(bytes(idt.cpu().tolist()))
+
+    def barrier():
+        g.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cb = args.chunk_bunches
+    n_chunk = cb * lb
+    px, pt = bp.PinnedArray((n_chunk, sizes[0])), bp.PinnedArray((n_chunk, sizes[-1]))
+    synth(n_chunk, sizes[0], sizes[-1], seed=100 + rank, out_x=px.array, out_t=pt.array)
+    g.upload_chunk(n_chunk, px.array, pt.array)
+
+    def run_resident(n_steps):
+        done = 0
+        while done < n_steps:
+            k = min(cb, n_steps - done)
+            if train:
+                g.train_resident(0, k)
+            else:
+                g.forward_resident(0, k * lb)
+            done += k
+
+    # ---- value: device-resident
+    run_resident(W)
+    launches0 = g.counters()[0]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    g.timer_start()
+    run_resident(K)
+    ms = g.timer_stop()
+    barrier()
+    ms = max_over_ranks(ms)
+    launches = g.counters()[0] - launches0
+    value = K * gb / (ms * 1e-3)
+
+    # ---- roofline split: same loop with per-class CUDA events (ring of the last 64 bunches, no host sync per bunch)
+    prof = None
+    if train:
+        g.set_profiling(True)
+        run_resident(min(K, 64))
+        prof, nprof = g.profile()
+        g.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: bp_train() from pinned host buffers, one chunk of `e2e_cb` bunches per call, loss read back per step
+    e2e_cb = 8
+    e2e = None
+    if train:
+        n_calls = max(1, K // e2e_cb)
+        g.train(e2e_cb * lb, px.array[: e2e_cb * lb], pt.array[: e2e_cb * lb])  # warm-up call
+        import ctypes as C
+        lossbuf = (C.c_double * e2e_cb)()
+        nout = C.c_int(0)
+        lib = bp.load_library()
+        lib.bp_train_losses.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(n_calls):
+            o = (c % (cb // e2e_cb)) * e2e_cb * lb
+            g.train(e2e_cb * lb, px.array[o: o + e2e_cb * lb], pt.array[o: o + e2e_cb * lb])
+            lib.bp_train_losses(g.handle, lossbuf, e2e_cb, C.byref(nout))   # D2H of every step's loss (8 B/step)
+        g.sync()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        e2e = {"value": n_calls * e2e_cb * gb / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": 4 * lb * (sizes[0] + sizes[-1]) * world, "d2h_bytes_per_step": 8 * world,
+               "api": f"bp_train() on pinned host chunks of {e2e_cb} bunches + bp_train_losses()",
+               "last_loss": float(lossbuf[0]) / (lb * sizes[-1])}
+    else:
+        n_calls = max(1, K // 4)
+        out = None
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(n_calls):
+            out = g.forward(lb, px.array[:lb])
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        e2e = {"value": n_calls * gb / dt, "unit": "frames/s", "h2d_bytes_per_step": 4 * lb * sizes[0] * world,
+               "d2h_bytes_per_step": 4 * lb * sizes[-1] * world, "api": "bp_forward() host in / host out"}
+
+    if rank != 0:
+        g.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = load_peaks()
+    line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "impl": "ours"}
+    fl = flops_per_frame(sizes, train) * lb   # per rank per step
+    if prof is not None and nprof > 0:
+        gemm_ms = (prof["fwd"] + prof["dx"] + prof["dw"]) / nprof
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        ach = fl / (gemm_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm_kernel (fwd + dX + dW launches of one bunch)",
+                            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                            "traffic": None,
+                            "peak_source": f"{peak_src}: bf16_tflops_sustained/2 (kind::tf32 issues at half the bf16 rate)",
+                            "per_class_ms": {k: v / nprof for k, v in prof.items()}}
+        sgd_ms = prof["sgd"] / nprof
+        sgd_bytes = 20.0 * n_params(sizes)  # algorithmic minimum
+        line["roofline_sgd"] = {"bound": "hbm", "kernel": "bp_sgd_kernel", "achieved": sgd_bytes / (sgd_ms * 1e-3) / 1e9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": sgd_bytes / (sgd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                "peak_source": peak_src}
+    else:
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        ach = fl / (ms / K * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm_kernel (forward chain)", "achieved": ach,
+                            "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                            "peak_source": f"{peak_src}: bf16_tflops_sustained/2"}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            fps, cores, what, dt = cpu_port_run(sizes, min(lb, 1024), train, 1, (dflag, vo, ho))
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": what,
+                                    "seconds": dt}
+        except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+                                    "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def n_params_padded(sizes):
+    """Floats in the device parameter arena (row stride padded to 32, +1 bias row per layer) — what the SGD kernel
+    actually streams; the algorithmic minimum is 20 B x n_params(sizes)."""
+    tot = 0
+    for i in range(len(sizes) - 1):
+        ld = (sizes[i + 1] + 31) // 32 * 32
+        tot += ((sizes[i] + 1) * ld + 63) // 64 * 64
+    return tot
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -218,9 +218,11 @@ struct Rank {
   uint64_t launches = 0, bunches = 0;
   uint32_t step = 0;
   bool profiling = false;
-  cudaEvent_t pev[16] = {};
-  float prof_ms[6] = {0, 0, 0, 0, 0, 0};
-  uint64_t prof_n = 0;
+  static constexpr int kProfCap = 64;        // profiled bunches kept (ring)
+  std::vector<cudaEvent_t> pev;              // 6 events per profiled bunch, no host sync while recording
+  uint64_t prof_cnt = 0;
+  double* loss_dev = nullptr;                // per-bunch sum of squared output error of the last train call
+  int loss_cap = 0, loss_n = 0;
   SgdBiasRanges bias_ranges{};
 
   int Nout() const { return cfg.layersizes[L]; }
@@ -273,6 +275,7 @@ int rank_destroy(Rank* r) {
     if (e) cudaEventDestroy(e);
   for (auto e : r->pev)
     if (e) cudaEventDestroy(e);
+  cudaFree(r->loss_dev);
   for (auto s : {r->compute, r->copy, r->comm_stream})
     if (s) cudaStreamDestroy(s);
   delete r;
@@ -339,6 +342,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       CU_TRY(cudaEventCreateWithFlags(&c.uploaded, cudaEventDisableTiming));
       CU_TRY(cudaEventCreateWithFlags(&c.consumed, cudaEventDisableTiming));
     }
+    r->pev.assign(6 * Rank::kProfCap, nullptr);
     for (auto& e : r->pev) CU_TRY(cudaEventCreate(&e));
 
     long long off = 0;
@@ -431,6 +435,7 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
 // ------------------------------------------------------------------------------------------------ forward
 // Forward over rows [f0, f0+n) of the resident chunk.  train=true: masks + D_L; train=false: keep-scaling (CV).
 int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, long long ldo2, double* sqerr) {
+  // train: sqerr (if non-null) receives this bunch's sum (out - targ)^2 (training-loss monitor, our extension)
   const bp_config& cf = r->cfg;
   const bool drop = cf.dropoutflag == 1;
   const uint32_t seed_lo = (uint32_t)cf.seed, seed_hi = (uint32_t)(cf.seed >> 32);
@@ -477,6 +482,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
         p.aux = c.t + (long long)f0 * ls.N;
         p.ldaux = ls.N;
         p.gscale = 2.0f / (float)cf.bunchsize;  // (2.0f/rows), rows = GLOBAL bunch (DevFunc.cu:263)
+        p.sqerr = sqerr;
       } else {
         p.out = nullptr;
         p.out2 = out2;
@@ -495,14 +501,14 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
 }
 
 // ------------------------------------------------------------------------------------------------ one train bunch
-int train_bunch(Rank* r, ChunkBuf& c, int f0) {
+int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
   const int n = r->local_bunch;
   const bool prof = r->profiling;
-  int pe = 0;
+  int pe = 6 * (int)(r->prof_cnt % Rank::kProfCap);
   auto mark = [&]() { if (prof) cudaEventRecord(r->pev[pe++], r->compute); };
   mark();                                               // 0
-  BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, nullptr));
+  BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, loss_slot));
   mark();                                               // 1: fwd done
   float* xb = c.x + (long long)f0 * r->ldx;
   // dX chain first (it only needs W, which the deferred update has not touched yet) ...
@@ -569,17 +575,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0) {
   mark();                                               // 5: sgd done
   r->step++;
   r->bunches++;
-  if (prof) {
-    CU_TRY(cudaEventSynchronize(r->pev[5]));
-    float ms;
-    // fwd (incl. input dropout), dX, dW, sgd, allreduce wait
-    cudaEventElapsedTime(&ms, r->pev[0], r->pev[1]); r->prof_ms[0] += ms;
-    cudaEventElapsedTime(&ms, r->pev[1], r->pev[2]); r->prof_ms[1] += ms;
-    cudaEventElapsedTime(&ms, r->pev[2], r->pev[3]); r->prof_ms[2] += ms;
-    cudaEventElapsedTime(&ms, r->pev[4], r->pev[5]); r->prof_ms[3] += ms;
-    cudaEventElapsedTime(&ms, r->pev[3], r->pev[4]); r->prof_ms[4] += ms;
-    r->prof_n++;
-  }
+  if (prof) r->prof_cnt++;
   return BP_OK;
 }
 
@@ -590,7 +586,17 @@ int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   if (first_bunch < 0 || n_bunches < 0 || (long long)(first_bunch + n_bunches) * r->local_bunch > c.rows)
     return fail(BP_EINVAL, "train_resident: bunches [%d,%d) exceed resident rows %d (bunch %d)", first_bunch,
                 first_bunch + n_bunches, c.rows, r->local_bunch);
-  for (int b = 0; b < n_bunches; ++b) BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch));
+  if (n_bunches > r->loss_cap) {
+    CU_TRY(cudaStreamSynchronize(r->compute));
+    if (r->loss_dev) CU_TRY(cudaFree(r->loss_dev));
+    r->loss_dev = nullptr;
+    r->loss_cap = std::max(n_bunches, 256);
+    CU_TRY(cudaMalloc(&r->loss_dev, sizeof(double) * r->loss_cap));
+  }
+  if (n_bunches > 0) CU_TRY(cudaMemsetAsync(r->loss_dev, 0, sizeof(double) * n_bunches, r->compute));
+  r->loss_n = n_bunches;
+  for (int b = 0; b < n_bunches; ++b)
+    BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev + b));
   CU_TRY(cudaEventRecord(c.consumed, r->compute));
   c.consumed_valid = true;
   return BP_OK;
@@ -874,16 +880,46 @@ int bp_set_profiling(bp_handle* h, int on) {
   if (!h) return fail(BP_EINVAL, "null handle");
   for (Rank* r : h->ranks) {
     r->profiling = on != 0;
-    for (float& m : r->prof_ms) m = 0.0f;
-    r->prof_n = 0;
+    r->prof_cnt = 0;
   }
   return BP_OK;
 }
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled) {
   if (!h || !ms) return fail(BP_EINVAL, "null argument");
   Rank* r = h->ranks[0];
-  for (int i = 0; i < 6; ++i) ms[i] = r->prof_ms[i];
-  if (bunches_profiled) *bunches_profiled = r->prof_n;
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  for (int i = 0; i < 6; ++i) ms[i] = 0.0f;
+  const int nb = (int)std::min<uint64_t>(r->prof_cnt, Rank::kProfCap);
+  for (int b = 0; b < nb; ++b) {
+    cudaEvent_t* e = &r->pev[6 * b];
+    float t;
+    // marks: 0 start | 1 fwd done | 2 dX done | 3 dW issued | 4 all-reduce waited | 5 SGD done
+    CU_TRY(cudaEventElapsedTime(&t, e[0], e[1])); ms[0] += t;
+    CU_TRY(cudaEventElapsedTime(&t, e[1], e[2])); ms[1] += t;
+    CU_TRY(cudaEventElapsedTime(&t, e[2], e[3])); ms[2] += t;
+    CU_TRY(cudaEventElapsedTime(&t, e[4], e[5])); ms[3] += t;
+    CU_TRY(cudaEventElapsedTime(&t, e[3], e[4])); ms[4] += t;
+  }
+  if (bunches_profiled) *bunches_profiled = (uint64_t)nb;
+  r->prof_cnt = 0;
+  return BP_OK;
+}
+
+int bp_train_losses(bp_handle* h, double* out, int max_n, int* n_out) {
+  if (!h || !out || max_n < 0) return fail(BP_EINVAL, "bp_train_losses: bad argument");
+  int n = std::min(max_n, h->ranks[0]->loss_n);
+  for (int i = 0; i < n; ++i) out[i] = 0.0;
+  std::vector<double> tmp(n > 0 ? n : 1);
+  for (Rank* r : h->ranks) {
+    CU_TRY(cudaSetDevice(r->cfg.device));
+    if (n > 0) {
+      CU_TRY(cudaMemcpyAsync(tmp.data(), r->loss_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, r->compute));
+      CU_TRY(cudaStreamSynchronize(r->compute));
+      for (int i = 0; i < n; ++i) out[i] += tmp[i];
+    }
+  }
+  if (n_out) *n_out = n;
   return BP_OK;
 }
 

@@ -1,0 +1,105 @@
+// BPtrain — one training epoch + cross-validation per invocation, same command line, files and log lines as the
+// reference binary (reference BPtrain.cc:16-101), driving the B200 trainer through the C-ABI of include/bp_gpu.h.
+//
+//   BPtrain fea_file=... norm_file=... targ_file=... outwts_file=... log_file=... initwts_file=...
+//           train_sent_range=a-b cv_sent_range=c-d fea_dim=.. fea_context=.. targ_offset=.. traincache=.. bunchsize=..
+//           layersizes=a,b,.. lrate=.. momentum=.. weightcost=.. dropoutflag=.. visible_omit=.. hid_omit=..
+//           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=..]
+//
+// Success exit status is 1 and every error path is "log + exit(0)", as in the reference (BPtrain.cc:100; App. D Q10).
+// The Perl epoch driver (finetune_DNN_speech_enhancement_dropout_NAT.pl) works unmodified against this binary.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <vector>
+
+#include "../../include/bp_gpu.h"
+#include "Interface.h"
+
+static void die(Interface* io, const char* what) {
+  fprintf(io->fp_log, "%s: %s\n", what, bp_last_error());
+  fflush(io->fp_log);
+  printf("%s: %s\n", what, bp_last_error());
+  exit(0);
+}
+
+int main(int argc, char* argv[]) {
+  const double t_start = time(NULL);
+
+  Interface* io = new Interface;
+  io->host_alloc = bp_host_alloc;  // page-locked chunk buffers -> asynchronous H2D overlapping the next Readchunk
+  io->host_free = bp_host_free;
+  io->Initial(argc, argv);
+  WorkPara* para = io->para;
+
+  if (para->activation == 1) setenv("BP_ACTIVATION", "sigmoid", 1);
+  {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%llu", para->seed);
+    setenv("BP_SEED", buf, 1);
+  }
+  bp_handle* trainer = nullptr;
+  if (bp_create(&trainer, para->gpu_used, io->numlayers, para->layersizes, para->bunchsize, para->lrate,
+                para->momentum, para->weightcost, para->weights, para->bias, para->dropoutflag, para->visible_omit,
+                para->hid_omit) != BP_OK)
+    die(io, "GPU trainer creation failed");
+
+  io->get_pfile_info();
+
+  // ---- train (BPtrain.cc:36-54)
+  io->get_chunk_info(para->train_sent_range);
+  std::vector<int> chunk_index(io->total_chunks);
+  for (unsigned int i = 0; i < io->total_chunks; ++i) chunk_index[i] = i;
+  io->GetRandIndex(chunk_index.data(), io->total_chunks);
+  unsigned long long trained_samples = 0;
+  const double t_train0 = time(NULL);
+  for (unsigned int i = 0; i < io->total_chunks; ++i) {
+    const int n = io->Readchunk(chunk_index[i]);
+    fprintf(io->fp_log, "Starting chunk %d of %d containing %d samples.\n", i + 1, io->total_chunks, n);
+    fflush(io->fp_log);
+    if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) die(io, "train failed");
+    trained_samples += n;
+  }
+
+  printf("begin to write weights\n");
+  if (bp_return_weights(trainer, para->weights, para->bias) != BP_OK) die(io, "returnWeights failed");
+  io->Writeweights();
+  printf("finish to write weights\n\n");
+  const double t_train = time(NULL) - t_train0;
+
+  // ---- CV (BPtrain.cc:61-86)
+  printf("begin to CV\n");
+  fprintf(io->fp_log, "Starting CV.\n");
+  io->get_chunk_info_cv(para->cv_sent_range);
+  float squared_err = 0.0f;
+  FILE* fdec = para->decode_FN[0] ? fopen(para->decode_FN, "wb") : nullptr;
+  std::vector<float> dec;
+  for (unsigned int i = 0; i < io->cv_total_chunks; ++i) {
+    const int n = io->Readchunk_cv(i);
+    printf("cur_chunk_samples=%d\n", n);
+    if (n <= 0) continue;
+    float s = 0.0f;
+    if (bp_crossvalid(trainer, n, para->indata, para->targ, &s) != BP_OK) die(io, "CrossValid failed");
+    squared_err += s;
+    if (fdec) {  // decode extension: enhanced (normalised-domain) LPS frames, raw little-endian float32 rows
+      dec.resize(static_cast<size_t>(n) * para->layersizes[io->numlayers - 1]);
+      if (bp_forward(trainer, n, para->indata, dec.data()) != BP_OK) die(io, "forward failed");
+      fwrite(dec.data(), sizeof(float), dec.size(), fdec);
+    }
+  }
+  if (fdec) fclose(fdec);
+  const float cvacc = squared_err / io->cv_total_samples;
+  fprintf(io->fp_log, "CV over. squared error: %f\n", cvacc);
+  fflush(io->fp_log);
+
+  const double t_total = time(NULL) - t_start;
+  fprintf(io->fp_log, "Total cost time: %.1f s.\n", t_total);
+  if (t_train > 0)  // added line: throughput of the training pass, reader included
+    fprintf(io->fp_log, "Training throughput: %.0f frames/sec.\n", trained_samples / t_train);
+
+  printf("all finish!\n");
+  bp_destroy(trainer);
+  delete io;
+  return 1;
+}

@@ -1,0 +1,122 @@
+// Host-side data / IO surface of BPtrain, re-written from scratch for the B200 build.
+//
+// Mirrors the reference's class `Interface` + struct `WorkPara` (reference Interface.h:8-101) member for member so
+// that main() reads like the reference's (BPtrain.cc:16-101): Initial, get_pfile_info, get_chunk_info(_cv),
+// Readchunk(_cv), GetRandIndex, Writeweights, and the public fields para / fp_log / total_chunks / ...
+// File formats (Pfile, norm file, MAT-v4 .wts), argv keys, RNG call order (srand48 -> weight init -> chunk shuffle ->
+// per-chunk sample shuffle) and log lines follow the reference; the implementation does not.
+//
+// Extensions (all optional, defaults = reference behaviour):
+//   nat=0|1        noise-aware-training block on/off (default: inferred from layersizes[0], HEAD hard-wires it on and
+//                  hard-codes fea_dim 129 — Interface.cc:395,777-778; here the block is fea_dim wide, identical at 129)
+//   activation=relu|sigmoid   (HEAD = relu, a source edit in the reference: DevFunc.cu:67-97)
+//   seed=<u64>     dropout seed (reference: time(NULL), BP_GPU.cu:77-78);  decode_file=<path> enhanced CV frames
+#pragma once
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#define MAXLAYER 10
+#define MAXLINE 1024
+#define MAXCHUNK 102400
+
+struct WorkPara {
+  char fea_FN[MAXLINE] = "";
+  char fea_normFN[MAXLINE] = "";
+  int fea_dim = 0;
+  int fea_context = 0;
+
+  char targ_FN[MAXLINE] = "";
+  int targ_offset = 0;
+  int dropoutflag = 0;
+  int traincache = 0;  // samples per chunk held in host memory
+  int bunchsize = 0;
+  int layersizes[MAXLAYER] = {0};
+  float momentum = 0.0f;
+  float weightcost = 0.0f;
+  float lrate = 0.0f;
+  float visible_omit = 0.0f;
+  float hid_omit = 0.0f;
+
+  char init_weightFN[MAXLINE] = "";
+  char out_weightFN[MAXLINE] = "";
+  char log_FN[MAXLINE] = "";
+
+  char train_sent_range[MAXLINE] = "";
+  char cv_sent_range[MAXLINE] = "";
+
+  int gpu_used = 1;
+  int init_randem_seed = 0;
+  float init_randem_weight_min = -0.1f;  // reference defaults, Interface.cc:79-82
+  float init_randem_weight_max = 0.1f;
+  float init_randem_bias_max = 0.1f;
+  float init_randem_bias_min = -0.1f;
+
+  float* indata = nullptr;               // traincache x layersizes[0]   (pinned when a GPU is present)
+  float* targ = nullptr;                 // traincache x layersizes[last]
+  float* weights[MAXLAYER - 1] = {nullptr};  // index 1..numlayers-1, w[in*n_out + out]
+  float* bias[MAXLAYER - 1] = {nullptr};
+
+  // extensions
+  int nat = -1;            // -1 = infer from layersizes[0]
+  int activation = 0;      // 0 relu, 1 sigmoid
+  unsigned long long seed = 0x5eed5eedULL;
+  char decode_FN[MAXLINE] = "";
+};
+
+class Interface {
+ public:
+  Interface();
+  ~Interface();
+
+  void Initial(int argc, char** argv);
+  void Writeweights();
+  void get_pfile_info();
+  void get_chunk_info(char* range);
+  void get_chunk_info_cv(char* range);
+  int Readchunk(int index);
+  int Readchunk_cv(int index);
+  void GetRandIndex(int* vec, int len);
+
+  WorkPara* para;
+
+  unsigned int total_frames = 0;
+  unsigned int total_sents = 0;
+  unsigned int total_chunks = 0;
+  unsigned int total_samples = 0;
+  unsigned int cv_total_chunks = 0;
+  unsigned int cv_total_samples = 0;
+
+  int* framesBeforeSent = nullptr;  // end-exclusive frame index of each sentence
+  int* chunk_frame_st = nullptr;
+  int* cv_chunk_frame_st = nullptr;
+
+  FILE* fp_log = nullptr;
+  int numlayers = 0;
+  int realbunchsize = 0;
+
+  // Set by main() when the trainer hands out page-locked chunk buffers (bp_host_alloc); freed with `host_free`.
+  void* (*host_alloc)(size_t) = nullptr;
+  void (*host_free)(void*) = nullptr;
+
+ private:
+  struct Range {
+    int st = 0, en = 0;
+  };
+  void fatal(const char* fmt, ...);
+  Range parse_range(const char* range, const char* what);
+  void plan_chunks(const Range& r, int* starts, unsigned int* n_chunks, unsigned int* n_samples);
+  int assemble(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,
+               bool shuffle);
+  void read_records(FILE* fp, int dim, long first_frame, int n_frames, std::vector<float>* rec, int* first_sent);
+  void get_uint(const char* hdr, const char* argname, unsigned int* val);
+  void read_tail(FILE* fp, long file_offset, unsigned int sentnum, int* out);
+  void GetRandWeight(float* vec, float lo, float hi, int len);
+
+  FILE* fp_data = nullptr;
+  FILE* fp_targ = nullptr;
+  FILE* fp_out = nullptr;
+  std::vector<float> mean, dVar;
+  Range train_r, cv_r;
+  bool use_nat = true;
+};

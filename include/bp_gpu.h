@@ -110,9 +110,13 @@ int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bun
 
 /* Per-kernel device time of the most recent bunch when profiling is on (CUDA events around each launch class):
  * ms[0] = forward GEMMs, ms[1] = dX GEMMs, ms[2] = dW GEMMs, ms[3] = SGD update, ms[4] = all-reduce wait,
- * ms[5] = input dropout.  Enabling it serialises nothing but adds event records. */
+ * ms[5] = reserved.  Sums over the last <= 64 profiled bunches; records events only, no host sync per bunch. */
 int bp_set_profiling(bp_handle* h, int on);
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled);
+
+/* Training-loss monitor (our extension): sum over this handle's rows and output dims of (out - targ)^2 for each bunch
+ * of the most recent bp_train / bp_train_resident call, accumulated in the output-layer epilogue.  Synchronises. */
+int bp_train_losses(bp_handle* h, double* out, int max_n, int* n_out);
 
 /* Data-parallel communicator (NCCL over NVLink): rank 0 obtains an id, every rank passes the same 128 bytes. */
 int bp_comm_unique_id(char id128[128]);
