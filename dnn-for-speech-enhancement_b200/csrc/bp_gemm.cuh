@@ -14,6 +14,13 @@
 //     dW  : M = units of layer l      N = fan-in (+1)     K = frames      A = dEdX^T (MN)     B = Yprev^T (MN)
 // Output element (row m, col n) is stored at out[n * ldo + m].
 //
+// L2 traffic: with 128x128 tiles every CTA streams 32 KB per 32-deep k-block, i.e. 32 flop/B, and 128+ CTAs doing
+// that exceed the L2->SM fabric (~10 TB/s measured) at a third of the TF32 tensor peak.  Thread-block clusters of
+// CM x CN CTAs therefore share operand tiles by TMA multicast: the CN CTAs of a cluster row (same m-tile) split the A
+// tile's 4-KB chunks between them and multicast each chunk to the whole row, likewise the CM CTAs of a column for B.
+// A CTA's smem slot is written by its peers, so the slot's "empty" barrier counts one tcgen05.commit arrival from
+// every CTA of its row and column (commit multicast), and a producer waits for all of them before re-filling.
+//
 // Pipeline: warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one elected lane) + TMEM owner,
 // warps 2..5 = epilogue (tcgen05.ld -> registers -> fused math -> coalesced global stores).  kStages-deep smem ring
 // (full/empty mbarriers), double-buffered TMEM accumulator (tfull/tempty mbarriers), persistent static tile loop.
@@ -71,7 +78,7 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
   return ((1.0f - y) * y) * e;
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N, int kStages>
+template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N, int kStages, int CM, int CN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
@@ -81,8 +88,10 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t CHUNK_BYTES = 32 * BLOCK_K * 4;  // one MN-major 32-wide column chunk: BLOCK_K rows x 128 B
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  constexpr int CSIZE = CM * CN;
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(TMEM_COLS <= 512, "TMEM");
+  static_assert(CSIZE >= 1 && CSIZE <= 8 && (BLOCK_M / 32) % CN == 0 && (BLOCK_N / 32) % CM == 0, "cluster shape");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -96,17 +105,28 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  // Tiles are scheduled per cluster: cluster-tile ct covers m-tiles [mc*CM, mc*CM+CM) x n-tiles [nc*CN, nc*CN+CN);
+  // CTA rank r of the cluster owns (rm, rn) = (r % CM, r / CM) of it.  Tiles past the edge are phantoms: they load
+  // (TMA zero-fills), multiply and skip their stores, so every CTA of a cluster runs the same barrier protocol.
+  const int num_mc = ((p.M + BLOCK_M - 1) / BLOCK_M + CM - 1) / CM;
+  const int num_nc = ((p.N + BLOCK_N - 1) / BLOCK_N + CN - 1) / CN;
+  const int num_ctiles = num_mc * num_nc;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int crank = CSIZE > 1 ? (int)cluster_ctarank() : 0;
+  const int rm = crank % CM, rn = crank / CM;
+  const int cid = blockIdx.x / CSIZE, num_clusters = gridDim.x / CSIZE;
+  uint16_t mask_row = 0, mask_col = 0;  // CTAs sharing my A tile (same rm) / my B tile (same rn)
+#pragma unroll
+  for (int j = 0; j < CN; ++j) mask_row |= uint16_t(1u << (rm + CM * j));
+#pragma unroll
+  for (int i = 0; i < CM; ++i) mask_col |= uint16_t(1u << (rn * CM + i));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CM + CN - 1);  // one commit arrival from every CTA of my row and column
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -121,6 +141,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CSIZE > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -129,26 +150,30 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % num_m_tiles) * BLOCK_M;
-        const int n0 = (t / num_m_tiles) * BLOCK_N;
+      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
+        const int m0 = ((ct % num_mc) * CM + rm) * BLOCK_M;
+        const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
+          mbar_expect_tx(&full[s], STAGE_BYTES);  // my A + my B, whoever delivers the chunks
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = kb * BLOCK_K;
-          if constexpr (!kAMN) {
-            tma_load_2d(sa, &tmA, &full[s], k0, m0);
-          } else {
+          // Every operand tile is 32-wide chunks of 4 KB (K-major: 32 rows x 128 B; MN-major: 32 k-rows x 128 B).
+          // Chunk c of my A tile is fetched by the row CTA with rn == c % CN and multicast to the row; same for B.
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * CHUNK_BYTES, &tmA, &full[s], m0 + 32 * j, k0);
+          for (int c = 0; c < BLOCK_M / 32; ++c) {
+            if (c % CN != rn) continue;
+            const int ci = kAMN ? m0 + 32 * c : k0, co = kAMN ? k0 : m0 + 32 * c;
+            if constexpr (CN > 1) tma_load_2d_mc(sa + c * CHUNK_BYTES, &tmA, &full[s], ci, co, mask_row);
+            else tma_load_2d(sa + c * CHUNK_BYTES, &tmA, &full[s], ci, co);
           }
-          if constexpr (!kBMN) {
-            tma_load_2d(sb, &tmB, &full[s], k0, n0);
-          } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, &full[s], n0 + 32 * j, k0);
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            if (c % CM != rm) continue;
+            const int ci = kBMN ? n0 + 32 * c : k0, co = kBMN ? k0 : n0 + 32 * c;
+            if constexpr (CM > 1) tma_load_2d_mc(sb + c * CHUNK_BYTES, &tmB, &full[s], ci, co, mask_col);
+            else tma_load_2d(sb + c * CHUNK_BYTES, &tmB, &full[s], ci, co);
           }
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
@@ -163,7 +188,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * BLOCK_N);
@@ -186,7 +211,9 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
             umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          // release slot s in every CTA that fills it for me or that I fill (my row and column)
+          if constexpr (CSIZE > 1) umma_commit_mc(&empty[s], uint16_t(mask_row | mask_col));
+          else umma_commit(&empty[s]);
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tfull[as]);
@@ -201,9 +228,9 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     float sq_local = 0.0f;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % num_m_tiles) * BLOCK_M;
-      const int n0 = (t / num_m_tiles) * BLOCK_N;
+    for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
+      const int m0 = ((ct % num_mc) * CM + rm) * BLOCK_M;
+      const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -297,6 +324,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CSIZE > 1) cluster_sync_all();  // nobody leaves while peers may still signal / multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

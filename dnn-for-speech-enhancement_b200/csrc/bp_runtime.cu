@@ -78,7 +78,8 @@ int get_encode() {
 }
 
 // 2-D fp32 tensor {inner (contiguous), outer (stride ld floats)}; box {32, box_outer}; OOB -> 0.
-// mn_major = false: operand whose reduction dim is contiguous (K-major)  -> SWIZZLE_128B, box {32 k, rows}.
+// Every tile is fetched as 4-KB chunks: box {32, 32} (so that cluster CTAs can split a shared tile between them).
+// mn_major = false: operand whose reduction dim is contiguous (K-major)  -> SWIZZLE_128B, box {32 k, 32 rows}.
 // mn_major = true : operand whose M/N dim is contiguous (MN-major)       -> SWIZZLE_128B_ATOM_32B, box {32 mn, 32 k}
 //                   (tcgen05 accepts only the 32-B-atom swizzle for MN-major 32-bit operands).
 int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
@@ -105,25 +106,81 @@ int make_map(CUtensorMap* m, const float* base, long long inner, long long outer
 constexpr int kBlockN = 128;
 constexpr int kStages = 6;
 
-template <bool kAMN, bool kBMN, int kEpi>
-int launch_gemm(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
-  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, kBlockN, kStages>;
+// Cluster shape (CM x CN CTAs sharing operand tiles by TMA multicast).  Default 2x2; BP_CLUSTER=1x1|2x1|1x2|2x2|4x1|1x4
+// overrides it for experiments.
+struct ClusterShape { int cm, cn; };
+ClusterShape cluster_shape() {
+  static ClusterShape cs = [] {
+    ClusterShape c{2, 2};
+    if (const char* e = getenv("BP_CLUSTER")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 4) c = ClusterShape{a, b};
+    }
+    return c;
+  }();
+  return cs;
+}
+
+template <bool kAMN, bool kBMN, int kEpi, int CM, int CN>
+int launch_gemm_c(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, kBlockN, kStages, CM, CN>;
   constexpr size_t smem = gemm_smem_bytes<kBlockN, kStages>();
+  constexpr int C = CM * CN;
   static thread_local int configured_dev = -1;
+  static thread_local int max_clusters = 0;
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   if (configured_dev != dev) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_clusters = num_sms / C;
+    if (C > 1) {
+      cudaLaunchConfig_t qc{};
+      qc.gridDim = dim3(num_sms / C * C);
+      qc.blockDim = dim3(GEMM_THREADS);
+      qc.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = C;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) max_clusters = n;
+      else cudaGetLastError();
+    }
     configured_dev = dev;
   }
-  const int mt = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-  const int nt = (p.N + kBlockN - 1) / kBlockN;
-  const int tiles = mt * nt;
-  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  const int grid = std::min(tiles, num_sms);
-  kern<<<grid, GEMM_THREADS, smem, st>>>(a, b, p);
-  CU_TRY(cudaGetLastError());
+  const int mt = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M + CM - 1) / CM;
+  const int nt = ((p.N + kBlockN - 1) / kBlockN + CN - 1) / CN;
+  const int ctiles = mt * nt;
+  if (ctiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(std::min(ctiles, max_clusters) * C);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a, b, p));
   return BP_OK;
+}
+
+template <bool kAMN, bool kBMN, int kEpi>
+int launch_gemm(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+  const ClusterShape cs = cluster_shape();
+  if (cs.cm == 1 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 1>(st, num_sms, a, b, p);
+  if (cs.cm == 2 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 2, 1>(st, num_sms, a, b, p);
+  if (cs.cm == 1 && cs.cn == 2) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 2>(st, num_sms, a, b, p);
+  if (cs.cm == 2 && cs.cn == 2) return launch_gemm_c<kAMN, kBMN, kEpi, 2, 2>(st, num_sms, a, b, p);
+  if (cs.cm == 4 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 4, 1>(st, num_sms, a, b, p);
+  if (cs.cm == 1 && cs.cn == 4) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 4>(st, num_sms, a, b, p);
+  return fail(BP_EINVAL, "unsupported cluster shape %dx%d", cs.cm, cs.cn);
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (lazy dlopen)
@@ -388,12 +445,12 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       LayerState& ls = r->layer[l];
       const float* wl = r->w + ls.off;
       BP_TRY(make_map(&ls.w_fwd, wl, ls.N, ls.K, ls.ldN, 32, true));
-      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
-      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
+      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, 32, false));
+      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, 32, false));
       BP_TRY(make_map(&ls.d_dw, ls.d, ls.N, r->local_bunch, ls.ldd, 32, true));
       if (l >= 2) {
         LayerState& lp = r->layer[l - 1];
-        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, kBlockN, false));
+        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, 32, false));
         BP_TRY(make_map(&ls.yprev_dw, lp.y, ls.K + 1, r->local_bunch, lp.ldy, 32, true));
       }
     }
@@ -467,7 +524,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     CUtensorMap xmap;
     const CUtensorMap* bmap = &ls.yprev_fwd;
     if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, kBlockN, false));
+      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, 32, false));
       bmap = &xmap;
     }
     if (l < r->L) {
@@ -992,8 +1049,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       CU_TRY(cudaMemcpy2D(dAux, dldaux * 4, aux, size_t(ldaux) * 4, size_t(M) * 4, N, cudaMemcpyHostToDevice));
     }
     CUtensorMap ma, mb;
-    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, amn ? 32 : GEMM_BLOCK_M, amn));
-    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, bmn ? 32 : kBlockN, bmn));
+    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, 32, amn));
+    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, 32, bmn));
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.out = dO; p.ldo = dldo;

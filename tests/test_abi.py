@@ -1,0 +1,66 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol include/bp_gpu.h
+declares, fails loudly (no CPU fallback) when asked to compute, and its host-side mask function equals the oracle's."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(bp):
+    if not os.path.exists(bp.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "dnn-for-speech-enhancement_b200", "csrc"), "-s"])
+    lib = bp.load_library()
+    names = bp.declared_symbols()
+    assert {"bp_create", "bp_create_ex", "bp_train", "bp_crossvalid", "bp_forward", "bp_return_weights",
+            "bp_destroy", "bp_last_error", "bp_upload_chunk", "bp_train_resident", "bp_comm_init"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bp_gpu.h but not exported"
+
+
+def test_built_for_sm100a_with_tcgen05_and_tma(bp):
+    """The shipped cubin is sm_100a and contains the Blackwell tensor / TMA / TMEM instructions (SASS names)."""
+    lib = bp.LIB_PATH
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    sass = out.stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "SYNCS"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+
+
+def test_no_cpu_fallback(bp):
+    """Without a GPU the product must refuse, not compute on the host."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except Exception:
+        pass
+    w = [None, np.zeros((4, 3), np.float32)]
+    b = [None, np.zeros(3, np.float32)]
+    with pytest.raises(bp.BpError) as e:
+        bp.BP_GPU(1, 2, [4, 3], 8, 1.0, 0.0, 0.0, w, b, device=0)
+    assert "no CUDA device" in str(e.value) or "rc=-2" in str(e.value) or "rc=-3" in str(e.value)
+
+
+def test_bad_arguments_are_rejected(bp):
+    lib = bp.load_library()
+    h = C.c_void_p()
+    assert lib.bp_create_ex(C.byref(h), None, None, None) != 0
+    assert b"null" in lib.bp_last_error()
+    assert lib.bp_train(None, 1, None, None) != 0
+    assert lib.bp_debug_gemm(9, 1, 1, 1, None, 1, None, 1, None, 1, None, None, 1, 1.0, 0, 0, None) != 0
+
+
+def test_dropout_mask_host_function_matches_oracle(bp, oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        seed = int(rng.integers(0, 2**63))
+        step, layer, f, u = (int(v) for v in rng.integers(0, 5000, size=4))
+        p = float(rng.uniform(0, 1))
+        assert bp.dropout_mask(seed, step, layer, f, u, p) == oracle.dropout_mask(seed, step, layer, f, u, p)
