@@ -265,24 +265,22 @@ def main():
     if train:
         n_calls = max(1, K // e2e_cb)
         g.train(e2e_cb * lb, px.array[: e2e_cb * lb], pt.array[: e2e_cb * lb])  # warm-up call
-        import ctypes as C
-        lossbuf = (C.c_double * e2e_cb)()
-        nout = C.c_int(0)
-        lib = bp.load_library()
-        lib.bp_train_losses.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
         barrier()
         t0 = time.perf_counter()
+        losses = None
         for c in range(n_calls):
             o = (c % (cb // e2e_cb)) * e2e_cb * lb
             g.train(e2e_cb * lb, px.array[o: o + e2e_cb * lb], pt.array[o: o + e2e_cb * lb])
-            lib.bp_train_losses(g.handle, lossbuf, e2e_cb, C.byref(nout))   # D2H of every step's loss (8 B/step)
+            if c > 0:
+                losses = g.train_losses(age=1, max_n=e2e_cb)   # D2H of every step's loss (8 B/step), one call behind
+        losses = g.train_losses(age=0, max_n=e2e_cb)
         g.sync()
         dt = time.perf_counter() - t0
         dt = max_over_ranks(dt)
         e2e = {"value": n_calls * e2e_cb * gb / dt, "unit": "frames/s",
                "h2d_bytes_per_step": 4 * lb * (sizes[0] + sizes[-1]) * world, "d2h_bytes_per_step": 8 * world,
                "api": f"bp_train() on pinned host chunks of {e2e_cb} bunches + bp_train_losses()",
-               "last_loss": float(lossbuf[0]) / (lb * sizes[-1])}
+               "last_loss": float(losses[0]) / (lb * sizes[-1])}
     else:
         n_calls = max(1, K // 4)
         out = None

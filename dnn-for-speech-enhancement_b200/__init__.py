@@ -75,7 +75,7 @@ def load_library() -> C.CDLL:
     lib.bp_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bp_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.bp_get_profile.argtypes = [C.c_void_p, C.c_float * 6, C.POINTER(C.c_uint64)]
-    lib.bp_train_losses.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+    lib.bp_train_losses.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
     lib.bp_comm_unique_id.argtypes = [C.c_char * 128]
     lib.bp_comm_init.argtypes = [C.c_void_p, C.c_char * 128]
     lib.bp_dropout_mask.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
@@ -269,11 +269,11 @@ class BP_GPU:
         names = ["fwd", "dx", "dw", "sgd", "allreduce_wait", "input_dropout"]
         return {k: float(v) for k, v in zip(names, ms)}, int(n.value)
 
-    def train_losses(self, max_n: int = 4096) -> np.ndarray:
-        """Per-bunch sum of squared output error of the most recent train call (training-loss monitor)."""
+    def train_losses(self, age: int = 0, max_n: int = 4096) -> np.ndarray:
+        """Per-bunch sum of squared output error of the most recent (age 0) / previous (age 1) train call."""
         buf = (C.c_double * max_n)()
         n = C.c_int(0)
-        _check(load_library().bp_train_losses(self._h, buf, max_n, C.byref(n)), "bp_train_losses")
+        _check(load_library().bp_train_losses(self._h, int(age), buf, max_n, C.byref(n)), "bp_train_losses")
         return np.array(buf[: n.value], dtype=np.float64)
 
     def comm_init(self, id128: bytes) -> None:

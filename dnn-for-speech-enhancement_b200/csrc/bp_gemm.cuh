@@ -57,6 +57,7 @@ struct GemmParams {
   uint32_t seed_lo, seed_hi, step, layer;
   int frame0;             // global frame index of column n=0 (data-parallel shard offset), multiple of 4
   uint32_t dbg_mn_lbo, dbg_mn_sbo;  // bring-up overrides for the MN-major descriptor strides (0 = default)
+  uint32_t dbg_flags;               // bit 0: skip the MMAs (TMA-only pipeline), bit 1: skip the TMA loads (MMA-only)
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -130,7 +131,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -155,6 +156,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
+          if (p.dbg_flags & 2u) {  // measurement aid: no loads, the stage is "full" at once
+            mbar_arrive(&full[s]);
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(&full[s], STAGE_BYTES);  // my A + my B, whoever delivers the chunks
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -199,6 +205,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = sa + A_BYTES;
           const uint32_t mn_lbo = p.dbg_mn_lbo ? p.dbg_mn_lbo : CHUNK_BYTES;
           const uint32_t mn_sbo = p.dbg_mn_sbo ? p.dbg_mn_sbo : 512u;
+          if ((p.dbg_flags & 1u) && CSIZE == 1) {  // measurement aid: consume the stage without multiplying
+            mbar_arrive(&empty[s]);
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 8; ++k) {
             // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); one k-step = 8 fp32 = 32 B
@@ -231,7 +242,10 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
       const int m0 = ((ct % num_mc) * CM + rm) * BLOCK_M;
       const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
-      mbar_wait(&tfull[as], aph);
+      // One lane per warp polls (128 threads hammering try_wait on one mbarrier saturate the SM's barrier unit and
+      // slow the producer/MMA hand-offs on the critical path — measured: ~450 ns per k-block regardless of work).
+      if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
+      __syncwarp();
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool m_ok = m < p.M;
@@ -308,7 +322,8 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }

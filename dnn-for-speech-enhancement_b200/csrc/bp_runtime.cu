@@ -278,8 +278,12 @@ struct Rank {
   static constexpr int kProfCap = 64;        // profiled bunches kept (ring)
   std::vector<cudaEvent_t> pev;              // 6 events per profiled bunch, no host sync while recording
   uint64_t prof_cnt = 0;
-  double* loss_dev = nullptr;                // per-bunch sum of squared output error of the last train call
-  int loss_cap = 0, loss_n = 0;
+  // per-bunch sum of squared output error of the two most recent train calls (ring), so that a caller can read
+  // call i-1's losses while call i computes (no compute-stream sync on the reading path)
+  double* loss_dev[2] = {nullptr, nullptr};
+  int loss_cap[2] = {0, 0}, loss_n[2] = {0, 0};
+  cudaEvent_t loss_done[2] = {nullptr, nullptr};
+  int loss_cur = 0;
   SgdBiasRanges bias_ranges{};
 
   int Nout() const { return cfg.layersizes[L]; }
@@ -332,7 +336,10 @@ int rank_destroy(Rank* r) {
     if (e) cudaEventDestroy(e);
   for (auto e : r->pev)
     if (e) cudaEventDestroy(e);
-  cudaFree(r->loss_dev);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(r->loss_dev[i]);
+    if (r->loss_done[i]) cudaEventDestroy(r->loss_done[i]);
+  }
   for (auto s : {r->compute, r->copy, r->comm_stream})
     if (s) cudaStreamDestroy(s);
   delete r;
@@ -399,6 +406,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       CU_TRY(cudaEventCreateWithFlags(&c.uploaded, cudaEventDisableTiming));
       CU_TRY(cudaEventCreateWithFlags(&c.consumed, cudaEventDisableTiming));
     }
+    for (auto& e : r->loss_done) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     r->pev.assign(6 * Rank::kProfCap, nullptr);
     for (auto& e : r->pev) CU_TRY(cudaEventCreate(&e));
 
@@ -643,17 +651,21 @@ int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   if (first_bunch < 0 || n_bunches < 0 || (long long)(first_bunch + n_bunches) * r->local_bunch > c.rows)
     return fail(BP_EINVAL, "train_resident: bunches [%d,%d) exceed resident rows %d (bunch %d)", first_bunch,
                 first_bunch + n_bunches, c.rows, r->local_bunch);
-  if (n_bunches > r->loss_cap) {
+  const int li = r->loss_cur ^ 1;
+  if (n_bunches > r->loss_cap[li]) {
     CU_TRY(cudaStreamSynchronize(r->compute));
-    if (r->loss_dev) CU_TRY(cudaFree(r->loss_dev));
-    r->loss_dev = nullptr;
-    r->loss_cap = std::max(n_bunches, 256);
-    CU_TRY(cudaMalloc(&r->loss_dev, sizeof(double) * r->loss_cap));
+    CU_TRY(cudaStreamSynchronize(r->copy));
+    if (r->loss_dev[li]) CU_TRY(cudaFree(r->loss_dev[li]));
+    r->loss_dev[li] = nullptr;
+    r->loss_cap[li] = std::max(n_bunches, 256);
+    CU_TRY(cudaMalloc(&r->loss_dev[li], sizeof(double) * r->loss_cap[li]));
   }
-  if (n_bunches > 0) CU_TRY(cudaMemsetAsync(r->loss_dev, 0, sizeof(double) * n_bunches, r->compute));
-  r->loss_n = n_bunches;
+  if (n_bunches > 0) CU_TRY(cudaMemsetAsync(r->loss_dev[li], 0, sizeof(double) * n_bunches, r->compute));
+  r->loss_n[li] = n_bunches;
+  r->loss_cur = li;
   for (int b = 0; b < n_bunches; ++b)
-    BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev + b));
+    BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev[li] + b));
+  CU_TRY(cudaEventRecord(r->loss_done[li], r->compute));
   CU_TRY(cudaEventRecord(c.consumed, r->compute));
   c.consumed_valid = true;
   return BP_OK;
@@ -963,16 +975,20 @@ int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled) {
   return BP_OK;
 }
 
-int bp_train_losses(bp_handle* h, double* out, int max_n, int* n_out) {
-  if (!h || !out || max_n < 0) return fail(BP_EINVAL, "bp_train_losses: bad argument");
-  int n = std::min(max_n, h->ranks[0]->loss_n);
+int bp_train_losses(bp_handle* h, int age, double* out, int max_n, int* n_out) {
+  if (!h || !out || max_n < 0 || age < 0 || age > 1) return fail(BP_EINVAL, "bp_train_losses: bad argument");
+  const int li0 = h->ranks[0]->loss_cur ^ age;
+  int n = std::min(max_n, h->ranks[0]->loss_n[li0]);
   for (int i = 0; i < n; ++i) out[i] = 0.0;
   std::vector<double> tmp(n > 0 ? n : 1);
   for (Rank* r : h->ranks) {
     CU_TRY(cudaSetDevice(r->cfg.device));
+    const int li = r->loss_cur ^ age;
     if (n > 0) {
-      CU_TRY(cudaMemcpyAsync(tmp.data(), r->loss_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, r->compute));
-      CU_TRY(cudaStreamSynchronize(r->compute));
+      // wait only for the call that produced these losses, not for whatever was queued after it
+      CU_TRY(cudaStreamWaitEvent(r->copy, r->loss_done[li], 0));
+      CU_TRY(cudaMemcpyAsync(tmp.data(), r->loss_dev[li], sizeof(double) * n, cudaMemcpyDeviceToHost, r->copy));
+      CU_TRY(cudaStreamSynchronize(r->copy));
       for (int i = 0; i < n; ++i) out[i] += tmp[i];
     }
   }
@@ -1060,22 +1076,26 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     p.act = act < 0 ? 0 : act;
     if (const char* e = getenv("BP_DBG_MN_LBO")) p.dbg_mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("BP_DBG_MN_SBO")) p.dbg_mn_sbo = (uint32_t)atoi(e);
+    if (const char* e = getenv("BP_DBG_FLAGS")) p.dbg_flags = (uint32_t)atoi(e);
+    int reps = 1;
+    if (const char* e = getenv("BP_DBG_REPS")) reps = std::max(1, atoi(e));
     const int sms = prop.multiProcessorCount;
-    CU_TRY(cudaEventRecord(e0, st));
-    if (kind == 0) {
-      if (!bias) return fail(BP_EINVAL, "kind 0 needs bias");
-      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p)));
-    } else if (kind == 3) {
-      BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p)));
-    } else if (kind == 1) {
-      if (!aux) return fail(BP_EINVAL, "kind 1 needs aux (Y)");
-      BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p)));
-    } else {
-      BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p)));
+    if (kind == 0 && !bias) return fail(BP_EINVAL, "kind 0 needs bias");
+    if (kind == 1 && !aux) return fail(BP_EINVAL, "kind 1 needs aux (Y)");
+    for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is an untimed warm-up when reps > 1
+      if (rep == (reps > 1 ? 1 : 0)) CU_TRY(cudaEventRecord(e0, st));
+      if (reps == 1 && rep == 1) break;
+      if (kind == 0) BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p)));
+      else if (kind == 3) BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p)));
+      else if (kind == 1) BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p)));
+      else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p)));
     }
     CU_TRY(cudaEventRecord(e1, st));
     CU_TRY(cudaStreamSynchronize(st));
-    if (elapsed_ms) CU_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    if (elapsed_ms) {
+      CU_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+      *elapsed_ms /= (float)reps;
+    }
     CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
     return BP_OK;
   }();

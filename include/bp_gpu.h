@@ -115,8 +115,9 @@ int bp_set_profiling(bp_handle* h, int on);
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled);
 
 /* Training-loss monitor (our extension): sum over this handle's rows and output dims of (out - targ)^2 for each bunch
- * of the most recent bp_train / bp_train_resident call, accumulated in the output-layer epilogue.  Synchronises. */
-int bp_train_losses(bp_handle* h, double* out, int max_n, int* n_out);
+ * of the most recent (age 0) or the previous (age 1) bp_train / bp_train_resident call, accumulated in the
+ * output-layer epilogue.  Waits only for that call to finish, so reading age 1 overlaps the current call's compute. */
+int bp_train_losses(bp_handle* h, int age, double* out, int max_n, int* n_out);
 
 /* Data-parallel communicator (NCCL over NVLink): rank 0 obtains an id, every rank passes the same 128 bytes. */
 int bp_comm_unique_id(char id128[128]);

@@ -1,0 +1,59 @@
+"""GPU end-to-end drop-in test: our `BPtrain` CLI against the reference's own `BPtrain` (oracle/_ref/BPtrain_ref,
+compiled from /root/reference by oracle/build_ref.sh) on identical synthetic Pfile / norm inputs and identical
+command lines, at the reference's own operating shape (129-dim LPS, 11-frame context + NAT block = 1548 inputs)."""
+import importlib
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "dnn-for-speech-enhancement_b200", "bin", "BPtrain")
+REF = os.path.join(ROOT, "oracle", "_ref", "BPtrain_ref")
+LS = [1548, 256, 192, 129]
+
+
+def _args(d, tag, extra=()):
+    return [f"fea_file={d}/fea.pfile", f"norm_file={d}/fea.norm", f"targ_file={d}/targ.pfile",
+            f"outwts_file={d}/{tag}.wts", f"log_file={d}/{tag}.log", "initwts_file=", "train_sent_range=0-29",
+            "cv_sent_range=30-39", "fea_dim=129", "fea_context=11", "targ_offset=5", "traincache=3000",
+            "bunchsize=64", "layersizes=" + ",".join(map(str, LS)), "numlayers=4", "gpu_used=1",
+            "init_randem_seed=7", "momentum=0.5", "weightcost=0", "lrate=1", "dropoutflag=0", "visible_omit=0",
+            "hid_omit=0", "init_randem_weight_min=-0.05", "init_randem_weight_max=0.05",
+            "init_randem_bias_min=-0.05", "init_randem_bias_max=0.05"] + list(extra)
+
+
+def _cv(path):
+    m = re.search(r"CV over\. squared error: ([-0-9.eE+naninf]+)", open(path).read())
+    assert m, open(path).read()[-500:]
+    return float(m.group(1))
+
+
+@pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists(REF)), reason="BPtrain / BPtrain_ref not built")
+def test_bptrain_cli_matches_reference_binary():
+    T = importlib.import_module("dnn-for-speech-enhancement_b200.tools.pfile")
+    with tempfile.TemporaryDirectory() as d:
+        feas, targs, mu, ivar = T.synth_corpus(40, 129, 129, seed=1, min_len=40, max_len=120)
+        T.write_pfile(f"{d}/fea.pfile", feas)
+        T.write_pfile(f"{d}/targ.pfile", targs)
+        T.write_norm(f"{d}/fea.norm", mu, ivar)
+        r = subprocess.run([REF] + _args(d, "ref"), cwd=d, capture_output=True, text=True, timeout=600)
+        assert os.path.exists(f"{d}/ref.wts") and os.path.getsize(f"{d}/ref.wts") > 0, r.stdout + r.stderr
+        o = subprocess.run([OURS] + _args(d, "ours"), cwd=d, capture_output=True, text=True, timeout=600)
+        assert o.returncode == 1, o.stdout + o.stderr          # success exit status is 1 (BPtrain.cc:100)
+        rw, rb = T.read_wts(f"{d}/ref.wts", LS)
+        ow, ob = T.read_wts(f"{d}/ours.wts", LS)
+        cv_ref, cv_ours = _cv(f"{d}/ref.log"), _cv(f"{d}/ours.log")
+        log = open(f"{d}/ours.log").read()
+    for line in ("parameters input:", "Get pfile info over:", "Get chunk info over:", "Starting chunk 1 of",
+                 "Saving weights to file...", "Starting CV.", "Total cost time:"):
+        assert line in log
+    fro = lambda a: float(np.linalg.norm(np.asarray(a, np.float64).ravel()))
+    for l in range(1, len(LS)):
+        assert fro(ow[l] - rw[l]) <= 1e-2 * fro(rw[l]), f"W{l}: {fro(ow[l] - rw[l]) / fro(rw[l]):.3e}"
+        assert fro(ob[l] - rb[l]) <= 2e-2 * fro(rb[l]) + 1e-6, f"b{l}"
+    assert abs(cv_ours - cv_ref) <= 1e-2 * abs(cv_ref), (cv_ours, cv_ref)

