@@ -14,16 +14,23 @@
 //     dW  : M = units of layer l      N = fan-in (+1)     K = frames      A = dEdX^T (MN)     B = Yprev^T (MN)
 // Output element (row m, col n) is stored at out[n * ldo + m].
 //
-// L2 traffic: with 128x128 tiles every CTA streams 32 KB per 32-deep k-block, i.e. 32 flop/B, and 128+ CTAs doing
-// that exceed the L2->SM fabric (~10 TB/s measured) at a third of the TF32 tensor peak.  Thread-block clusters of
-// CM x CN CTAs therefore share operand tiles by TMA multicast: the CN CTAs of a cluster row (same m-tile) split the A
-// tile's 4-KB chunks between them and multicast each chunk to the whole row, likewise the CM CTAs of a column for B.
-// A CTA's smem slot is written by its peers, so the slot's "empty" barrier counts one tcgen05.commit arrival from
-// every CTA of its row and column (commit multicast), and a producer waits for all of them before re-filling.
+// Operand fetch.  Every operand is a row-major fp32 matrix [R x ld] with ld % 32 == 0, viewed by ONE 3-D tensor map
+// {32 floats, R rows (stride ld), ld/32 chunks (stride 128 B)}:
+//   K-major  (reduction dim contiguous): rows = M/N index, chunks = k/32.   box {32, 128|BLOCK_N rows, 2 chunks}
+//            -> smem [k-chunk][row][128 B], SWIZZLE_128B;            UMMA desc: SBO 1024, k-step 8 = +32 B in the row.
+//   MN-major (M/N dim contiguous):       rows = k index,   chunks = mn/32.  box {32, 64 k-rows, 4|BLOCK_N/32 chunks}
+//            -> smem [mn-chunk][k-row][128 B], SWIZZLE_128B_ATOM_32B; UMMA desc layout 1: LBO = 8192 (chunk), SBO 512
+//               (4-row swizzle group), k-step 8 = +1024 B.  (tcgen05 accepts no other layout for MN-major 32-bit.)
+// so a 64-deep k-block of a tile is ONE cp.async.bulk.tensor.3d per operand (32-64 KB).  Out-of-range reduction
+// indices are zero-filled by TMA on at least one operand of every product (rows are exact extents; pad columns up
+// to ld are kept zero); out-of-range M/N indices only reach accumulator rows/columns that are never stored.
 //
-// Pipeline: warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one elected lane) + TMEM owner,
-// warps 2..5 = epilogue (tcgen05.ld -> registers -> fused math -> coalesced global stores).  kStages-deep smem ring
-// (full/empty mbarriers), double-buffered TMEM accumulator (tfull/tempty mbarriers), persistent static tile loop.
+// Pipeline (all role loops are WARP-UNIFORM, the asynchronous instructions are issued under elect.sync — issuing
+// them from a divergent `if (lane == 0)` costs ~100 cycles per tcgen05.mma / TMA because every operand is first moved
+// from vector to uniform registers; measured with the clock64 trace below): warp 0 = TMA producer, warp 1 =
+// tcgen05.mma issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> registers -> fused math -> coalesced global
+// stores).  kStages-deep smem ring of 64-deep k-blocks (full/empty mbarriers), double-buffered TMEM accumulator
+// (tfull/tempty mbarriers), persistent static tile loop, every wait bounded (a protocol bug traps, never hangs).
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -56,17 +63,22 @@ struct GemmParams {
   float drop_p;           // >0: zero y where u < drop_p (kernDropout DevFunc.cu:34-45), no rescale
   uint32_t seed_lo, seed_hi, step, layer;
   int frame0;             // global frame index of column n=0 (data-parallel shard offset), multiple of 4
-  uint32_t dbg_mn_lbo, dbg_mn_sbo;  // bring-up overrides for the MN-major descriptor strides (0 = default)
-  uint32_t dbg_flags;               // bit 0: skip the MMAs (TMA-only pipeline), bit 1: skip the TMA loads (MMA-only)
+  uint32_t dbg_flags;     // measurement aids: bit 0 skip the MMAs (TMA-only), bit 1 skip the loads (MMA-only)
+  long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
+                          // [256..511] loads issued, [512..767] stage full seen, [768..1023] MMAs issued,
+                          // [1024] accumulator ready seen by epilogue, [1025] epilogue done, [1026] CTA start
 };
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 32;  // 32 fp32 = one 128-byte swizzle span
+constexpr int GEMM_BLOCK_K = 64;   // two 32-float (128-byte) swizzle spans per stage
 constexpr int GEMM_THREADS = 192;
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N>
+__host__ __device__ constexpr int gemm_stages() { return BLOCK_N == 128 ? 3 : 2; }
+
+template <int BLOCK_N>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(kStages) * (GEMM_BLOCK_M * GEMM_BLOCK_K * 4 + BLOCK_N * GEMM_BLOCK_K * 4) + 1024 /*align slack*/ +
+  return size_t(gemm_stages<BLOCK_N>()) * (GEMM_BLOCK_M + BLOCK_N) * GEMM_BLOCK_K * 4 + 1024 /*align slack*/ +
          256 /*barriers*/;
 }
 
@@ -79,24 +91,31 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
   return ((1.0f - y) * y) * e;
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N, int kStages, int CM, int CN>
+template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
+  constexpr int kStages = gemm_stages<BLOCK_N>();
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 4;
   constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 4;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t CHUNK_BYTES = 32 * BLOCK_K * 4;  // one MN-major 32-wide column chunk: BLOCK_K rows x 128 B
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
-  constexpr int CSIZE = CM * CN;
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(TMEM_COLS <= 512, "TMEM");
-  static_assert(CSIZE >= 1 && CSIZE <= 8 && (BLOCK_M / 32) % CN == 0 && (BLOCK_N / 32) % CM == 0, "cluster shape");
+  // UMMA shared-memory descriptors: constant high word, low word = start address >> 4 | LBO field.
+  //   hi: [0,14) SBO>>4, [14,16) version 1, [29,32) layout;  lo: [0,14) addr>>4, [16,30) LBO>>4
+  constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
+  constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (kLayoutSW128Base32 << 29);
+  constexpr uint32_t kDescLoK = (16u >> 4) << 16;
+  constexpr uint32_t kDescLoMN = ((uint32_t(BLOCK_K) * 128u) >> 4) << 16;  // LBO = one mn-chunk = BLOCK_K rows x 128 B
+  constexpr uint32_t kAsub = BLOCK_M * 128;  // K-major: bytes between the two 32-wide k-chunks of a stage
+  constexpr uint32_t kBsub = BLOCK_N * 128;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;          // shared-space address of stage 0
+  uint8_t* smem = smem_raw + (smem_base - raw_addr);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * STAGE_BYTES);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
@@ -105,29 +124,20 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool tracing = p.dbg_trace != nullptr && blockIdx.x == 0;
+  if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
 
-  // Tiles are scheduled per cluster: cluster-tile ct covers m-tiles [mc*CM, mc*CM+CM) x n-tiles [nc*CN, nc*CN+CN);
-  // CTA rank r of the cluster owns (rm, rn) = (r % CM, r / CM) of it.  Tiles past the edge are phantoms: they load
-  // (TMA zero-fills), multiply and skip their stores, so every CTA of a cluster runs the same barrier protocol.
-  const int num_mc = ((p.M + BLOCK_M - 1) / BLOCK_M + CM - 1) / CM;
-  const int num_nc = ((p.N + BLOCK_N - 1) / BLOCK_N + CN - 1) / CN;
-  const int num_ctiles = num_mc * num_nc;
+  const int num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int crank = CSIZE > 1 ? (int)cluster_ctarank() : 0;
-  const int rm = crank % CM, rn = crank / CM;
-  const int cid = blockIdx.x / CSIZE, num_clusters = gridDim.x / CSIZE;
-  uint16_t mask_row = 0, mask_col = 0;  // CTAs sharing my A tile (same rm) / my B tile (same rn)
-#pragma unroll
-  for (int j = 0; j < CN; ++j) mask_row |= uint16_t(1u << (rm + CM * j));
-#pragma unroll
-  for (int i = 0; i < CM; ++i) mask_col |= uint16_t(1u << (rn * CM + i));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CM + CN - 1);  // one commit arrival from every CTA of my row and column
+      mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -142,110 +152,90 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CSIZE > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
-        const int m0 = ((ct % num_mc) * CM + rm) * BLOCK_M;
-        const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1u);
-          if (p.dbg_flags & 2u) {  // measurement aid: no loads, the stage is "full" at once
-            mbar_arrive(&full[s]);
-            if (++s == kStages) { s = 0; ph ^= 1u; }
-            continue;
-          }
-          mbar_expect_tx(&full[s], STAGE_BYTES);  // my A + my B, whoever delivers the chunks
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % num_m_tiles) * BLOCK_M;
+      const int n0 = (t / num_m_tiles) * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1u);
+        if (elect_one()) {
+          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[kb] = clock64();
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const int k0 = kb * BLOCK_K;
-          // Every operand tile is 32-wide chunks of 4 KB (K-major: 32 rows x 128 B; MN-major: 32 k-rows x 128 B).
-          // Chunk c of my A tile is fetched by the row CTA with rn == c % CN and multicast to the row; same for B.
-#pragma unroll
-          for (int c = 0; c < BLOCK_M / 32; ++c) {
-            if (c % CN != rn) continue;
-            const int ci = kAMN ? m0 + 32 * c : k0, co = kAMN ? k0 : m0 + 32 * c;
-            if constexpr (CN > 1) tma_load_2d_mc(sa + c * CHUNK_BYTES, &tmA, &full[s], ci, co, mask_row);
-            else tma_load_2d(sa + c * CHUNK_BYTES, &tmA, &full[s], ci, co);
+          if (p.dbg_flags & 2u) {  // measurement aid: no loads, the stage is "full" at once
+            mbar_arrive(&full[s]);
+          } else {
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            if constexpr (kAMN) tma_load_3d(sa, &tmA, &full[s], 0, kb * BLOCK_K, m0 / 32);
+            else tma_load_3d(sa, &tmA, &full[s], 0, m0, kb * (BLOCK_K / 32));
+            if constexpr (kBMN) tma_load_3d(sb, &tmB, &full[s], 0, kb * BLOCK_K, n0 / 32);
+            else tma_load_3d(sb, &tmB, &full[s], 0, n0, kb * (BLOCK_K / 32));
           }
-#pragma unroll
-          for (int c = 0; c < BLOCK_N / 32; ++c) {
-            if (c % CM != rm) continue;
-            const int ci = kBMN ? n0 + 32 * c : k0, co = kBMN ? k0 : n0 + 32 * c;
-            if constexpr (CM > 1) tma_load_2d_mc(sb + c * CHUNK_BYTES, &tmB, &full[s], ci, co, mask_col);
-            else tma_load_2d(sb + c * CHUNK_BYTES, &tmB, &full[s], ci, co);
-          }
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[256 + kb] = clock64();
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
-        mbar_wait(&tempty[as], aph ^ 1u);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(as * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(as * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          const uint32_t mn_lbo = p.dbg_mn_lbo ? p.dbg_mn_lbo : CHUNK_BYTES;
-          const uint32_t mn_sbo = p.dbg_mn_sbo ? p.dbg_mn_sbo : 512u;
-          if ((p.dbg_flags & 1u) && CSIZE == 1) {  // measurement aid: consume the stage without multiplying
+        const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        if (elect_one()) {
+          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[512 + kb] = clock64();
+          if (p.dbg_flags & 1u) {  // measurement aid: consume the stage without multiplying
             mbar_arrive(&empty[s]);
-            if (++s == kStages) { s = 0; ph ^= 1u; }
-            continue;
-          }
+          } else {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 8; ++k) {
-            // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); one k-step = 8 fp32 = 32 B
-            //   inside the swizzled row.
-            // MN-major (SWIZZLE_128B_BASE32B): 32-wide column chunks CHUNK_BYTES apart (LBO); k-rows of 128 B,
-            //   4-row swizzle groups 512 B apart (SBO); one k-step = 8 k-rows = 1024 B.
-            const uint64_t adesc = kAMN ? make_smem_desc(sa + k * 1024, mn_lbo, mn_sbo, kLayoutSW128Base32)
-                                        : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
-            const uint64_t bdesc = kBMN ? make_smem_desc(sb + k * 1024, mn_lbo, mn_sbo, kLayoutSW128Base32)
-                                        : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 8; ++k) {
+              const uint32_t a_off = kAMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kAsub + uint32_t(k % 4) * 32u;
+              const uint32_t b_off = kBMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kBsub + uint32_t(k % 4) * 32u;
+              const uint32_t alo = (kAMN ? kDescLoMN : kDescLoK) | ((sa + a_off) >> 4);
+              const uint32_t blo = (kBMN ? kDescLoMN : kDescLoK) | ((sb + b_off) >> 4);
+              umma_tf32_lohi(d_tmem, alo, kAMN ? kDescHiMN : kDescHiK, blo, kBMN ? kDescHiMN : kDescHiK, idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);  // slot s is free again once these MMAs have read it
           }
-          // release slot s in every CTA that fills it for me or that I fill (my row and column)
-          if constexpr (CSIZE > 1) umma_commit_mc(&empty[s], uint16_t(mask_row | mask_col));
-          else umma_commit(&empty[s]);
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[768 + kb] = clock64();
         }
-        umma_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aph ^= 1u;
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
     int as = 0;
     uint32_t aph = 0;
     float sq_local = 0.0f;
-    for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
-      const int m0 = ((ct % num_mc) * CM + rm) * BLOCK_M;
-      const int n0 = ((ct / num_mc) * CN + rn) * BLOCK_N;
-      // One lane per warp polls (128 threads hammering try_wait on one mbarrier saturate the SM's barrier unit and
-      // slow the producer/MMA hand-offs on the critical path — measured: ~450 ns per k-block regardless of work).
-      if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % num_m_tiles) * BLOCK_M;
+      const int n0 = (t / num_m_tiles) * BLOCK_N;
+      if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
+      if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool m_ok = m < p.M;
@@ -258,6 +248,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int nc = n0 + c * 32;
         if (nc >= p.N) break;
+        const bool whole = nc + 32 <= p.N;  // warp-uniform: all 32 columns of the chunk are real
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c * 32), v);
         tmem_ld_wait();
@@ -265,8 +256,8 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (m_ok) {
             float* o = p.out + size_t(nc) * p.ldo + m;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) o[size_t(j) * p.ldo] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j, o += p.ldo)
+              if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
           }
         } else if constexpr (kEpi == EPI_FWD_HID) {
           if (m_ok) {
@@ -279,11 +270,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 philox_uniform4(p.seed_lo, p.seed_hi, uint32_t(p.frame0 + nc + j4 * 4) >> 2, uint32_t(m), p.layer,
                                 p.step, u4);
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
+              for (int jj = 0; jj < 4; ++jj, o += p.ldo) {
                 const int j = j4 * 4 + jj;
                 float y = act_fwd(fmaf(p.scale, __uint_as_float(v[j]), bias), p.act);
                 if (drop && u4[jj] < p.drop_p) y = 0.0f;
-                if (nc + j < p.N) o[size_t(j) * p.ldo] = y;
+                if (whole || nc + j < p.N) *o = y;
               }
             }
           }
@@ -293,11 +284,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.aux != nullptr) {
               const float* a = p.aux + size_t(nc) * p.ldaux + m;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) tg[j] = (nc + j < p.N) ? __ldg(a + size_t(j) * p.ldaux) : 0.0f;
+              for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (nc + j < p.N) {
+              if (whole || nc + j < p.N) {
                 const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
                 if (p.out2 != nullptr) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
                 if (p.aux != nullptr) {
@@ -313,16 +304,17 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float yv[32];
             const float* a = p.aux + size_t(nc) * p.ldaux + m;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) yv[j] = (nc + j < p.N) ? __ldg(a + size_t(j) * p.ldaux) : 0.0f;
+            for (int j = 0; j < 32; ++j, a += p.ldaux) yv[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
             float* o = p.out + size_t(nc) * p.ldo + m;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) o[size_t(j) * p.ldo] = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
+            for (int j = 0; j < 32; ++j, o += p.ldo)
+              if (whole || nc + j < p.N) *o = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1025] = clock64();
       if (lane == 0) mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aph ^= 1u;
@@ -339,7 +331,6 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CSIZE > 1) cluster_sync_all();  // nobody leaves while peers may still signal / multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -27,6 +27,7 @@
 #include "../../include/bp_gpu.h"
 #include "bp_elementwise.cuh"
 #include "bp_gemm.cuh"
+#include "bp_microbench.cuh"
 
 namespace {
 
@@ -77,110 +78,62 @@ int get_encode() {
   return BP_OK;
 }
 
-// 2-D fp32 tensor {inner (contiguous), outer (stride ld floats)}; box {32, box_outer}; OOB -> 0.
-// Every tile is fetched as 4-KB chunks: box {32, 32} (so that cluster CTAs can split a shared tile between them).
-// mn_major = false: operand whose reduction dim is contiguous (K-major)  -> SWIZZLE_128B, box {32 k, 32 rows}.
-// mn_major = true : operand whose M/N dim is contiguous (MN-major)       -> SWIZZLE_128B_ATOM_32B, box {32 mn, 32 k}
-//                   (tcgen05 accepts only the 32-B-atom swizzle for MN-major 32-bit operands).
-int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
-             bool mn_major) {
+// 3-D view {32 floats, rows (stride ld floats), ld/32 chunks (stride 128 B)} of a row-major fp32 matrix [rows x ld]
+// (see the "Operand fetch" paragraph of bp_gemm.cuh).  OOB rows / chunks are zero-filled.
+//   K-major operand  (reduction dim contiguous): rows = exact M/N extent, chunks = ceil(K/32); box {32, box_rows, 2};
+//                    SWIZZLE_128B.
+//   MN-major operand (M/N dim contiguous):       rows = exact K extent,   chunks = ceil(MN/32); box {32, 64, box_mn/32};
+//                    SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands).
+int make_map(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
+             int box_outer, bool mn_major) {
   BP_TRY(get_encode());
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0)
-    return fail(BP_EINVAL, "tensor map: base/stride not 16-byte aligned (ld=%lld)", ld);
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_outer)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 31) != 0)
+    return fail(BP_EINVAL, "tensor map: base not 16-byte aligned or ld %% 32 != 0 (ld=%lld)", ld);
+  const long long chunks = (contiguous_extent + 31) / 32;
+  if (chunks * 32 > ld) return fail(BP_EINVAL, "tensor map: extent %lld exceeds ld %lld", contiguous_extent, ld);
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(chunks)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? GEMM_BLOCK_K : box_outer),
+                       static_cast<cuuint32_t>(mn_major ? box_outer / 32 : GEMM_BLOCK_K / 32)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(BP_ECUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%d", (int)r, inner,
-                outer, ld, box_outer);
+    return fail(BP_ECUDA, "cuTensorMapEncodeTiled failed (%d) extent=%lld rows=%lld ld=%lld box=%d mn=%d", (int)r,
+                contiguous_extent, rows, ld, box_outer, (int)mn_major);
   return BP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
-constexpr int kBlockN = 128;
-constexpr int kStages = 6;
-
-// Cluster shape (CM x CN CTAs sharing operand tiles by TMA multicast).  Default 2x2; BP_CLUSTER=1x1|2x1|1x2|2x2|4x1|1x4
-// overrides it for experiments.
-struct ClusterShape { int cm, cn; };
-ClusterShape cluster_shape() {
-  static ClusterShape cs = [] {
-    ClusterShape c{2, 2};
-    if (const char* e = getenv("BP_CLUSTER")) {
-      int a = 0, b = 0;
-      if (sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 4) c = ClusterShape{a, b};
-    }
-    return c;
-  }();
-  return cs;
-}
-
-template <bool kAMN, bool kBMN, int kEpi, int CM, int CN>
-int launch_gemm_c(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
-  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, kBlockN, kStages, CM, CN>;
-  constexpr size_t smem = gemm_smem_bytes<kBlockN, kStages>();
-  constexpr int C = CM * CN;
+template <bool kAMN, bool kBMN, int kEpi, int BN>
+int launch_gemm_bn(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, BN>;
+  constexpr size_t smem = gemm_smem_bytes<BN>();
   static thread_local int configured_dev = -1;
-  static thread_local int max_clusters = 0;
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   if (configured_dev != dev) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_clusters = num_sms / C;
-    if (C > 1) {
-      cudaLaunchConfig_t qc{};
-      qc.gridDim = dim3(num_sms / C * C);
-      qc.blockDim = dim3(GEMM_THREADS);
-      qc.dynamicSmemBytes = smem;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = C;
-      qa[0].val.clusterDim.y = 1;
-      qa[0].val.clusterDim.z = 1;
-      qc.attrs = qa;
-      qc.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) max_clusters = n;
-      else cudaGetLastError();
-    }
     configured_dev = dev;
   }
-  const int mt = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M + CM - 1) / CM;
-  const int nt = ((p.N + kBlockN - 1) / kBlockN + CN - 1) / CN;
-  const int ctiles = mt * nt;
-  if (ctiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(std::min(ctiles, max_clusters) * C);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a, b, p));
+  const int mt = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int nt = (p.N + BN - 1) / BN;
+  const int tiles = mt * nt;
+  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  const int grid = std::min(tiles, num_sms);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(a, b, p);
+  CU_TRY(cudaGetLastError());
   return BP_OK;
 }
 
+// Tile width along N.  The B-operand tensor map's box must match (kBoxN below is what make_map is called with).
+constexpr int kBlockN = 128;
+
 template <bool kAMN, bool kBMN, int kEpi>
 int launch_gemm(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
-  const ClusterShape cs = cluster_shape();
-  if (cs.cm == 1 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 1>(st, num_sms, a, b, p);
-  if (cs.cm == 2 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 2, 1>(st, num_sms, a, b, p);
-  if (cs.cm == 1 && cs.cn == 2) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 2>(st, num_sms, a, b, p);
-  if (cs.cm == 2 && cs.cn == 2) return launch_gemm_c<kAMN, kBMN, kEpi, 2, 2>(st, num_sms, a, b, p);
-  if (cs.cm == 4 && cs.cn == 1) return launch_gemm_c<kAMN, kBMN, kEpi, 4, 1>(st, num_sms, a, b, p);
-  if (cs.cm == 1 && cs.cn == 4) return launch_gemm_c<kAMN, kBMN, kEpi, 1, 4>(st, num_sms, a, b, p);
-  return fail(BP_EINVAL, "unsupported cluster shape %dx%d", cs.cm, cs.cn);
+  return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (lazy dlopen)
@@ -261,7 +214,9 @@ struct Rank {
   int local_bunch = 0;
   int num_sms = 0;
   cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr;
+  cudaStream_t side = nullptr;  // weight-gradient GEMMs run here, concurrently with the dX chain on `compute`
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
   float *w = nullptr, *dw = nullptr, *g = nullptr;
   long long arena_floats = 0;
   LayerState layer[BP_MAXLAYER];
@@ -332,7 +287,9 @@ int rank_destroy(Rank* r) {
   cudaFree(r->g);
   cudaFree(r->out_dev);
   cudaFree(r->sqerr_dev);
-  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm})
+  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side})
+    if (e) cudaEventDestroy(e);
+  for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
   for (auto e : r->pev)
     if (e) cudaEventDestroy(e);
@@ -340,7 +297,7 @@ int rank_destroy(Rank* r) {
     cudaFree(r->loss_dev[i]);
     if (r->loss_done[i]) cudaEventDestroy(r->loss_done[i]);
   }
-  for (auto s : {r->compute, r->copy, r->comm_stream})
+  for (auto s : {r->compute, r->copy, r->comm_stream, r->side})
     if (s) cudaStreamDestroy(s);
   delete r;
   return BP_OK;
@@ -398,6 +355,9 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_side, cudaEventDisableTiming));
+    for (auto& e : r->ev_d) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&r->ev_t0));
     CU_TRY(cudaEventCreate(&r->ev_t1));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_grad, cudaEventDisableTiming));
@@ -452,14 +412,14 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     for (int l = 1; l <= r->L; ++l) {
       LayerState& ls = r->layer[l];
       const float* wl = r->w + ls.off;
-      BP_TRY(make_map(&ls.w_fwd, wl, ls.N, ls.K, ls.ldN, 32, true));
-      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, 32, false));
-      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, 32, false));
-      BP_TRY(make_map(&ls.d_dw, ls.d, ls.N, r->local_bunch, ls.ldd, 32, true));
+      BP_TRY(make_map(&ls.w_fwd, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, true));
+      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
+      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
+      BP_TRY(make_map(&ls.d_dw, ls.d, ls.N, r->local_bunch, ls.ldd, GEMM_BLOCK_M, true));
       if (l >= 2) {
         LayerState& lp = r->layer[l - 1];
-        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, 32, false));
-        BP_TRY(make_map(&ls.yprev_dw, lp.y, ls.K + 1, r->local_bunch, lp.ldy, 32, true));
+        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, kBlockN, false));
+        BP_TRY(make_map(&ls.yprev_dw, lp.y, ls.K + 1, r->local_bunch, lp.ldy, kBlockN, true));
       }
     }
     BP_TRY(upload_params(r, weights, bias));
@@ -532,7 +492,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     CUtensorMap xmap;
     const CUtensorMap* bmap = &ls.yprev_fwd;
     if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, 32, false));
+      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, kBlockN, false));
       bmap = &xmap;
     }
     if (l < r->L) {
@@ -576,7 +536,37 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, loss_slot));
   mark();                                               // 1: fwd done
   float* xb = c.x + (long long)f0 * r->ldx;
-  // dX chain first (it only needs W, which the deferred update has not touched yet) ...
+  // The weight(+bias)-gradient GEMM of layer l needs only dE/dX_l and Y_{l-1}; the dX chain needs only W (the deferred
+  // update has not touched it yet).  So dW_l is launched on the side stream as soon as dE/dX_l exists and runs
+  // concurrently with the rest of the dX chain, filling the SMs a 128-tile GEMM leaves idle on a 148-SM part.
+  // Last layer first, so its all-reduce starts earliest.
+  auto launch_dw = [&](int l) -> int {
+    LayerState& ls = r->layer[l];
+    CU_TRY(cudaStreamWaitEvent(r->side, r->ev_d[l], 0));
+    GemmParams p{};
+    p.M = ls.N;
+    p.N = ls.K + 1;  // + the all-ones column -> row K of the gradient block = bias gradient
+    p.K = n;
+    p.out = r->g + ls.off;
+    p.ldo = ls.ldN;
+    CUtensorMap xmap;
+    const CUtensorMap* bmap = &ls.yprev_dw;
+    if (l == 1) {
+      BP_TRY(make_map(&xmap, xb, ls.K + 1, n, r->ldx, kBlockN, true));
+      bmap = &xmap;
+    }
+    BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
+    r->launches++;
+    if (r->nccl_comm) {
+      CU_TRY(cudaEventRecord(r->ev_grad, r->side));
+      CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_grad, 0));
+      NCCL_TRY(g_nccl.AllReduce(r->g + ls.off, r->g + ls.off, (size_t)ls.size, kNcclFloat32, kNcclSum, r->nccl_comm,
+                                r->comm_stream));
+    }
+    return BP_OK;
+  };
+  CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
+  BP_TRY(launch_dw(r->L));
   for (int l = r->L; l >= 2; --l) {
     LayerState& ls = r->layer[l];
     LayerState& lp = r->layer[l - 1];
@@ -591,33 +581,13 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.act = cf.activation;
     BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->num_sms, ls.w_dx, ls.d_dx, p)));
     r->launches++;
+    CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
+    BP_TRY(launch_dw(l - 1));
   }
-  mark();                                               // 2: dX done
-  // ... then the weight (+bias) gradients, last layer first so its all-reduce starts earliest.
-  for (int l = r->L; l >= 1; --l) {
-    LayerState& ls = r->layer[l];
-    GemmParams p{};
-    p.M = ls.N;
-    p.N = ls.K + 1;  // + the all-ones column -> row K of the gradient block = bias gradient
-    p.K = n;
-    p.out = r->g + ls.off;
-    p.ldo = ls.ldN;
-    CUtensorMap xmap;
-    const CUtensorMap* bmap = &ls.yprev_dw;
-    if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, ls.K + 1, n, r->ldx, 32, true));
-      bmap = &xmap;
-    }
-    BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->compute, r->num_sms, ls.d_dw, *bmap, p)));
-    r->launches++;
-    if (r->nccl_comm) {
-      CU_TRY(cudaEventRecord(r->ev_grad, r->compute));
-      CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_grad, 0));
-      NCCL_TRY(g_nccl.AllReduce(r->g + ls.off, r->g + ls.off, (size_t)ls.size, kNcclFloat32, kNcclSum, r->nccl_comm,
-                                r->comm_stream));
-    }
-  }
-  mark();                                               // 3: dW done
+  mark();                                               // 2: dX chain issued/done on `compute`
+  CU_TRY(cudaEventRecord(r->ev_side, r->side));
+  CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_side, 0));
+  mark();                                               // 3: all dW done
   if (r->nccl_comm) {
     CU_TRY(cudaEventRecord(r->ev_comm, r->comm_stream));
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
@@ -902,6 +872,7 @@ int bp_sync(bp_handle* h) {
     CU_TRY(cudaSetDevice(r->cfg.device));
     CU_TRY(cudaStreamSynchronize(r->copy));
     CU_TRY(cudaStreamSynchronize(r->comm_stream));
+    CU_TRY(cudaStreamSynchronize(r->side));
     CU_TRY(cudaStreamSynchronize(r->compute));
     return BP_OK;
   });
@@ -1065,8 +1036,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       CU_TRY(cudaMemcpy2D(dAux, dldaux * 4, aux, size_t(ldaux) * 4, size_t(M) * 4, N, cudaMemcpyHostToDevice));
     }
     CUtensorMap ma, mb;
-    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, 32, amn));
-    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, 32, bmn));
+    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, GEMM_BLOCK_M, amn));
+    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, kBlockN, bmn));
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.out = dO; p.ldo = dldo;
@@ -1074,9 +1045,13 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     p.aux = dAux; p.ldaux = dldaux;
     p.scale = scale;
     p.act = act < 0 ? 0 : act;
-    if (const char* e = getenv("BP_DBG_MN_LBO")) p.dbg_mn_lbo = (uint32_t)atoi(e);
-    if (const char* e = getenv("BP_DBG_MN_SBO")) p.dbg_mn_sbo = (uint32_t)atoi(e);
     if (const char* e = getenv("BP_DBG_FLAGS")) p.dbg_flags = (uint32_t)atoi(e);
+    long long* dtrace = nullptr;
+    if (getenv("BP_DBG_TRACE")) {
+      CU_TRY(cudaMalloc(&dtrace, 1027 * sizeof(long long)));
+      CU_TRY(cudaMemset(dtrace, 0, 1027 * sizeof(long long)));
+      p.dbg_trace = dtrace;
+    }
     int reps = 1;
     if (const char* e = getenv("BP_DBG_REPS")) reps = std::max(1, atoi(e));
     const int sms = prop.multiProcessorCount;
@@ -1097,9 +1072,61 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       *elapsed_ms /= (float)reps;
     }
     CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
+    if (dtrace) {  // bring-up aid: print CTA 0's timeline of the last launch (cycles relative to kernel start)
+      std::vector<long long> t(1027);
+      CU_TRY(cudaMemcpy(t.data(), dtrace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(dtrace);
+      const long long t0 = t[1026];
+      const int nkb = std::min(256, (K + 31) / 32);
+      printf("trace (cycles since CTA start): kb | slot_free  loads_issued  full_seen  mma_issued\n");
+      for (int kb = 0; kb < nkb; ++kb)
+        if (kb < 24 || kb >= nkb - 4)
+          printf("  %3d | %9lld %9lld %9lld %9lld\n", kb, t[kb] - t0, t[256 + kb] - t0, t[512 + kb] - t0,
+                 t[768 + kb] - t0);
+      printf("  accumulator ready seen %lld, epilogue done %lld\n", t[1024] - t0, t[1025] - t0);
+      fflush(stdout);
+    }
     return BP_OK;
   }();
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux);
+  return rc;
+}
+
+// Bring-up aid: cycles per 128 x bn x 8 TF32 MMA (issue, issue+drain) on one SM; combo 0 = A MN/B K, 1 = K/K, 2 = MN/MN,
+// 3 = K/MN.  mode bit 0: fence before each group of 8, bit 1: commit after each group.
+int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total) {
+  long long* d = nullptr;
+  long long h[2] = {0, 0};
+  int rc = [&]() -> int {
+    CU_TRY(cudaMalloc(&d, 16));
+    const size_t smem = (128 + 256) * 64 * 4 + 1024;
+#define BP_RATE(AM, BM, BN_)                                                                         \
+  {                                                                                                  \
+    auto k = bp_mma_rate_kernel<AM, BM, BN_>;                                                        \
+    CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    k<<<1, 64, smem>>>(iters, mode, d);                                                              \
+  }
+    if (bn == 128) {
+      if (combo == 0) BP_RATE(true, false, 128) else if (combo == 1) BP_RATE(false, false, 128)
+      else if (combo == 2) BP_RATE(true, true, 128) else BP_RATE(false, true, 128)
+    } else if (bn == 256) {
+      if (combo == 0) BP_RATE(true, false, 256) else if (combo == 1) BP_RATE(false, false, 256)
+      else if (combo == 2) BP_RATE(true, true, 256) else BP_RATE(false, true, 256)
+    } else if (bn == 64) {
+      if (combo == 0) BP_RATE(true, false, 64) else if (combo == 1) BP_RATE(false, false, 64)
+      else if (combo == 2) BP_RATE(true, true, 64) else BP_RATE(false, true, 64)
+    } else {
+      return fail(BP_EINVAL, "bn must be 64, 128 or 256");
+    }
+#undef BP_RATE
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+    return BP_OK;
+  }();
+  cudaFree(d);
+  if (cyc_issue) *cyc_issue = (double)h[0] / (8.0 * iters);
+  if (cyc_total) *cyc_total = (double)h[1] / (8.0 * iters);
   return rc;
 }
 

@@ -141,6 +141,10 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
 int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bunch, float momentum, float lrate,
                  float weightcost);
 
+/* Bring-up microbenchmark (testing only): cycles per 128 x bn x 8 TF32 tcgen05.mma on one SM with both operands in
+ * shared memory.  combo 0 = A MN-major/B K-major, 1 = K/K, 2 = MN/MN, 3 = K/MN. */
+int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total);
+
 int bp_version(void);
 
 #ifdef __cplusplus

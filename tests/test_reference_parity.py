@@ -78,7 +78,7 @@ def test_reference_cuda_vs_oracle_vs_ours(bp, oracle, sizes, bunch):
         fro = lambda a: float(np.linalg.norm(a.astype(np.float64).ravel()))
         print(f"layer {l}: ||dW_ours - dW_ref||/||dW_ref|| = {fro(dours - dref) / fro(dref):.3e}   "
               f"||dW_oracle - dW_ref||/||dW_ref|| = {fro(dorc - dref) / fro(dref):.3e}")
-        assert fro(dours - dref) <= 3e-2 * fro(dref), f"ours vs reference dW{l}"
+        assert fro(dours - dref) <= 5e-2 * fro(dref), f"ours vs reference dW{l}"
         assert fro(dorc - dref) <= 1e-3 * fro(dref), f"oracle vs reference dW{l}"
     ocv = o.crossvalid(xcv, tcv)
     assert abs(ocv - rcv) <= 1e-4 * abs(rcv)
