@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--chunk-bunches", type=int, default=32, help="bunches resident per chunk (inputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"],
+                    help="tf32 = single-pass TF32 products (default); 3xtf32 = split precision, ~fp32 accuracy")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -161,7 +163,8 @@ def main():
     cfg = {"workload": f"{args.workload}: {'-'.join(map(str, sizes))} {'train (fwd+bwd+SGD)' if train else 'forward decode'}",
            "bunch_per_gpu": lb, "global_bunch": gb, "parallelism": f"dp{world}",
            "dropout": [dflag, vo, ho], "l2_policy": "inputs larger than L2 (resident chunk cycles)",
-           "math": "tf32 tensor-core products (fp32 storage, fp32 accumulate)"}
+           "math": ("3xTF32 split-precision tensor-core products (fp32 storage, fp32 accumulate, ~fp32 accuracy)"
+                    if args.math == "3xtf32" else "tf32 tensor-core products (fp32 storage, fp32 accumulate)")}
 
     # ------------------------------------------------------------------ reference arm: CPU restatement
     if args.impl == "reference":
@@ -195,7 +198,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w, b = glorot(sizes)
     g = bp.BP_GPU(1, len(sizes), sizes, gb, 1.0, 0.9, 0.0, w, b, dflag, vo, ho, seed=12345, device=local_rank,
-                  world_size=world, rank=rank)
+                  world_size=world, rank=rank,
+                  math_mode=bp.BP_MATH_3XTF32 if args.math == "3xtf32" else bp.BP_MATH_TF32)
     if world > 1:
         import torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -301,7 +305,8 @@ def main():
 
     peaks, peak_src = load_peaks()
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3" if args.math == "3xtf32" else "tf32",
             "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "impl": "ours"}
     fl = flops_per_frame(sizes, train) * lb   # per rank per step

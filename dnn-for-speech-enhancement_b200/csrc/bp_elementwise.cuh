@@ -19,10 +19,12 @@ struct SgdBiasRanges {
 //   delta = momentum*delta - (1-momentum)*lr*(grad/n + weightcost*w);  w = delta + 1.0*w
 // evaluated literally in fp32, one rounding per operation (no FMA contraction) so the CPU oracle can match bit-wise.
 // Traffic: reads delta,w,grad (12 B) + writes delta,w (8 B) = 20 B per parameter (the reference moves 28).
+// w_lo (optional): w - trunc_tf32(w) for the split-precision (3xTF32) GEMMs, +4 B per parameter.
 template <bool kHasWC>
 __global__ void __launch_bounds__(256)
 bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad, long long n4,
-              float nf, float momentum, float one_minus_m_lr, float weightcost, SgdBiasRanges br) {
+              float nf, float momentum, float one_minus_m_lr, float weightcost, SgdBiasRanges br,
+              float4* __restrict__ w_lo) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 g = __ldcs(grad + i);  // gradient is dead after this read: streaming load
@@ -47,6 +49,12 @@ bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* 
     }
     delta[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
     w[i] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    if (w_lo != nullptr) {
+      float lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo[k] = xv[k] - __uint_as_float(__float_as_uint(xv[k]) & 0xFFFFE000u);
+      w_lo[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -66,6 +74,21 @@ bp_input_dropout_kernel(float* __restrict__ x, long long ldx, int frames, int un
   for (int j = 0; j < 4; ++j) {
     const int f = fq * 4 + j;
     if (f < frames && r[j] < p) x[static_cast<long long>(f) * ldx + u] = 0.0f;
+  }
+}
+
+// lo[i] = x[i] - trunc_tf32(x[i]) (split-precision operand preparation for uploaded inputs / weights).
+__global__ void __launch_bounds__(256)
+bp_split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    float4 r;
+    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo[i] = r;
   }
 }
 

@@ -27,7 +27,8 @@
 //
 // Pipeline (all role loops are WARP-UNIFORM, the asynchronous instructions are issued under elect.sync — issuing
 // them from a divergent `if (lane == 0)` costs ~100 cycles per tcgen05.mma / TMA because every operand is first moved
-// from vector to uniform registers; measured with the clock64 trace below): warp 0 = TMA producer, warp 1 =
+// from vector to uniform registers — while every mbarrier wait is polled by ONE lane (not the issuing lane, see
+// kPollLane) followed by __syncwarp; all measured with the clock64 trace below): warp 0 = TMA producer, warp 1 =
 // tcgen05.mma issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> registers -> fused math -> coalesced global
 // stores).  kStages-deep smem ring of 64-deep k-blocks (full/empty mbarriers), double-buffered TMEM accumulator
 // (tfull/tempty mbarriers), persistent static tile loop, every wait bounded (a protocol bug traps, never hangs).
@@ -63,6 +64,9 @@ struct GemmParams {
   float drop_p;           // >0: zero y where u < drop_p (kernDropout DevFunc.cu:34-45), no rescale
   uint32_t seed_lo, seed_hi, step, layer;
   int frame0;             // global frame index of column n=0 (data-parallel shard offset), multiple of 4
+  int passes;             // 1 = single-pass TF32; 3 = split precision (3xTF32): A*B + A_lo*B + A*B_lo, where X_lo =
+                          // X - trunc_tf32(X) is kept as a second fp32 array by whoever writes X (~fp32 accuracy)
+  float* out_lo;          // if non-null: out_lo[...] = v - trunc_tf32(v) for every v stored to `out` (same layout)
   uint32_t dbg_flags;     // measurement aids: bit 0 skip the MMAs (TMA-only), bit 1 skip the loads (MMA-only)
   long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
                           // [256..511] loads issued, [512..767] stage full seen, [768..1023] MMAs issued,
@@ -82,6 +86,10 @@ constexpr size_t gemm_smem_bytes() {
          256 /*barriers*/;
 }
 
+// x - trunc_tf32(x): exactly representable (<= 13 significant bits); the tensor core truncates the same way.
+__device__ __forceinline__ float tf32_lo(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == 0) return x > 0.0f ? x : 0.0f;
   return 1.0f / (1.0f + expf(-x));
@@ -94,6 +102,7 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
 template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                const GemmParams p) {
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
   constexpr int kStages = gemm_stages<BLOCK_N>();
@@ -124,6 +133,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // The lane that polls mbarriers must NOT be the lane elect.sync picks (lane 0) to issue tcgen05.commit: a thread's
+  // barrier-unit operations are processed in order, and a try_wait queued behind its own pending commit-arrive only
+  // returns when the committed MMAs have COMPLETED — which serialises issue with execution (measured: ~480 idle
+  // tensor-pipe cycles per k-block).
+  constexpr int kPollLane = 1;
   const bool tracing = p.dbg_trace != nullptr && blockIdx.x == 0;
   if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
 
@@ -131,6 +145,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_it = num_kb * (p.passes == 3 ? 3 : 1);  // pipeline iterations per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -162,8 +177,12 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t % num_m_tiles) * BLOCK_M;
       const int n0 = (t / num_m_tiles) * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1u);
+      for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
+        if (kb == num_kb) { kb = 0; ++pass; }
+        const CUtensorMap* mapA = pass == 1 ? &tmAlo : &tmA;   // pass 0: A*B   pass 1: A_lo*B   pass 2: A*B_lo
+        const CUtensorMap* mapB = pass == 2 ? &tmBlo : &tmB;
+        if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);  // ONE lane polls (see header)
+        __syncwarp();
         if (elect_one()) {
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[kb] = clock64();
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
@@ -172,10 +191,10 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(&full[s]);
           } else {
             mbar_expect_tx(&full[s], STAGE_BYTES);
-            if constexpr (kAMN) tma_load_3d(sa, &tmA, &full[s], 0, kb * BLOCK_K, m0 / 32);
-            else tma_load_3d(sa, &tmA, &full[s], 0, m0, kb * (BLOCK_K / 32));
-            if constexpr (kBMN) tma_load_3d(sb, &tmB, &full[s], 0, kb * BLOCK_K, n0 / 32);
-            else tma_load_3d(sb, &tmB, &full[s], 0, n0, kb * (BLOCK_K / 32));
+            if constexpr (kAMN) tma_load_3d(sa, mapA, &full[s], 0, kb * BLOCK_K, m0 / 32);
+            else tma_load_3d(sa, mapA, &full[s], 0, m0, kb * (BLOCK_K / 32));
+            if constexpr (kBMN) tma_load_3d(sb, mapB, &full[s], 0, kb * BLOCK_K, n0 / 32);
+            else tma_load_3d(sb, mapB, &full[s], 0, n0, kb * (BLOCK_K / 32));
           }
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[256 + kb] = clock64();
         }
@@ -191,12 +210,18 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(&tempty[as], aph ^ 1u);
+      if (lane == kPollLane) mbar_wait(&tempty[as], aph ^ 1u);
+      __syncwarp();
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(as * BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[s], ph);
+      for (int kb = 0; kb < num_it; ++kb) {  // kb counts pipeline iterations (k-blocks x passes)
+        const bool fine = tracing && kb < 64 && t == (int)blockIdx.x;  // fine-grained stamps: [1100 + 8*kb + i]
+        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 0] = clock64();
+        if (lane == kPollLane) mbar_wait(&full[s], ph);
+        __syncwarp();
+        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 1] = clock64();
         tc_fence_after();
+        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 2] = clock64();
         const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
         if (elect_one()) {
@@ -204,21 +229,26 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.dbg_flags & 1u) {  // measurement aid: consume the stage without multiplying
             mbar_arrive(&empty[s]);
           } else {
+            // descriptor low words: one base per operand per stage, then base + constant per k-step (the tensor pipe's
+            // instruction queue is shallow, so every cycle of issue overhead beyond ~250 per k-block idles the pipe)
+            const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + (sa >> 4);
+            const uint32_t b_lo = (kBMN ? kDescLoMN : kDescLoK) + (sb >> 4);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 8; ++k) {
               const uint32_t a_off = kAMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kAsub + uint32_t(k % 4) * 32u;
               const uint32_t b_off = kBMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kBsub + uint32_t(k % 4) * 32u;
-              const uint32_t alo = (kAMN ? kDescLoMN : kDescLoK) | ((sa + a_off) >> 4);
-              const uint32_t blo = (kBMN ? kDescLoMN : kDescLoK) | ((sb + b_off) >> 4);
-              umma_tf32_lohi(d_tmem, alo, kAMN ? kDescHiMN : kDescHiK, blo, kBMN ? kDescHiMN : kDescHiK, idesc,
-                             (kb | k) != 0 ? 1u : 0u);
+              umma_tf32_lohi(d_tmem, a_lo + (a_off >> 4), kAMN ? kDescHiMN : kDescHiK, b_lo + (b_off >> 4),
+                             kBMN ? kDescHiMN : kDescHiK, idesc, (k != 0 || kb != 0) ? 1u : 0u);
             }
+            if (fine) p.dbg_trace[1100 + 8 * kb + 3] = clock64();
             umma_commit(&empty[s]);  // slot s is free again once these MMAs have read it
+            if (fine) p.dbg_trace[1100 + 8 * kb + 4] = clock64();
           }
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+          if (kb == num_it - 1) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[768 + kb] = clock64();
         }
         __syncwarp();
+        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 5] = clock64();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       as ^= 1;
@@ -274,7 +304,10 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int j = j4 * 4 + jj;
                 float y = act_fwd(fmaf(p.scale, __uint_as_float(v[j]), bias), p.act);
                 if (drop && u4[jj] < p.drop_p) y = 0.0f;
-                if (whole || nc + j < p.N) *o = y;
+                if (whole || nc + j < p.N) {
+                  *o = y;
+                  if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(y);
+                }
               }
             }
           }
@@ -293,7 +326,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.out2 != nullptr) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
                 if (p.aux != nullptr) {
                   const float diff = o - tg[j];
-                  if (p.out != nullptr) p.out[size_t(nc + j) * p.ldo + m] = p.gscale * diff;
+                  if (p.out != nullptr) {
+                    const float dv = p.gscale * diff;
+                    p.out[size_t(nc + j) * p.ldo + m] = dv;
+                    if (p.out_lo != nullptr) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+                  }
                   sq_local = fmaf(diff, diff, sq_local);
                 }
               }
@@ -308,7 +345,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* o = p.out + size_t(nc) * p.ldo + m;
 #pragma unroll
             for (int j = 0; j < 32; ++j, o += p.ldo)
-              if (whole || nc + j < p.N) *o = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
+              if (whole || nc + j < p.N) {
+                const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
+                *o = dv;
+                if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
+              }
           }
         }
       }

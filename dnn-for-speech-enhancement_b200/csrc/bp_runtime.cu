@@ -84,8 +84,8 @@ int get_encode() {
 //                    SWIZZLE_128B.
 //   MN-major operand (M/N dim contiguous):       rows = exact K extent,   chunks = ceil(MN/32); box {32, 64, box_mn/32};
 //                    SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands).
-int make_map(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
-             int box_outer, bool mn_major) {
+int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
+              int box_outer, bool mn_major) {
   BP_TRY(get_encode());
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 31) != 0)
     return fail(BP_EINVAL, "tensor map: base not 16-byte aligned or ld %% 32 != 0 (ld=%lld)", ld);
@@ -106,9 +106,22 @@ int make_map(CUtensorMap* m, const float* base, long long contiguous_extent, lon
   return BP_OK;
 }
 
+// An operand and (split-precision mode only) its low part X_lo = X - trunc_tf32(X), same shape and stride.
+struct MapPair {
+  CUtensorMap m;
+  CUtensorMap lo;
+};
+int make_map(MapPair* mp, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
+             long long ld, int box_outer, bool mn_major) {
+  BP_TRY(make_map1(&mp->m, base, contiguous_extent, rows, ld, box_outer, mn_major));
+  if (lo_base) BP_TRY(make_map1(&mp->lo, lo_base, contiguous_extent, rows, ld, box_outer, mn_major));
+  else mp->lo = mp->m;
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <bool kAMN, bool kBMN, int kEpi, int BN>
-int launch_gemm_bn(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
   auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, BN>;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   static thread_local int configured_dev = -1;
@@ -123,7 +136,7 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUt
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   const int grid = std::min(tiles, num_sms);
-  kern<<<grid, GEMM_THREADS, smem, st>>>(a, b, p);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(a.m, b.m, a.lo, b.lo, p);
   CU_TRY(cudaGetLastError());
   return BP_OK;
 }
@@ -132,7 +145,7 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUt
 constexpr int kBlockN = 128;
 
 template <bool kAMN, bool kBMN, int kEpi>
-int launch_gemm(cudaStream_t st, int num_sms, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
+int launch_gemm(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
   return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a, b, p);
 }
 
@@ -185,25 +198,29 @@ struct LayerState {
   long long off = 0;       // arena offset (floats) of row 0
   long long size = 0;      // (K+1)*ldN rounded up to 64 floats
   float* y = nullptr;      // activation output Y_l (hidden layers only): rows x ldy
+  float* y_lo = nullptr;   // split-precision low part (3xTF32 mode only)
   long long ldy = 0;
   float* d = nullptr;      // dE/dX_l: rows x ldd
+  float* d_lo = nullptr;
   long long ldd = 0;
   // tensor maps that do not depend on the chunk
-  CUtensorMap w_fwd;       // W^T as MN-major A: {N, K}, box {32,32}
-  CUtensorMap w_dx;        // W as K-major A:    {N, K}, box {32,128}
-  CUtensorMap yprev_fwd;   // Y_{l-1} as K-major B (l >= 2): {K, rows}, box {32,kBlockN}
-  CUtensorMap yprev_dw;    // Y_{l-1}^T as MN-major B (l >= 2): {K+1, bunch}, box {32,32}
-  CUtensorMap d_dx;        // D_l as K-major B: {N, bunch}, box {32,kBlockN}
-  CUtensorMap d_dw;        // D_l^T as MN-major A: {N, bunch}, box {32,32}
+  MapPair w_fwd;       // W^T as MN-major A: {N, K}, box {32,32}
+  MapPair w_dx;        // W as K-major A:    {N, K}, box {32,128}
+  MapPair yprev_fwd;   // Y_{l-1} as K-major B (l >= 2): {K, rows}, box {32,kBlockN}
+  MapPair yprev_dw;    // Y_{l-1}^T as MN-major B (l >= 2): {K+1, bunch}, box {32,32}
+  MapPair d_dx;        // D_l as K-major B: {N, bunch}, box {32,kBlockN}
+  MapPair d_dw;        // D_l^T as MN-major A: {N, bunch}, box {32,32}
 };
 
 struct ChunkBuf {
   float* x = nullptr;
+  float* x_lo = nullptr;   // split-precision low part of x (3xTF32 mode only)
   float* t = nullptr;
   long long cap_rows = 0;
   int rows = 0;            // rows currently resident
   bool has_targ = false;
   cudaEvent_t uploaded = nullptr;  // recorded on the copy stream after the H2D
+  cudaEvent_t split_done = nullptr;  // 3xTF32: x_lo has been derived from x
   cudaEvent_t consumed = nullptr;  // recorded on the compute stream after the last kernel that reads the buffer
   bool consumed_valid = false;
 };
@@ -214,10 +231,13 @@ struct Rank {
   int local_bunch = 0;
   int num_sms = 0;
   cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
+  int dw_bn = 128;              // N-tile of the weight-gradient GEMM (BP_DW_BN=256 for experiments)
   cudaStream_t side = nullptr;  // weight-gradient GEMMs run here, concurrently with the dX chain on `compute`
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
   cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
   float *w = nullptr, *dw = nullptr, *g = nullptr;
+  float* w_lo = nullptr;   // split-precision low part of the weights (3xTF32 mode only)
+  int passes = 1;          // 1 = TF32, 3 = 3xTF32
   long long arena_floats = 0;
   LayerState layer[BP_MAXLAYER];
   long long ldx = 0;
@@ -252,12 +272,17 @@ int ensure_chunk(Rank* r, ChunkBuf& c, long long rows) {
     CU_TRY(cudaStreamSynchronize(r->copy));
     CU_TRY(cudaFree(c.x));
     CU_TRY(cudaFree(c.t));
-    c.x = c.t = nullptr;
+    if (c.x_lo) CU_TRY(cudaFree(c.x_lo));
+    c.x = c.t = c.x_lo = nullptr;
   }
   const long long cap = std::max<long long>(rows, r->cfg.bunchsize);
   CU_TRY(cudaMalloc(&c.x, sizeof(float) * cap * r->ldx));
   CU_TRY(cudaMalloc(&c.t, sizeof(float) * cap * r->Nout()));
   CU_TRY(cudaMemsetAsync(c.x, 0, sizeof(float) * cap * r->ldx, r->copy));
+  if (r->passes == 3) {
+    CU_TRY(cudaMalloc(&c.x_lo, sizeof(float) * cap * r->ldx));
+    CU_TRY(cudaMemsetAsync(c.x_lo, 0, sizeof(float) * cap * r->ldx, r->copy));
+  }
   bp_fill_col_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, r->copy>>>(c.x, r->ldx, cap, r->K0(), 1.0f);
   CU_TRY(cudaGetLastError());
   r->launches++;
@@ -274,15 +299,20 @@ int rank_destroy(Rank* r) {
   if (r->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(r->nccl_comm);
   for (auto& c : r->chunk) {
     cudaFree(c.x);
+    cudaFree(c.x_lo);
     cudaFree(c.t);
     if (c.uploaded) cudaEventDestroy(c.uploaded);
+    if (c.split_done) cudaEventDestroy(c.split_done);
     if (c.consumed) cudaEventDestroy(c.consumed);
   }
   for (int l = 1; l <= r->L; ++l) {
     cudaFree(r->layer[l].y);
     cudaFree(r->layer[l].d);
+    cudaFree(r->layer[l].y_lo);
+    cudaFree(r->layer[l].d_lo);
   }
   cudaFree(r->w);
+  cudaFree(r->w_lo);
   cudaFree(r->dw);
   cudaFree(r->g);
   cudaFree(r->out_dev);
@@ -311,6 +341,12 @@ int upload_params(Rank* r, float* const* weights, float* const* bias) {
     CU_TRY(cudaMemcpyAsync(r->w + ls.off + (long long)ls.K * ls.ldN, bias[l], size_t(ls.N) * 4,
                            cudaMemcpyHostToDevice, r->compute));
   }
+  if (r->passes == 3) {
+    bp_split_lo_kernel<<<r->num_sms * 8, 256, 0, r->compute>>>((const float4*)r->w, (float4*)r->w_lo,
+                                                               r->arena_floats / 4);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+  }
   CU_TRY(cudaStreamSynchronize(r->compute));
   return BP_OK;
 }
@@ -329,7 +365,8 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   if ((cfg->bunchsize / cfg->world_size) % 4 != 0 && cfg->dropoutflag == 1)
     return fail(BP_EINVAL, "bp_create: per-rank bunch (%d) must be a multiple of 4 when dropout is on",
                 cfg->bunchsize / cfg->world_size);
-  if (cfg->math_mode != BP_MATH_TF32) return fail(BP_EINVAL, "bp_create: math_mode %d not built", cfg->math_mode);
+  if (cfg->math_mode != BP_MATH_TF32 && cfg->math_mode != BP_MATH_3XTF32)
+    return fail(BP_EINVAL, "bp_create: math_mode %d", cfg->math_mode);
   if (cfg->activation != BP_ACT_RELU && cfg->activation != BP_ACT_SIGMOID)
     return fail(BP_EINVAL, "bp_create: activation %d", cfg->activation);
 
@@ -351,6 +388,8 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->L = cfg->numlayers - 1;
   r->local_bunch = cfg->bunchsize / cfg->world_size;
   r->num_sms = prop.multiProcessorCount;
+  r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
+  if (const char* e = getenv("BP_DW_BN")) r->dw_bn = atoi(e) == 256 ? 256 : 128;
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -364,6 +403,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaEventCreateWithFlags(&r->ev_comm, cudaEventDisableTiming));
     for (auto& c : r->chunk) {
       CU_TRY(cudaEventCreateWithFlags(&c.uploaded, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&c.split_done, cudaEventDisableTiming));
       CU_TRY(cudaEventCreateWithFlags(&c.consumed, cudaEventDisableTiming));
     }
     for (auto& e : r->loss_done) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -388,6 +428,10 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaMalloc(&r->w, off * 4));
     CU_TRY(cudaMalloc(&r->dw, off * 4));
     CU_TRY(cudaMalloc(&r->g, off * 4));
+    if (r->passes == 3) {
+      CU_TRY(cudaMalloc(&r->w_lo, off * 4));
+      CU_TRY(cudaMemsetAsync(r->w_lo, 0, off * 4, r->compute));
+    }
     CU_TRY(cudaMemsetAsync(r->w, 0, off * 4, r->compute));
     CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
     CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
@@ -400,10 +444,18 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       ls.ldd = round_up(ls.N, 32);
       CU_TRY(cudaMalloc(&ls.d, rows * ls.ldd * 4));
       CU_TRY(cudaMemsetAsync(ls.d, 0, rows * ls.ldd * 4, r->compute));
+      if (r->passes == 3) {
+        CU_TRY(cudaMalloc(&ls.d_lo, rows * ls.ldd * 4));
+        CU_TRY(cudaMemsetAsync(ls.d_lo, 0, rows * ls.ldd * 4, r->compute));
+      }
       if (l < r->L) {
         ls.ldy = round_up(ls.N + 1, 32);
         CU_TRY(cudaMalloc(&ls.y, rows * ls.ldy * 4));
         CU_TRY(cudaMemsetAsync(ls.y, 0, rows * ls.ldy * 4, r->compute));
+        if (r->passes == 3) {  // the ones column's low part is 0: 1.0f truncates exactly
+          CU_TRY(cudaMalloc(&ls.y_lo, rows * ls.ldy * 4));
+          CU_TRY(cudaMemsetAsync(ls.y_lo, 0, rows * ls.ldy * 4, r->compute));
+        }
         bp_fill_col_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, r->compute>>>(ls.y, ls.ldy, rows, ls.N, 1.0f);
         CU_TRY(cudaGetLastError());
         r->launches++;
@@ -412,14 +464,15 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     for (int l = 1; l <= r->L; ++l) {
       LayerState& ls = r->layer[l];
       const float* wl = r->w + ls.off;
-      BP_TRY(make_map(&ls.w_fwd, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, true));
-      BP_TRY(make_map(&ls.w_dx, wl, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
-      BP_TRY(make_map(&ls.d_dx, ls.d, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
-      BP_TRY(make_map(&ls.d_dw, ls.d, ls.N, r->local_bunch, ls.ldd, GEMM_BLOCK_M, true));
+      const float* wlo = r->w_lo ? r->w_lo + ls.off : nullptr;
+      BP_TRY(make_map(&ls.w_fwd, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, true));
+      BP_TRY(make_map(&ls.w_dx, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
+      BP_TRY(make_map(&ls.d_dx, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
+      BP_TRY(make_map(&ls.d_dw, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, GEMM_BLOCK_M, true));
       if (l >= 2) {
         LayerState& lp = r->layer[l - 1];
-        BP_TRY(make_map(&ls.yprev_fwd, lp.y, ls.K, rows, lp.ldy, kBlockN, false));
-        BP_TRY(make_map(&ls.yprev_dw, lp.y, ls.K + 1, r->local_bunch, lp.ldy, kBlockN, true));
+        BP_TRY(make_map(&ls.yprev_fwd, lp.y, lp.y_lo, ls.K, rows, lp.ldy, kBlockN, false));
+        BP_TRY(make_map(&ls.yprev_dw, lp.y, lp.y_lo, ls.K + 1, r->local_bunch, lp.ldy, r->dw_bn, true));
       }
     }
     BP_TRY(upload_params(r, weights, bias));
@@ -447,11 +500,18 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
   CU_TRY(cudaMemcpy2DAsync(c.x, r->ldx * 4, in, rowb, rowb, n_frames, cudaMemcpyHostToDevice, r->copy));
   if (targ)
     CU_TRY(cudaMemcpyAsync(c.t, targ, size_t(n_frames) * r->Nout() * 4, cudaMemcpyHostToDevice, r->copy));
-  CU_TRY(cudaEventRecord(c.uploaded, r->copy));
+  CU_TRY(cudaEventRecord(c.uploaded, r->copy));  // host buffers are consumed here
+  if (r->passes == 3) {
+    bp_split_lo_kernel<<<r->num_sms * 8, 256, 0, r->copy>>>((const float4*)c.x, (float4*)c.x_lo,
+                                                            (long long)n_frames * r->ldx / 4);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+    CU_TRY(cudaEventRecord(c.split_done, r->copy));
+  }
   c.rows = n_frames;
   c.has_targ = targ != nullptr;
   r->cur = nb;
-  CU_TRY(cudaStreamWaitEvent(r->compute, c.uploaded, 0));
+  CU_TRY(cudaStreamWaitEvent(r->compute, r->passes == 3 ? c.split_done : c.uploaded, 0));
   // The caller may overwrite its buffers as soon as we return (BP_GPU::train semantics): wait for the DMA only.
   CU_TRY(cudaEventSynchronize(c.uploaded));
   return BP_OK;
@@ -473,6 +533,12 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
                                                           r->step, frame0);
     CU_TRY(cudaGetLastError());
     r->launches++;
+    if (r->passes == 3) {  // the same mask on the low part
+      bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(c.x_lo + (long long)f0 * r->ldx, r->ldx, n, r->K0(),
+                                                            cf.visible_omit, seed_lo, seed_hi, r->step, frame0);
+      CU_TRY(cudaGetLastError());
+      r->launches++;
+    }
   }
   for (int l = 1; l <= r->L; ++l) {
     LayerState& ls = r->layer[l];
@@ -489,20 +555,23 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     p.step = r->step;
     p.layer = (uint32_t)l;
     p.frame0 = frame0;
-    CUtensorMap xmap;
-    const CUtensorMap* bmap = &ls.yprev_fwd;
+    p.passes = r->passes;
+    MapPair xmap;
+    const MapPair* bmap = &ls.yprev_fwd;
     if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, ls.K, n, r->ldx, kBlockN, false));
+      BP_TRY(make_map(&xmap, xb, c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr, ls.K, n, r->ldx, kBlockN, false));
       bmap = &xmap;
     }
     if (l < r->L) {
       p.out = ls.y;
+      p.out_lo = ls.y_lo;
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
       BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->num_sms, ls.w_fwd, *bmap, p)));
     } else {
       if (train) {
         p.out = ls.d;
+        p.out_lo = ls.d_lo;
         p.ldo = ls.ldd;
         p.aux = c.t + (long long)f0 * ls.N;
         p.ldaux = ls.N;
@@ -549,13 +618,16 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.K = n;
     p.out = r->g + ls.off;
     p.ldo = ls.ldN;
-    CUtensorMap xmap;
-    const CUtensorMap* bmap = &ls.yprev_dw;
+    p.passes = r->passes;
+    MapPair xmap;
+    const MapPair* bmap = &ls.yprev_dw;
     if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, ls.K + 1, n, r->ldx, kBlockN, true));
+      BP_TRY(make_map(&xmap, xb, c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr, ls.K + 1, n, r->ldx, r->dw_bn,
+                      true));
       bmap = &xmap;
     }
-    BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
+    if (r->dw_bn == 256) BP_TRY((launch_gemm_bn<true, true, EPI_PLAIN, 256>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
+    else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
     r->launches++;
     if (r->nccl_comm) {
       CU_TRY(cudaEventRecord(r->ev_grad, r->side));
@@ -575,10 +647,12 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.N = n;
     p.K = ls.N;
     p.out = lp.d;
+    p.out_lo = lp.d_lo;
     p.ldo = lp.ldd;
     p.aux = lp.y;
     p.ldaux = lp.ldy;
     p.act = cf.activation;
+    p.passes = r->passes;
     BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->num_sms, ls.w_dx, ls.d_dx, p)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
@@ -600,10 +674,11 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     const float c1 = (1 - cf.momentum) * cf.lrate;
     if (cf.weightcost != 0.0f)
       bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
-                                                        cf.momentum, c1, cf.weightcost, r->bias_ranges);
+                                                        cf.momentum, c1, cf.weightcost, r->bias_ranges,
+                                                        (float4*)r->w_lo);
     else
       bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
-                                                         cf.momentum, c1, 0.0f, r->bias_ranges);
+                                                         cf.momentum, c1, 0.0f, r->bias_ranges, (float4*)r->w_lo);
     CU_TRY(cudaGetLastError());
     r->launches++;
   }
@@ -763,6 +838,7 @@ int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes,
   cfg.seed = 0x5eed5eedULL;
   if (const char* e = getenv("BP_ACTIVATION")) cfg.activation = (strcmp(e, "sigmoid") == 0) ? BP_ACT_SIGMOID : 0;
   if (const char* e = getenv("BP_SEED")) cfg.seed = strtoull(e, nullptr, 0);
+  if (const char* e = getenv("BP_MATH")) cfg.math_mode = (strcmp(e, "3xtf32") == 0) ? BP_MATH_3XTF32 : BP_MATH_TF32;
 
   bp_handle* hh = new bp_handle();
   hh->ranks.assign(gpu_used, nullptr);
@@ -995,7 +1071,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
                   int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
                   float* elapsed_ms) {
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return fail(BP_EINVAL, "bp_debug_gemm: bad argument");
-  if (math_mode != BP_MATH_TF32) return fail(BP_EINVAL, "bp_debug_gemm: math_mode %d not built", math_mode);
+  if (math_mode != BP_MATH_TF32 && math_mode != BP_MATH_3XTF32)
+    return fail(BP_EINVAL, "bp_debug_gemm: math_mode %d", math_mode);
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -1012,7 +1089,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
   }
   const long long dlda = round_up(a_cols, 32), dldb = round_up(b_cols, 32), dldo = round_up(M, 32),
                   dldaux = round_up(M, 32);
-  float *dA = nullptr, *dB = nullptr, *dO = nullptr, *dBias = nullptr, *dAux = nullptr;
+  float *dA = nullptr, *dB = nullptr, *dO = nullptr, *dBias = nullptr, *dAux = nullptr, *dAlo = nullptr,
+        *dBlo = nullptr;
   cudaStream_t st;
   cudaEvent_t e0, e1;
   int rc = [&]() -> int {
@@ -1035,10 +1113,19 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       CU_TRY(cudaMalloc(&dAux, (long long)N * dldaux * 4));
       CU_TRY(cudaMemcpy2D(dAux, dldaux * 4, aux, size_t(ldaux) * 4, size_t(M) * 4, N, cudaMemcpyHostToDevice));
     }
-    CUtensorMap ma, mb;
-    BP_TRY(make_map(&ma, dA, a_cols, a_rows, dlda, GEMM_BLOCK_M, amn));
-    BP_TRY(make_map(&mb, dB, b_cols, b_rows, dldb, kBlockN, bmn));
+    if (math_mode == BP_MATH_3XTF32) {
+      CU_TRY(cudaMalloc(&dAlo, a_rows * dlda * 4));
+      CU_TRY(cudaMalloc(&dBlo, b_rows * dldb * 4));
+      bp_split_lo_kernel<<<1184, 256>>>((const float4*)dA, (float4*)dAlo, a_rows * dlda / 4);
+      bp_split_lo_kernel<<<1184, 256>>>((const float4*)dB, (float4*)dBlo, b_rows * dldb / 4);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaDeviceSynchronize());
+    }
+    MapPair ma, mb;
+    BP_TRY(make_map(&ma, dA, dAlo, a_cols, a_rows, dlda, GEMM_BLOCK_M, amn));
+    BP_TRY(make_map(&mb, dB, dBlo, b_cols, b_rows, dldb, kBlockN, bmn));
     GemmParams p{};
+    p.passes = math_mode == BP_MATH_3XTF32 ? 3 : 1;
     p.M = M; p.N = N; p.K = K;
     p.out = dO; p.ldo = dldo;
     p.bias = dBias;
@@ -1048,8 +1135,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     if (const char* e = getenv("BP_DBG_FLAGS")) p.dbg_flags = (uint32_t)atoi(e);
     long long* dtrace = nullptr;
     if (getenv("BP_DBG_TRACE")) {
-      CU_TRY(cudaMalloc(&dtrace, 1027 * sizeof(long long)));
-      CU_TRY(cudaMemset(dtrace, 0, 1027 * sizeof(long long)));
+      CU_TRY(cudaMalloc(&dtrace, 2048 * sizeof(long long)));
+      CU_TRY(cudaMemset(dtrace, 0, 2048 * sizeof(long long)));
       p.dbg_trace = dtrace;
     }
     int reps = 1;
@@ -1073,7 +1160,7 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     }
     CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
     if (dtrace) {  // bring-up aid: print CTA 0's timeline of the last launch (cycles relative to kernel start)
-      std::vector<long long> t(1027);
+      std::vector<long long> t(2048);
       CU_TRY(cudaMemcpy(t.data(), dtrace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       cudaFree(dtrace);
       const long long t0 = t[1026];
@@ -1084,11 +1171,17 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
           printf("  %3d | %9lld %9lld %9lld %9lld\n", kb, t[kb] - t0, t[256 + kb] - t0, t[512 + kb] - t0,
                  t[768 + kb] - t0);
       printf("  accumulator ready seen %lld, epilogue done %lld\n", t[1024] - t0, t[1025] - t0);
+      printf("MMA warp fine stamps: kb | before_wait after_wait after_fence mmas_issued commit_issued after_syncwarp\n");
+      for (int kb = 2; kb < std::min(nkb, 10); ++kb) {
+        printf("  %3d |", kb);
+        for (int i = 0; i < 6; ++i) printf(" %9lld", t[1100 + 8 * kb + i] - t0);
+        printf("\n");
+      }
       fflush(stdout);
     }
     return BP_OK;
   }();
-  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux); cudaFree(dAlo); cudaFree(dBlo);
   return rc;
 }
 
@@ -1149,10 +1242,10 @@ int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bun
     const float c1 = (1 - momentum) * lrate;
     if (weightcost != 0.0f)
       bp_sgd_kernel<true><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum, c1,
-                                            weightcost, br);
+                                            weightcost, br, nullptr);
     else
       bp_sgd_kernel<false><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum,
-                                             c1, 0.0f, br);
+                                             c1, 0.0f, br, nullptr);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(delta, d, size_t(n) * 4, cudaMemcpyDeviceToHost));

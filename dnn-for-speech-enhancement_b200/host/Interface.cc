@@ -128,6 +128,10 @@ void Interface::Initial(int argc, char** argv) {
       para->activation = (strcmp(val, "sigmoid") == 0) ? 1 : 0;
       continue;
     }
+    if (key == "math") {  // tf32 (default) | 3xtf32 (split precision, ~fp32 accuracy)
+      setenv("BP_MATH", val, 1);
+      continue;
+    }
     if (key == "seed") {
       para->seed = strtoull(val, nullptr, 0);
       continue;

@@ -79,6 +79,32 @@ def test_gemm_against_truncated_float64(bp, kind, shape):
     assert_close(out, ref, TOL_GEMM, f"gemm kind {kind} {shape}")
 
 
+@pytest.mark.parametrize("kind", [3, 1, 2])
+def test_gemm_3xtf32_is_fp32_accurate(bp, kind):
+    """Split precision (A*B + A_lo*B + A*B_lo): error against the float64 product of the RAW fp32 operands."""
+    import ctypes as C
+    lib = bp.load_library()
+    M, N, K = 300, 260, 1030
+    rng = np.random.default_rng(kind)
+    fp = C.POINTER(C.c_float)
+    if kind == 3:
+        A = rng.standard_normal((K, M), dtype=np.float32); B = rng.standard_normal((N, K), dtype=np.float32)
+        ref = B.astype(np.float64) @ A.astype(np.float64)
+    elif kind == 1:
+        A = rng.standard_normal((M, K), dtype=np.float32); B = rng.standard_normal((N, K), dtype=np.float32)
+        ref = B.astype(np.float64) @ A.astype(np.float64).T
+    else:
+        A = rng.standard_normal((K, M), dtype=np.float32); B = rng.standard_normal((K, N), dtype=np.float32)
+        ref = B.astype(np.float64).T @ A.astype(np.float64)
+    out = np.full((N, M), np.nan, dtype=np.float32)
+    aux = np.ones((N, M), dtype=np.float32)
+    rc = lib.bp_debug_gemm(kind, M, N, K, A.ctypes.data_as(fp), A.shape[1], B.ctypes.data_as(fp), B.shape[1],
+                           out.ctypes.data_as(fp), M, None, aux.ctypes.data_as(fp) if kind == 1 else None, M, 1.0, 0,
+                           bp.BP_MATH_3XTF32, None)
+    assert rc == 0, lib.bp_last_error().decode()
+    assert_close(out, ref, 2e-5, f"3xTF32 gemm kind {kind}")
+
+
 def test_sgd_update_bit_exact(bp, oracle):
     import ctypes as C
     lib = bp.load_library()
@@ -127,6 +153,27 @@ def test_train_matches_oracle(bp, oracle, act):
         assert_close(bs[l], o_tf.b[l], 2 * TOL_TF32, f"b{l} vs tf32 oracle (act {act})")
         assert_close(ws[l], o_fp.w[l], TOL_FP32, f"W{l} vs fp32 oracle (act {act})")
     assert g.counters()[1] == 5  # trailing 7 frames skipped (BP_GPU.cu:315-318)
+    g.close()
+
+
+def test_3xtf32_training_matches_literal_fp32_oracle(bp, oracle):
+    """BP_MATH_3XTF32 against the literal-fp32 oracle (= the reference's cuBLAS-FP32 arithmetic) at fp32-class
+    tolerance: 1e-4 * rms on the weights, 5e-3 relative Frobenius on the update (ReLU' flips, see assert_fro)."""
+    sizes = [75, 96, 130, 33]
+    x, t = oracle.synth_data(5 * 32, sizes[0], sizes[-1], seed=21)
+    w, b = oracle.glorot_init(sizes, seed=3)
+    kw = dict(lrate=0.7, momentum=0.9, weightcost=1e-4)
+    o = oracle.Net(sizes, 32, weights=w, bias=b, dropoutflag=1, visible_omit=0.1, hid_omit=0.2, seed=5, **kw)
+    g = bp.BP_GPU(1, len(sizes), sizes, 32, kw["lrate"], kw["momentum"], kw["weightcost"], w, b, 1, 0.1, 0.2, seed=5,
+                  device=0, math_mode=bp.BP_MATH_3XTF32)
+    g.train(x.shape[0], x, t)
+    o.train(x.shape[0], x, t)
+    ws, bs = g.returnWeights()
+    for l in range(1, len(sizes)):
+        assert_close(ws[l], o.w[l], 1e-4, f"3xTF32 W{l}")
+        assert_fro(ws[l] - w[l], o.w[l] - w[l], 5e-3, f"3xTF32 dW{l}")
+    out = g.forward(100, x[:100])
+    assert_close(out, o.forward(x[:100]), 2e-4, "3xTF32 forward (keep-scaled)")
     g.close()
 
 
