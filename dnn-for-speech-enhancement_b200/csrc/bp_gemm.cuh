@@ -215,13 +215,9 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(as * BLOCK_N);
       for (int kb = 0; kb < num_it; ++kb) {  // kb counts pipeline iterations (k-blocks x passes)
-        const bool fine = tracing && kb < 64 && t == (int)blockIdx.x;  // fine-grained stamps: [1100 + 8*kb + i]
-        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 0] = clock64();
         if (lane == kPollLane) mbar_wait(&full[s], ph);
         __syncwarp();
-        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 1] = clock64();
         tc_fence_after();
-        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 2] = clock64();
         const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
         if (elect_one()) {
@@ -240,15 +236,12 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_tf32_lohi(d_tmem, a_lo + (a_off >> 4), kAMN ? kDescHiMN : kDescHiK, b_lo + (b_off >> 4),
                              kBMN ? kDescHiMN : kDescHiK, idesc, (k != 0 || kb != 0) ? 1u : 0u);
             }
-            if (fine) p.dbg_trace[1100 + 8 * kb + 3] = clock64();
             umma_commit(&empty[s]);  // slot s is free again once these MMAs have read it
-            if (fine) p.dbg_trace[1100 + 8 * kb + 4] = clock64();
           }
           if (kb == num_it - 1) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[768 + kb] = clock64();
         }
         __syncwarp();
-        if (fine && lane == 0) p.dbg_trace[1100 + 8 * kb + 5] = clock64();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       as ^= 1;

@@ -1171,12 +1171,6 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
           printf("  %3d | %9lld %9lld %9lld %9lld\n", kb, t[kb] - t0, t[256 + kb] - t0, t[512 + kb] - t0,
                  t[768 + kb] - t0);
       printf("  accumulator ready seen %lld, epilogue done %lld\n", t[1024] - t0, t[1025] - t0);
-      printf("MMA warp fine stamps: kb | before_wait after_wait after_fence mmas_issued commit_issued after_syncwarp\n");
-      for (int kb = 2; kb < std::min(nkb, 10); ++kb) {
-        printf("  %3d |", kb);
-        for (int i = 0; i < 6; ++i) printf(" %9lld", t[1100 + 8 * kb + i] - t0);
-        printf("\n");
-      }
       fflush(stdout);
     }
     return BP_OK;
