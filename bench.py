@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -68,42 +67,54 @@ def synth(n, k0, nout, seed, out_x=None, out_t=None):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """One `nvidia-smi -lms 100` process sampling SM clock / power / throttle reasons for the whole loaded part of the
+    run (warm-up, timed region, profiled pass, e2e pass) — B200_PROFILING.md recipe."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.stop_flag, self.th = gpu_index, [], False, None
-
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                    str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.idx, self.proc, self.t0 = gpu_index, None, 0.0
 
     def start(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        if self.th:
-            self.th.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[c.strip() for c in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+        def num(s):
+            try:
+                return float(s)
+            except Exception:
+                return None
+        sm = [num(r[1]) for r in rows if len(r) > 7 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if len(r) > 7 and num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if len(r) > 7 and num(r[3]) is not None]
+        loaded = [s for s, p in zip(sm, pw) if p is not None and p > 300.0] or sm   # samples taken under load
         reasons = set()
-        for r in self.rows:
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            if len(r) > 7:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                   r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(loaded) if pw else 0}
 
 
 def load_peaks():
@@ -153,6 +164,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Exactly ONE line on stdout: libraries (NCCL prints its version) write to fd 1 too, so fd 1 is pointed at stderr
+    # for the duration of the run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if world == 1 and args.gpus > 1:
         print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU)", file=sys.stderr)
         return 2
@@ -184,7 +204,7 @@ def main():
                 "gpu_launches": 0,
                 "note": "the reference has no CPU implementation of this path (CUDA+cuBLAS only); this is the literal "
                         "fp32 CPU restatement oracle/bp_oracle.c timed on the host cores"}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -240,11 +260,11 @@ def main():
             done += k
 
     # ---- value: device-resident
-    run_resident(W)
-    launches0 = g.counters()[0]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    run_resident(W)
+    launches0 = g.counters()[0]
     barrier()
     g.timer_start()
     run_resident(K)
@@ -261,7 +281,6 @@ def main():
         run_resident(min(K, 64))
         prof, nprof = g.profile()
         g.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: bp_train() from pinned host buffers, one chunk of `e2e_cb` bunches per call, loss read back per step
     e2e_cb = 8
@@ -297,6 +316,7 @@ def main():
         e2e = {"value": n_calls * gb / dt, "unit": "frames/s", "h2d_bytes_per_step": 4 * lb * sizes[0] * world,
                "d2h_bytes_per_step": 4 * lb * sizes[-1] * world, "api": "bp_forward() host in / host out"}
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         g.close()
         if dist is not None:
@@ -339,7 +359,7 @@ def main():
         except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
                                     "sample": f"unavailable: {e}"}
-    print(json.dumps(line))
+    emit(line)
     g.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -169,6 +169,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+  // the tail of the previous kernel in the stream; nothing below may touch global memory before that kernel's
+  // writes are visible.  Dependents may in turn start their own prologue as soon as our CTAs retire.
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)

@@ -136,8 +136,27 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   const int grid = std::min(tiles, num_sms);
-  kern<<<grid, GEMM_THREADS, smem, st>>>(a.m, b.m, a.lo, b.lo, p);
-  CU_TRY(cudaGetLastError());
+  static const uint32_t env_flags = [] {
+    const char* e = getenv("BP_GEMM_FLAGS");  // measurement aid, see GemmParams::dbg_flags
+    return e ? (uint32_t)atoi(e) : 0u;
+  }();
+  static const bool use_pdl = [] {
+    const char* e = getenv("BP_PDL");  // programmatic dependent launch between consecutive GEMMs (default on)
+    return e ? atoi(e) != 0 : true;
+  }();
+  GemmParams q = p;
+  q.dbg_flags |= env_flags;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a.m, b.m, a.lo, b.lo, q));
   return BP_OK;
 }
 
