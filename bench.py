@@ -67,54 +67,51 @@ def synth(n, k0, nout, seed, out_x=None, out_t=None):
 
 
 class ClockSampler:
-    """One `nvidia-smi -lms 100` process sampling SM clock / power / throttle reasons for the whole loaded part of the
-    run (warm-up, timed region, profiled pass, e2e pass) — B200_PROFILING.md recipe."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / clock-event reasons through NVML (nvidia_ml_py) every ~2 ms from a thread while the
+    warm-up and the timed region run, so that even a 60 ms timed region is covered (nvidia-smi -lms cannot)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.t0 = gpu_index, None, 0.0
+        self.idx, self.rows, self.stop_flag, self.th, self.max_mhz = gpu_index, [], False, None, None
+        self.in_region = False
+
+    def _run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), pw, int(rs), self.in_region))
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        import threading
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
     def stop(self):
-        rows = []
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-                out, _ = self.proc.communicate(timeout=5)
-                rows = [[c.strip() for c in ln.split(",")] for ln in out.splitlines() if ln.strip()]
-            except Exception:
-                try:
-                    self.proc.kill()
-                except Exception:
-                    pass
-        def num(s):
-            try:
-                return float(s)
-            except Exception:
-                return None
-        sm = [num(r[1]) for r in rows if len(r) > 7 and num(r[1]) is not None]
-        mx = [num(r[2]) for r in rows if len(r) > 7 and num(r[2]) is not None]
-        pw = [num(r[3]) for r in rows if len(r) > 7 and num(r[3]) is not None]
-        loaded = [s for s, p in zip(sm, pw) if p is not None and p > 300.0] or sm   # samples taken under load
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=5)
+        timed = [r for r in self.rows if r[3]] or self.rows
+        sm = [r[0] for r in timed]
         reasons = set()
-        for r in rows:
-            if len(r) > 7:
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
-                                   r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
-                "samples_under_load": len(loaded) if pw else 0}
+        for r in timed:
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max((r[1] for r in timed), default=None), "reasons": sorted(reasons),
+                "samples": len(self.rows), "samples_in_timed_region": sum(1 for r in self.rows if r[3])}
 
 
 def load_peaks():
@@ -266,9 +263,11 @@ def main():
     run_resident(W)
     launches0 = g.counters()[0]
     barrier()
+    sampler.in_region = True
     g.timer_start()
     run_resident(K)
     ms = g.timer_stop()
+    sampler.in_region = False
     barrier()
     ms = max_over_ranks(ms)
     launches = g.counters()[0] - launches0
@@ -324,6 +323,11 @@ def main():
         return 0
 
     peaks, peak_src = load_peaks()
+    traffic = {}
+    try:  # DRAM bytes of the committed ncu --set full capture (profiles/), per bunch / per launch
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+    except Exception:
+        pass
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32x3" if args.math == "3xtf32" else "tf32",
@@ -336,14 +340,15 @@ def main():
         ach = fl / (gemm_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm_kernel (fwd + dX + dW launches of one bunch)",
                             "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                            "traffic": None,
+                            "traffic": traffic.get("gemm_dram_bytes_per_bunch") if args.workload == "C2" else None,
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2 (kind::tf32 issues at half the bf16 rate)",
                             "per_class_ms": {k: v / nprof for k, v in prof.items()}}
         sgd_ms = prof["sgd"] / nprof
         sgd_bytes = 20.0 * n_params(sizes)  # algorithmic minimum
         line["roofline_sgd"] = {"bound": "hbm", "kernel": "bp_sgd_kernel", "achieved": sgd_bytes / (sgd_ms * 1e-3) / 1e9,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": sgd_bytes / (sgd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                "frac": sgd_bytes / (sgd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                "traffic": traffic.get("sgd_dram_bytes_per_launch") if args.workload == "C2" else None,
                                 "peak_source": peak_src}
     else:
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0

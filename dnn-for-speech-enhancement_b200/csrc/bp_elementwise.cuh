@@ -20,15 +20,18 @@ struct SgdBiasRanges {
 // evaluated literally in fp32, one rounding per operation (no FMA contraction) so the CPU oracle can match bit-wise.
 // Traffic: reads delta,w,grad (12 B) + writes delta,w (8 B) = 20 B per parameter (the reference moves 28).
 // w_lo (optional): w - trunc_tf32(w) for the split-precision (3xTF32) GEMMs, +4 B per parameter.
+// L2 policy: the momentum deltas and the gradients are touched by nobody else until the next update, so they are
+// streamed (evict-first loads/stores) and do not push the weights — which the next bunch's forward and dX GEMMs read —
+// out of the 126 MB L2 (the three arenas of the C2 net are 176 MB).
 template <bool kHasWC>
 __global__ void __launch_bounds__(256)
 bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad, long long n4,
               float nf, float momentum, float one_minus_m_lr, float weightcost, SgdBiasRanges br,
-              float4* __restrict__ w_lo) {
+              float4* __restrict__ w_lo, int stream_delta) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 g = __ldcs(grad + i);  // gradient is dead after this read: streaming load
-    float4 d = delta[i];
+    float4 d = stream_delta ? __ldcs(delta + i) : delta[i];
     float4 x = w[i];
     float wc = weightcost;
     if (kHasWC) {
@@ -47,7 +50,8 @@ bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* 
       dv[k] = nd;
       xv[k] = __fadd_rn(nd, xv[k]);
     }
-    delta[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    if (stream_delta) __stcs(delta + i, make_float4(dv[0], dv[1], dv[2], dv[3]));
+    else delta[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
     w[i] = make_float4(xv[0], xv[1], xv[2], xv[3]);
     if (w_lo != nullptr) {
       float lo[4];

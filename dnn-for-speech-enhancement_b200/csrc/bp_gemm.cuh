@@ -67,6 +67,7 @@ struct GemmParams {
   int passes;             // 1 = single-pass TF32; 3 = split precision (3xTF32): A*B + A_lo*B + A*B_lo, where X_lo =
                           // X - trunc_tf32(X) is kept as a second fp32 array by whoever writes X (~fp32 accuracy)
   float* out_lo;          // if non-null: out_lo[...] = v - trunc_tf32(v) for every v stored to `out` (same layout)
+  unsigned long long hint_a, hint_b;  // L2 eviction-priority policy for the A / B operand loads (0 = none)
   uint32_t dbg_flags;     // measurement aids: bit 0 skip the MMAs (TMA-only), bit 1 skip the loads (MMA-only)
   long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
                           // [256..511] loads issued, [512..767] stage full seen, [768..1023] MMAs issued,
@@ -196,10 +197,12 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(&full[s]);
           } else {
             mbar_expect_tx(&full[s], STAGE_BYTES);
-            if constexpr (kAMN) tma_load_3d(sa, mapA, &full[s], 0, kb * BLOCK_K, m0 / 32);
-            else tma_load_3d(sa, mapA, &full[s], 0, m0, kb * (BLOCK_K / 32));
-            if constexpr (kBMN) tma_load_3d(sb, mapB, &full[s], 0, kb * BLOCK_K, n0 / 32);
-            else tma_load_3d(sb, mapB, &full[s], 0, n0, kb * (BLOCK_K / 32));
+            const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
+            const int b1 = kBMN ? kb * BLOCK_K : n0, b2 = kBMN ? n0 / 32 : kb * (BLOCK_K / 32);
+            if (p.hint_a) tma_load_3d_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
+            else tma_load_3d(sa, mapA, &full[s], 0, a1, a2);
+            if (p.hint_b) tma_load_3d_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
+            else tma_load_3d(sb, mapB, &full[s], 0, b1, b2);
           }
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[256 + kb] = clock64();
         }

@@ -121,6 +121,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Same with an L2 eviction-priority hint (createpolicy-encoded: kEvictLast keeps re-read operands such as the weights
+// resident, kEvictFirst marks streaming data).
+constexpr unsigned long long kEvictNormal = 0x1000000000000000ull;
+constexpr unsigned long long kEvictFirst = 0x12F0000000000000ull;
+constexpr unsigned long long kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 int c2, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+
 // One lane of a converged warp (the role loops stay warp-uniform; only the issue is predicated).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -146,6 +146,11 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
   }();
   GemmParams q = p;
   q.dbg_flags |= env_flags;
+  static const bool use_hints = [] {
+    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (!use_hints) q.hint_a = q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -575,6 +580,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     p.layer = (uint32_t)l;
     p.frame0 = frame0;
     p.passes = r->passes;
+    p.hint_a = kEvictLast;  // A = the weights: re-read by dX and by the next bunch, keep them in L2
     MapPair xmap;
     const MapPair* bmap = &ls.yprev_fwd;
     if (l == 1) {
@@ -672,6 +678,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.ldaux = lp.ldy;
     p.act = cf.activation;
     p.passes = r->passes;
+    p.hint_a = kEvictLast;  // A = the weights
     BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->num_sms, ls.w_dx, ls.d_dx, p)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
@@ -691,13 +698,18 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     const int grid = r->num_sms * 8;
     const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
     const float c1 = (1 - cf.momentum) * cf.lrate;
+    static const int sgd_stream = [] {
+      const char* e = getenv("BP_SGD_STREAM");
+      return e ? atoi(e) : 1;
+    }();
     if (cf.weightcost != 0.0f)
       bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
                                                         cf.momentum, c1, cf.weightcost, r->bias_ranges,
-                                                        (float4*)r->w_lo);
+                                                        (float4*)r->w_lo, sgd_stream);
     else
       bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
-                                                         cf.momentum, c1, 0.0f, r->bias_ranges, (float4*)r->w_lo);
+                                                         cf.momentum, c1, 0.0f, r->bias_ranges, (float4*)r->w_lo,
+                                                         sgd_stream);
     CU_TRY(cudaGetLastError());
     r->launches++;
   }
@@ -1255,10 +1267,10 @@ int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bun
     const float c1 = (1 - momentum) * lrate;
     if (weightcost != 0.0f)
       bp_sgd_kernel<true><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum, c1,
-                                            weightcost, br, nullptr);
+                                            weightcost, br, nullptr, 1);
     else
       bp_sgd_kernel<false><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum,
-                                             c1, 0.0f, br, nullptr);
+                                             c1, 0.0f, br, nullptr, 1);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(delta, d, size_t(n) * 4, cudaMemcpyDeviceToHost));
