@@ -50,6 +50,8 @@ enum Epi : int {
 
 struct GemmParams {
   int M, N, K;            // logical extents (see header comment)
+  int n_begin;            // first column of this launch (multiple of BLOCK_N): columns [n_begin, N) are computed, so a
+                          // product can be cut into column slices whose all-reduce starts while the rest computes
   float* out;             // primary output, element (m,n) at out[n*ldo + m]; may be null for EPI_FWD_OUT
   long long ldo;
   const float* bias;      // bias[m]                      (EPI_FWD_*)
@@ -143,7 +145,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
 
   const int num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_n_tiles = (p.N - p.n_begin + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_it = num_kb * (p.passes == 3 ? 3 : 1);  // pipeline iterations per tile
@@ -182,7 +184,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t % num_m_tiles) * BLOCK_M;
-      const int n0 = (t / num_m_tiles) * BLOCK_N;
+      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;
       for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
         if (kb == num_kb) { kb = 0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? &tmAlo : &tmA;   // pass 0: A*B   pass 1: A_lo*B   pass 2: A*B_lo
@@ -263,7 +265,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float sq_local = 0.0f;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t % num_m_tiles) * BLOCK_M;
-      const int n0 = (t / num_m_tiles) * BLOCK_N;
+      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
       if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();

@@ -132,7 +132,7 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
     configured_dev = dev;
   }
   const int mt = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-  const int nt = (p.N + BN - 1) / BN;
+  const int nt = (p.N - p.n_begin + BN - 1) / BN;
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   const int grid = std::min(tiles, num_sms);
@@ -255,7 +255,8 @@ struct Rank {
   int local_bunch = 0;
   int num_sms = 0;
   cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
-  int dw_bn = 128;              // N-tile of the weight-gradient GEMM (BP_DW_BN=256 for experiments)
+  int dw_bn = 128;              // N-tile of the weight-gradient GEMM
+  int ar_slices = 4;            // data-parallel: slices per layer gradient whose all-reduce is pipelined (BP_AR_SLICES)
   cudaStream_t side = nullptr;  // weight-gradient GEMMs run here, concurrently with the dX chain on `compute`
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
   cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
@@ -413,7 +414,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->local_bunch = cfg->bunchsize / cfg->world_size;
   r->num_sms = prop.multiProcessorCount;
   r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
-  if (const char* e = getenv("BP_DW_BN")) r->dw_bn = atoi(e) == 256 ? 256 : 128;
+  if (const char* e = getenv("BP_AR_SLICES")) r->ar_slices = std::max(1, atoi(e));
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -651,14 +652,26 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
                       true));
       bmap = &xmap;
     }
-    if (r->dw_bn == 256) BP_TRY((launch_gemm_bn<true, true, EPI_PLAIN, 256>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
-    else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
-    r->launches++;
-    if (r->nccl_comm) {
-      CU_TRY(cudaEventRecord(r->ev_grad, r->side));
-      CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_grad, 0));
-      NCCL_TRY(g_nccl.AllReduce(r->g + ls.off, r->g + ls.off, (size_t)ls.size, kNcclFloat32, kNcclSum, r->nccl_comm,
-                                r->comm_stream));
+    // Data-parallel ranks cut the gradient block into row slices (= column slices of the product, contiguous in the
+    // arena) so that each slice's all-reduce runs while the next slice is still being computed; only the last
+    // slice's reduction is exposed.  A single rank computes the block in one launch.
+    const int total = p.N;
+    int slices = 1;
+    if (r->nccl_comm) slices = std::max(1, std::min(r->ar_slices, (total + kBlockN - 1) / kBlockN));
+    const int per = ((total + slices - 1) / slices + kBlockN - 1) / kBlockN * kBlockN;
+    for (int b0 = 0; b0 < total; b0 += per) {
+      p.n_begin = b0;
+      p.N = std::min(total, b0 + per);
+      BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
+      r->launches++;
+      if (r->nccl_comm) {
+        float* gs = r->g + ls.off + (long long)b0 * ls.ldN;
+        const size_t cnt = (p.N == total) ? (size_t)(ls.size - (long long)b0 * ls.ldN)
+                                          : (size_t)(p.N - b0) * (size_t)ls.ldN;
+        CU_TRY(cudaEventRecord(r->ev_grad, r->side));
+        CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_grad, 0));
+        NCCL_TRY(g_nccl.AllReduce(gs, gs, cnt, kNcclFloat32, kNcclSum, r->nccl_comm, r->comm_stream));
+      }
     }
     return BP_OK;
   };
