@@ -206,6 +206,9 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     bp = importlib.import_module("dnn-for-speech-enhancement_b200")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     dist = None
     if world > 1:
         import torch
@@ -257,10 +260,12 @@ def main():
             done += k
 
     # ---- value: device-resident
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     run_resident(W)
+    if rank == 0:   # NVML initialisation can take a second: make sure the sampler is live before the timed region
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.01)
+        run_resident(W)
     launches0 = g.counters()[0]
     barrier()
     sampler.in_region = True

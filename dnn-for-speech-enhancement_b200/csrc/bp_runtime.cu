@@ -256,7 +256,11 @@ struct Rank {
   int num_sms = 0;
   cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
   int dw_bn = 128;              // N-tile of the weight-gradient GEMM
-  int ar_slices = 4;            // data-parallel: slices per layer gradient whose all-reduce is pipelined (BP_AR_SLICES)
+  int ar_slices = 1;            // data-parallel: slices per layer gradient (BP_AR_SLICES; >1 measured slower: many
+                                // small all-reduces are latency-bound)
+  int comm_sms = 0;             // data-parallel: SMs the persistent GEMMs leave free so that NCCL's kernels can run
+                                // next to them instead of behind them (BP_COMM_SMS; 16/32 measured no better: the
+                                // exposed all-reduce time is that of the last, largest layers' gradients)
   cudaStream_t side = nullptr;  // weight-gradient GEMMs run here, concurrently with the dX chain on `compute`
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
   cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
@@ -286,6 +290,7 @@ struct Rank {
   int loss_cur = 0;
   SgdBiasRanges bias_ranges{};
 
+  int gemm_sms() const { return nccl_comm ? std::max(8, num_sms - comm_sms) : num_sms; }
   int Nout() const { return cfg.layersizes[L]; }
   int K0() const { return cfg.layersizes[0]; }
 };
@@ -415,6 +420,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->num_sms = prop.multiProcessorCount;
   r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
   if (const char* e = getenv("BP_AR_SLICES")) r->ar_slices = std::max(1, atoi(e));
+  if (const char* e = getenv("BP_COMM_SMS")) r->comm_sms = std::max(0, std::min(64, atoi(e)));
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -593,7 +599,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
       p.out_lo = ls.y_lo;
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
-      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->num_sms, ls.w_fwd, *bmap, p)));
+      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p)));
     } else {
       if (train) {
         p.out = ls.d;
@@ -613,7 +619,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
           p.sqerr = sqerr;
         }
       }
-      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->num_sms, ls.w_fwd, *bmap, p)));
+      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p)));
     }
     r->launches++;
   }
@@ -662,7 +668,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     for (int b0 = 0; b0 < total; b0 += per) {
       p.n_begin = b0;
       p.N = std::min(total, b0 + per);
-      BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->num_sms, ls.d_dw, *bmap, p)));
+      BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
       r->launches++;
       if (r->nccl_comm) {
         float* gs = r->g + ls.off + (long long)b0 * ls.ldN;
@@ -692,7 +698,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.act = cf.activation;
     p.passes = r->passes;
     p.hint_a = kEvictLast;  // A = the weights
-    BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->num_sms, ls.w_dx, ls.d_dx, p)));
+    BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
     BP_TRY(launch_dw(l - 1));
