@@ -102,6 +102,83 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
   return ((1.0f - y) * y) * e;
 }
 
+// Fused epilogue math for one chunk of 32 accumulator columns [nc, nc+32) of TMEM lane (= output row) m.
+template <int kEpi>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_t (&v)[32], int m, bool m_ok, int nc,
+                                                    float bias, float& sq_local) {
+  const bool whole = nc + 32 <= p.N;  // warp-uniform: all 32 columns of the chunk are real
+  if constexpr (kEpi == EPI_PLAIN) {
+    if (m_ok) {
+      float* o = p.out + size_t(nc) * p.ldo + m;
+#pragma unroll
+      for (int j = 0; j < 32; ++j, o += p.ldo)
+        if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
+    }
+  } else if constexpr (kEpi == EPI_FWD_HID) {
+    if (m_ok) {
+      float* o = p.out + size_t(nc) * p.ldo + m;
+      const bool drop = p.drop_p > 0.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float u4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (drop)
+          philox_uniform4(p.seed_lo, p.seed_hi, uint32_t(p.frame0 + nc + j4 * 4) >> 2, uint32_t(m), p.layer,
+                          p.step, u4);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj, o += p.ldo) {
+          const int j = j4 * 4 + jj;
+          float y = act_fwd(fmaf(p.scale, __uint_as_float(v[j]), bias), p.act);
+          if (drop && u4[jj] < p.drop_p) y = 0.0f;
+          if (whole || nc + j < p.N) {
+            *o = y;
+            if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(y);
+          }
+        }
+      }
+    }
+  } else if constexpr (kEpi == EPI_FWD_OUT) {
+    if (m_ok) {
+      float tg[32];
+      if (p.aux != nullptr) {
+        const float* a = p.aux + size_t(nc) * p.ldaux + m;
+#pragma unroll
+        for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (whole || nc + j < p.N) {
+          const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
+          if (p.out2 != nullptr) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
+          if (p.aux != nullptr) {
+            const float diff = o - tg[j];
+            if (p.out != nullptr) {
+              const float dv = p.gscale * diff;
+              p.out[size_t(nc + j) * p.ldo + m] = dv;
+              if (p.out_lo != nullptr) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+            }
+            sq_local = fmaf(diff, diff, sq_local);
+          }
+        }
+      }
+    }
+  } else if constexpr (kEpi == EPI_DX) {
+    if (m_ok) {
+      float yv[32];
+      const float* a = p.aux + size_t(nc) * p.ldaux + m;
+#pragma unroll
+      for (int j = 0; j < 32; ++j, a += p.ldaux) yv[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
+      float* o = p.out + size_t(nc) * p.ldo + m;
+#pragma unroll
+      for (int j = 0; j < 32; ++j, o += p.ldo)
+        if (whole || nc + j < p.N) {
+          const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
+          *o = dv;
+          if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
+        }
+    }
+  }
+}
+
 template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -281,80 +358,10 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int nc = n0 + c * 32;
         if (nc >= p.N) break;
-        const bool whole = nc + 32 <= p.N;  // warp-uniform: all 32 columns of the chunk are real
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c * 32), v);
         tmem_ld_wait();
-        if constexpr (kEpi == EPI_PLAIN) {
-          if (m_ok) {
-            float* o = p.out + size_t(nc) * p.ldo + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j, o += p.ldo)
-              if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
-          }
-        } else if constexpr (kEpi == EPI_FWD_HID) {
-          if (m_ok) {
-            float* o = p.out + size_t(nc) * p.ldo + m;
-            const bool drop = p.drop_p > 0.0f;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float u4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-              if (drop)
-                philox_uniform4(p.seed_lo, p.seed_hi, uint32_t(p.frame0 + nc + j4 * 4) >> 2, uint32_t(m), p.layer,
-                                p.step, u4);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj, o += p.ldo) {
-                const int j = j4 * 4 + jj;
-                float y = act_fwd(fmaf(p.scale, __uint_as_float(v[j]), bias), p.act);
-                if (drop && u4[jj] < p.drop_p) y = 0.0f;
-                if (whole || nc + j < p.N) {
-                  *o = y;
-                  if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(y);
-                }
-              }
-            }
-          }
-        } else if constexpr (kEpi == EPI_FWD_OUT) {
-          if (m_ok) {
-            float tg[32];
-            if (p.aux != nullptr) {
-              const float* a = p.aux + size_t(nc) * p.ldaux + m;
-#pragma unroll
-              for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (whole || nc + j < p.N) {
-                const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
-                if (p.out2 != nullptr) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
-                if (p.aux != nullptr) {
-                  const float diff = o - tg[j];
-                  if (p.out != nullptr) {
-                    const float dv = p.gscale * diff;
-                    p.out[size_t(nc + j) * p.ldo + m] = dv;
-                    if (p.out_lo != nullptr) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
-                  }
-                  sq_local = fmaf(diff, diff, sq_local);
-                }
-              }
-            }
-          }
-        } else if constexpr (kEpi == EPI_DX) {
-          if (m_ok) {
-            float yv[32];
-            const float* a = p.aux + size_t(nc) * p.ldaux + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j, a += p.ldaux) yv[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
-            float* o = p.out + size_t(nc) * p.ldo + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j, o += p.ldo)
-              if (whole || nc + j < p.N) {
-                const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
-                *o = dv;
-                if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
-              }
-          }
-        }
+        gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local);
       }
       tc_fence_before();
       __syncwarp();

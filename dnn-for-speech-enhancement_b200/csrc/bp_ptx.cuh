@@ -135,6 +135,71 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Shared-window address of the same variable in the pair's leader CTA (even rank): clear the peer bit.
+__device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+// 3-D tiled load into MY shared memory whose completion is signalled on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// mbarrier.arrive on the same barrier in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      " .reg .b32 ra;\n"
+      " mapa.shared::cluster.u32 ra, %0, %1;\n"
+      " mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// One instruction drives both SMs' tensor cores: D[256 x N] (+)= A[256 x 8] * B[N x 8]^T, each CTA holding its 128 rows of
+// A and its N/2 columns of B in its own shared memory and its 128 rows of D in its own TMEM.  Leader CTA issues.
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " .reg .b64 da, db;\n"
+      " mov.b64 da, {%1, %2};\n"
+      " mov.b64 db, {%3, %4};\n"
+      " setp.ne.b32 p, %6, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Completion of the pair's MMAs arrives on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // One lane of a converged warp (the role loops stay warp-uniform; only the issue is predicated).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -27,6 +27,7 @@
 #include "../../include/bp_gpu.h"
 #include "bp_elementwise.cuh"
 #include "bp_gemm.cuh"
+#include "bp_gemm2.cuh"
 #include "bp_microbench.cuh"
 
 namespace {
@@ -165,11 +166,85 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
   return BP_OK;
 }
 
+// CTA-pair (cta_group::2) variant: 256 x 256 pair tiles, cluster of 2.  Same tensor maps (boxes of 128 rows/columns).
+template <bool kAMN, bool kBMN, int kEpi>
+int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi>;
+  constexpr size_t smem = gemm2_smem_bytes();
+  static thread_local int configured_dev = -1;
+  static thread_local int max_pairs = 0;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_pairs = num_sms / 2;
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(num_sms / 2 * 2);
+    qc.blockDim = dim3(GEMM_THREADS);
+    qc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) max_pairs = std::min(n, num_sms / 2);
+    else cudaGetLastError();
+    configured_dev = dev;
+  }
+  const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  const int nt = (p.N - p.n_begin + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  const int tiles = mt * nt;
+  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  static const bool use_pdl = [] {
+    const char* e = getenv("BP_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  static const bool use_hints = [] {
+    const char* e = getenv("BP_TMA_HINT");
+    return e ? atoi(e) != 0 : true;
+  }();
+  GemmParams q = p;
+  (void)use_hints;  // the pair kernel issues plain loads (cta_group::2 loads carry no cache-hint operand here)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(std::min(tiles, std::min(max_pairs, num_sms / 2)) * 2);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 2 : 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a.m, b.m, a.lo, b.lo, q));
+  return BP_OK;
+}
+
+// BP_PAIRS: 0 = never use CTA pairs, 1 = when the pair tiles fill at least ~60 % of the SM pairs (default), 2 = always.
+inline bool want_pairs(const GemmParams& p, int num_sms) {
+  static const int mode = [] {
+    const char* e = getenv("BP_PAIRS");
+    return e ? atoi(e) : 1;
+  }();
+  if (mode == 0) return false;
+  if (mode == 2) return true;
+  const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  const int nt = (p.N - p.n_begin + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  return mt * nt * 10 >= (num_sms / 2) * 6;
+}
+
 // Tile width along N.  The B-operand tensor map's box must match (kBoxN below is what make_map is called with).
 constexpr int kBlockN = 128;
 
 template <bool kAMN, bool kBMN, int kEpi>
 int launch_gemm(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
+  if (want_pairs(p, num_sms)) return launch_gemm2<kAMN, kBMN, kEpi>(st, num_sms, a, b, p);
   return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a, b, p);
 }
 
