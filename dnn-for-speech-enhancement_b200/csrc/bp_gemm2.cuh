@@ -25,25 +25,31 @@
 
 namespace bp {
 
-constexpr int GEMM2_BLOCK_N = 256;  // pair tile: 256 rows (2 x 128) x 256 columns
-constexpr int GEMM2_STAGES = 3;
+// Pair tile: 256 rows (2 x 128) x PAIR_N columns.  PAIR_N = 256: 64 KB stages x 3, shared-memory roof = tensor roof.
+// PAIR_N = 128 (for products too small to fill the machine with 256-wide pair tiles, e.g. 2048 x 1024 outputs):
+// 48 KB stages x 4, each CTA stages 64 B columns; 96 KB of shared-memory traffic per 512 pipe cycles -> 67 % roof
+// instead of the lone CTA's 50 %.
+template <int PAIR_N>
+__host__ __device__ constexpr int gemm2_stages() { return PAIR_N == 256 ? 3 : 4; }
 
+template <int PAIR_N>
 constexpr size_t gemm2_smem_bytes() {
-  return size_t(GEMM2_STAGES) * (GEMM_BLOCK_M + GEMM2_BLOCK_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
+  return size_t(gemm2_stages<PAIR_N>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
 }
 
-template <bool kAMN, bool kBMN, int kEpi>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                 const GemmParams p) {
-  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = GEMM2_BLOCK_N, kStages = GEMM2_STAGES;
+  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = PAIR_N, kStages = gemm2_stages<PAIR_N>();
+  static_assert(PAIR_N == 128 || PAIR_N == 256, "PAIR_N");
   constexpr int HALF_N = BLOCK_N / 2;                    // B columns staged by each CTA
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 4;    // my 128 rows of A
   constexpr uint32_t B_BYTES = HALF_N * BLOCK_K * 4;     // my half of B
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
-  static_assert(TMEM_COLS == 512, "TMEM");
+  static_assert(TMEM_COLS <= 512, "TMEM");
   constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
   constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (kLayoutSW128Base32 << 29);
   constexpr uint32_t kDescLoK = (16u >> 4) << 16;

@@ -167,10 +167,10 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
 }
 
 // CTA-pair (cta_group::2) variant: 256 x 256 pair tiles, cluster of 2.  Same tensor maps (boxes of 128 rows/columns).
-template <bool kAMN, bool kBMN, int kEpi>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
 int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi>;
-  constexpr size_t smem = gemm2_smem_bytes();
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N>;
+  constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
   static thread_local int configured_dev = -1;
   static thread_local int max_pairs = 0;
   int dev = 0;
@@ -195,7 +195,7 @@ int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& 
     configured_dev = dev;
   }
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const int nt = (p.N - p.n_begin + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  const int nt = (p.N - p.n_begin + PAIR_N - 1) / PAIR_N;
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   static const bool use_pdl = [] {
@@ -226,25 +226,35 @@ int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& 
   return BP_OK;
 }
 
-// BP_PAIRS: 0 = never use CTA pairs, 1 = when the pair tiles fill at least ~60 % of the SM pairs (default), 2 = always.
-inline bool want_pairs(const GemmParams& p, int num_sms) {
+// Kernel choice per product.  BP_PAIRS: 0 = lone CTAs only, 1 = automatic (default), 2 = 256-wide pairs always,
+// 3 = 128-wide pairs whenever the narrow B map exists.  Automatic: 256 x 256 pair tiles if they fill >= 60 % of the SM
+// pairs, else 256 x 128 pair tiles under the same condition, else 128 x 128 tiles on lone CTAs.
+inline int pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
   static const int mode = [] {
     const char* e = getenv("BP_PAIRS");
     return e ? atoi(e) : 1;
   }();
-  if (mode == 0) return false;
-  if (mode == 2) return true;
+  if (mode == 0) return 0;
+  if (mode == 2) return 256;
+  if (mode == 3) return have_b64 ? 128 : 0;
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const int nt = (p.N - p.n_begin + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
-  return mt * nt * 10 >= (num_sms / 2) * 6;
+  const int n = p.N - p.n_begin;
+  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return 256;
+  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return 128;
+  return 0;
 }
 
 // Tile width along N.  The B-operand tensor map's box must match (kBoxN below is what make_map is called with).
 constexpr int kBlockN = 128;
 
+// b = B operand map with 128-wide boxes (lone CTAs and 256-wide pairs); b64 = the same operand with 64-wide boxes
+// (128-wide pairs: each CTA stages 64 B columns), or null.
 template <bool kAMN, bool kBMN, int kEpi>
-int launch_gemm(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  if (want_pairs(p, num_sms)) return launch_gemm2<kAMN, kBMN, kEpi>(st, num_sms, a, b, p);
+int launch_gemm(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p,
+                const MapPair* b64 = nullptr) {
+  const int k = pick_kernel(p, num_sms, b64 != nullptr);
+  if (k == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256>(st, num_sms, a, b, p);
+  if (k == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128>(st, num_sms, a, *b64, p);
   return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a, b, p);
 }
 
@@ -306,6 +316,8 @@ struct LayerState {
   MapPair w_fwd;       // W^T as MN-major A: {N, K}, box {32,32}
   MapPair w_dx;        // W as K-major A:    {N, K}, box {32,128}
   MapPair yprev_fwd;   // Y_{l-1} as K-major B (l >= 2): {K, rows}, box {32,kBlockN}
+  MapPair yprev_fwd64; // same, 64-row boxes (128-wide CTA pairs)
+  MapPair d_dx64;      // D_l as K-major B, 64-row boxes
   MapPair yprev_dw;    // Y_{l-1}^T as MN-major B (l >= 2): {K+1, bunch}, box {32,32}
   MapPair d_dx;        // D_l as K-major B: {N, bunch}, box {32,kBlockN}
   MapPair d_dw;        // D_l^T as MN-major A: {N, bunch}, box {32,32}
@@ -574,10 +586,12 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       BP_TRY(make_map(&ls.w_fwd, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, true));
       BP_TRY(make_map(&ls.w_dx, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
       BP_TRY(make_map(&ls.d_dx, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
+      BP_TRY(make_map(&ls.d_dx64, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, 64, false));
       BP_TRY(make_map(&ls.d_dw, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, GEMM_BLOCK_M, true));
       if (l >= 2) {
         LayerState& lp = r->layer[l - 1];
         BP_TRY(make_map(&ls.yprev_fwd, lp.y, lp.y_lo, ls.K, rows, lp.ldy, kBlockN, false));
+        BP_TRY(make_map(&ls.yprev_fwd64, lp.y, lp.y_lo, ls.K, rows, lp.ldy, 64, false));
         BP_TRY(make_map(&ls.yprev_dw, lp.y, lp.y_lo, ls.K + 1, r->local_bunch, lp.ldy, r->dw_bn, true));
       }
     }
@@ -663,18 +677,22 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     p.frame0 = frame0;
     p.passes = r->passes;
     p.hint_a = kEvictLast;  // A = the weights: re-read by dX and by the next bunch, keep them in L2
-    MapPair xmap;
+    MapPair xmap, xmap64;
     const MapPair* bmap = &ls.yprev_fwd;
+    const MapPair* bmap64 = &ls.yprev_fwd64;
     if (l == 1) {
-      BP_TRY(make_map(&xmap, xb, c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr, ls.K, n, r->ldx, kBlockN, false));
+      const float* xlo = c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr;
+      BP_TRY(make_map(&xmap, xb, xlo, ls.K, n, r->ldx, kBlockN, false));
+      BP_TRY(make_map(&xmap64, xb, xlo, ls.K, n, r->ldx, 64, false));
       bmap = &xmap;
+      bmap64 = &xmap64;
     }
     if (l < r->L) {
       p.out = ls.y;
       p.out_lo = ls.y_lo;
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
-      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p)));
+      BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
     } else {
       if (train) {
         p.out = ls.d;
@@ -694,7 +712,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
           p.sqerr = sqerr;
         }
       }
-      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p)));
+      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
     }
     r->launches++;
   }
@@ -773,7 +791,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.act = cf.activation;
     p.passes = r->passes;
     p.hint_a = kEvictLast;  // A = the weights
-    BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p)));
+    BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
     BP_TRY(launch_dw(l - 1));
@@ -1249,6 +1267,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     MapPair ma, mb;
     BP_TRY(make_map(&ma, dA, dAlo, a_cols, a_rows, dlda, GEMM_BLOCK_M, amn));
     BP_TRY(make_map(&mb, dB, dBlo, b_cols, b_rows, dldb, kBlockN, bmn));
+    MapPair mb64;
+    BP_TRY(make_map(&mb64, dB, dBlo, b_cols, b_rows, dldb, 64, bmn));
     GemmParams p{};
     p.passes = math_mode == BP_MATH_3XTF32 ? 3 : 1;
     p.M = M; p.N = N; p.K = K;
@@ -1272,10 +1292,10 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is an untimed warm-up when reps > 1
       if (rep == (reps > 1 ? 1 : 0)) CU_TRY(cudaEventRecord(e0, st));
       if (reps == 1 && rep == 1) break;
-      if (kind == 0) BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p)));
-      else if (kind == 3) BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p)));
-      else if (kind == 1) BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p)));
-      else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p)));
+      if (kind == 0) BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p, &mb64)));
+      else if (kind == 3) BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p, &mb64)));
+      else if (kind == 1) BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p, &mb64)));
+      else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p, &mb64)));
     }
     CU_TRY(cudaEventRecord(e1, st));
     CU_TRY(cudaStreamSynchronize(st));
