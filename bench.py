@@ -330,7 +330,7 @@ def main():
     peaks, peak_src = load_peaks()
     traffic = {}
     try:  # DRAM bytes of the committed ncu --set full capture (profiles/), per bunch / per launch
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
     except Exception:
         pass
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
