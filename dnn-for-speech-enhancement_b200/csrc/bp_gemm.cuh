@@ -50,6 +50,9 @@ enum Epi : int {
 
 struct GemmParams {
   int M, N, K;            // logical extents (see header comment)
+  int k_splits;           // >1 (EPI_PLAIN, lone-CTA kernel only): the K range is cut into k_splits slices, slice s writes
+                          // its partial product to out + s*split_stride; a finishing kernel adds the slices in order
+  long long split_stride; // floats between partial-product planes
   int n_begin;            // first column of this launch (multiple of BLOCK_N): columns [n_begin, N) are computed, so a
                           // product can be cut into column slices whose all-reduce starts while the rest computes
   float* out;             // primary output, element (m,n) at out[n*ldo + m]; may be null for EPI_FWD_OUT
@@ -105,11 +108,11 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
 // Fused epilogue math for one chunk of 32 accumulator columns [nc, nc+32) of TMEM lane (= output row) m.
 template <int kEpi>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_t (&v)[32], int m, bool m_ok, int nc,
-                                                    float bias, float& sq_local) {
+                                                    float bias, float& sq_local, size_t plane_off = 0) {
   const bool whole = nc + 32 <= p.N;  // warp-uniform: all 32 columns of the chunk are real
   if constexpr (kEpi == EPI_PLAIN) {
     if (m_ok) {
-      float* o = p.out + size_t(nc) * p.ldo + m;
+      float* o = p.out + plane_off + size_t(nc) * p.ldo + m;
 #pragma unroll
       for (int j = 0; j < 32; ++j, o += p.ldo)
         if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
@@ -225,7 +228,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_n_tiles = (p.N - p.n_begin + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int num_it = num_kb * (p.passes == 3 ? 3 : 1);  // pipeline iterations per tile
+  const int num_passes = p.passes == 3 ? 3 : 1;
+  // split-K: work item t = (tile, k-slice); slice s covers k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per))
+  const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int kb_per = (num_kb + k_splits - 1) / k_splits;
+  const int num_items = num_tiles * k_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -259,11 +266,15 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
     int s = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % num_m_tiles) * BLOCK_M;
-      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;
-      for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
-        if (kb == num_kb) { kb = 0; ++pass; }
+    for (int t = blockIdx.x; t < num_items; t += gridDim.x) {
+      const int tile = t % num_tiles;
+      const int m0 = (tile % num_m_tiles) * BLOCK_M;
+      const int n0 = p.n_begin + (tile / num_m_tiles) * BLOCK_N;
+      const int kb0 = (t / num_tiles) * kb_per;
+      const int kb1 = min(num_kb, kb0 + kb_per);
+      const int num_it = (kb1 - kb0) * num_passes;  // pipeline iterations of this work item
+      for (int it = 0, kb = kb0, pass = 0; it < num_it; ++it, ++kb) {
+        if (kb == kb1) { kb = kb0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? &tmAlo : &tmA;   // pass 0: A*B   pass 1: A_lo*B   pass 2: A*B_lo
         const CUtensorMap* mapB = pass == 2 ? &tmBlo : &tmB;
         if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);  // ONE lane polls (see header)
@@ -296,7 +307,9 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_items; t += gridDim.x) {
+      const int kb0 = (t / num_tiles) * kb_per;
+      const int num_it = (min(num_kb, kb0 + kb_per) - kb0) * num_passes;
       if (lane == kPollLane) mbar_wait(&tempty[as], aph ^ 1u);
       __syncwarp();
       tc_fence_after();
@@ -340,9 +353,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     float sq_local = 0.0f;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % num_m_tiles) * BLOCK_M;
-      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;
+    for (int t = blockIdx.x; t < num_items; t += gridDim.x) {
+      const int tile = t % num_tiles;
+      const int m0 = (tile % num_m_tiles) * BLOCK_M;
+      const int n0 = p.n_begin + (tile / num_m_tiles) * BLOCK_N;
+      const size_t plane_off = size_t(t / num_tiles) * size_t(p.split_stride);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
       if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
@@ -361,7 +376,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c * 32), v);
         tmem_ld_wait();
-        gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local);
+        gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local, plane_off);
       }
       tc_fence_before();
       __syncwarp();
@@ -385,6 +400,46 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Finisher of a split-K output-layer product: adds the k_splits partial planes (in slice order, so the result does not
+// depend on scheduling) and applies the EPI_FWD_OUT epilogue.  ws plane s holds element (m,n) at ws[s*stride+n*ldw+m].
+// One thread per (n, m) with m contiguous: every access is coalesced; ~1.2 MB per plane at the C2 shape.
+__global__ void __launch_bounds__(256)
+bp_out_finish_kernel(const float* __restrict__ ws, long long ldw, const GemmParams p) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = static_cast<int>(idx / ldw);
+  const int m = static_cast<int>(idx - static_cast<long long>(n) * ldw);
+  float sq_local = 0.0f;
+  if (n < p.N && m < p.M) {
+    const float* w = ws + static_cast<size_t>(n) * ldw + m;
+    float acc = w[0];
+    for (int s = 1; s < p.k_splits; ++s) acc += w[static_cast<size_t>(s) * p.split_stride];
+    const float o = fmaf(p.scale, acc, __ldg(p.bias + m));
+    if (p.out2 != nullptr) p.out2[static_cast<size_t>(n) * p.ldo2 + m] = o;
+    if (p.aux != nullptr) {
+      const float diff = o - __ldg(p.aux + static_cast<size_t>(n) * p.ldaux + m);
+      if (p.out != nullptr) {
+        const float dv = p.gscale * diff;
+        p.out[static_cast<size_t>(n) * p.ldo + m] = dv;
+        if (p.out_lo != nullptr) p.out_lo[static_cast<size_t>(n) * p.ldo + m] = tf32_lo(dv);
+      }
+      sq_local = diff * diff;
+    }
+  }
+  if (p.sqerr != nullptr) {
+    double sq = static_cast<double>(sq_local);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    __shared__ double warp_sum[8];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < 8; ++i) tot += warp_sum[i];
+      if (tot != 0.0) atomicAdd(p.sqerr, tot);
+    }
   }
 }
 

@@ -136,7 +136,8 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
   const int nt = (p.N - p.n_begin + BN - 1) / BN;
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  const int grid = std::min(tiles, num_sms);
+  if (p.k_splits > 1 && kEpi != EPI_PLAIN) return fail(BP_EINVAL, "gemm: split-K needs the plain epilogue");
+  const int grid = std::min(tiles * std::max(1, p.k_splits), num_sms);
   static const uint32_t env_flags = [] {
     const char* e = getenv("BP_GEMM_FLAGS");  // measurement aid, see GemmParams::dbg_flags
     return e ? (uint32_t)atoi(e) : 0u;
@@ -246,6 +247,7 @@ inline int pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
 
 // Tile width along N.  The B-operand tensor map's box must match (kBoxN below is what make_map is called with).
 constexpr int kBlockN = 128;
+constexpr int kMaxSplits = 8;  // split-K planes of the output-layer product (see out_layer_splits)
 
 // b = B operand map with 128-wide boxes (lone CTAs and 256-wide pairs); b64 = the same operand with 64-wide boxes
 // (128-wide pairs: each CTA stages 64 B columns), or null.
@@ -362,6 +364,7 @@ struct Rank {
   float* out_dev = nullptr;
   long long out_cap_rows = 0;
   double* sqerr_dev = nullptr;
+  float* splitk_ws = nullptr;  // kMaxSplits partial planes of the output-layer product (bunchsize x ldN_out each)
   void* nccl_comm = nullptr;
   uint64_t launches = 0, bunches = 0;
   uint32_t step = 0;
@@ -434,6 +437,7 @@ int rank_destroy(Rank* r) {
   cudaFree(r->g);
   cudaFree(r->out_dev);
   cudaFree(r->sqerr_dev);
+  cudaFree(r->splitk_ws);
   for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side})
     if (e) cudaEventDestroy(e);
   for (auto e : r->ev_d)
@@ -554,6 +558,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
     CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
     CU_TRY(cudaMalloc(&r->sqerr_dev, sizeof(double)));
+    CU_TRY(cudaMalloc(&r->splitk_ws, sizeof(float) * kMaxSplits * (size_t)cfg->bunchsize * r->layer[r->L].ldN));
 
     r->ldx = round_up(r->K0() + 1, 32);
     const long long rows = cfg->bunchsize;  // activation buffers hold a full (global) bunch so CV can use it
@@ -637,6 +642,22 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
   return BP_OK;
 }
 
+// Number of K slices for the output-layer product (1 = no split).  BP_SPLITK: 0 = never, N>1 = force N, unset = auto:
+// as many slices as idle SMs allow, each at least 4 k-blocks deep, at most kMaxSplits.
+inline int out_layer_splits(const GemmParams& p, int num_sms) {
+  static const int mode = [] {
+    const char* e = getenv("BP_SPLITK");
+    return e ? atoi(e) : -1;
+  }();
+  if (mode == 0) return 1;
+  const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + kBlockN - 1) / kBlockN);
+  const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  int s = mode > 1 ? mode : std::min(num_sms / std::max(1, tiles), num_kb / 4);
+  s = std::max(1, std::min({s, kMaxSplits, num_kb}));
+  const int per = (num_kb + s - 1) / s;
+  return (num_kb + per - 1) / per;  // every slice non-empty
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // Forward over rows [f0, f0+n) of the resident chunk.  train=true: masks + D_L; train=false: keep-scaling (CV).
 int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, long long ldo2, double* sqerr) {
@@ -712,7 +733,26 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
           p.sqerr = sqerr;
         }
       }
-      BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
+      // The 257-wide output layer makes only ceil(257/128) x ceil(n/128) tiles (24 at bunch 1024) with a long K loop:
+      // cut K into slices so the product covers the machine, then add the slices and apply the epilogue in a finisher.
+      const int splits = r->splitk_ws ? out_layer_splits(p, r->gemm_sms()) : 1;
+      if (splits > 1) {
+        GemmParams g = p;
+        g.k_splits = splits;
+        g.split_stride = (long long)n * ls.ldN;
+        g.out = r->splitk_ws;
+        g.out_lo = nullptr;
+        g.ldo = ls.ldN;
+        BP_TRY((launch_gemm_bn<true, false, EPI_PLAIN, kBlockN>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, g)));
+        r->launches++;
+        p.k_splits = splits;
+        p.split_stride = g.split_stride;
+        const long long cells = (long long)n * ls.ldN;
+        bp_out_finish_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, r->compute>>>(r->splitk_ws, ls.ldN, p);
+        CU_TRY(cudaGetLastError());
+      } else {
+        BP_TRY((launch_gemm<true, false, EPI_FWD_OUT>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
+      }
     }
     r->launches++;
   }

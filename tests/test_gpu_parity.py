@@ -156,6 +156,28 @@ def test_train_matches_oracle(bp, oracle, act):
     g.close()
 
 
+def test_split_k_output_layer_matches_oracle(bp, oracle):
+    """A wide last hidden layer makes the runtime cut the output product's K range into slices
+    (bp_runtime.cu out_layer_splits) and finish it in bp_out_finish_kernel: train, loss, CV and forward must still
+    agree with the oracle (BP_GPU.cu:560-575 / kernSubClean DevFunc.cu:263)."""
+    sizes = [75, 600, 33]   # 10 k-blocks of 64 -> 2 slices
+    x, t = oracle.synth_data(4 * 64 + 9, sizes[0], sizes[-1], seed=33)
+    kw = dict(lrate=0.5, momentum=0.9, weightcost=0.0)
+    o_tf, g = make_pair(bp, oracle, sizes, 64, 1, **kw)
+    g.train(x.shape[0], x, t)
+    o_tf.train(x.shape[0], x, t)
+    ws, bs = g.returnWeights()
+    for l in range(1, len(sizes)):
+        assert_close(ws[l], o_tf.w[l], TOL_TF32, f"split-K W{l}")
+        assert_close(bs[l], o_tf.b[l], 2 * TOL_TF32, f"split-K b{l}")
+    out = g.forward(x.shape[0], x)
+    assert_close(out, o_tf.forward(x), TOL_TF32, "split-K forward")
+    cv = g.CrossValid(x.shape[0], x, t)
+    ref = o_tf.crossvalid(x, t)
+    assert abs(cv - ref) <= 2e-3 * abs(ref), (cv, ref)
+    g.close()
+
+
 def test_3xtf32_training_matches_literal_fp32_oracle(bp, oracle):
     """BP_MATH_3XTF32 against the literal-fp32 oracle (= the reference's cuBLAS-FP32 arithmetic) at fp32-class
     tolerance: 1e-4 * rms on the weights, 5e-3 relative Frobenius on the update (ReLU' flips, see assert_fro)."""
