@@ -36,6 +36,29 @@ class BpConfig(C.Structure):
                 ("math_mode", C.c_int), ("seed", C.c_uint64)]
 
 
+class BpRawChunk(C.Structure):
+    """struct bp_raw_chunk of include/bp_gpu.h."""
+    _fields_ = [("fea_dim", C.c_int), ("fea_context", C.c_int), ("targ_offset", C.c_int), ("nat", C.c_int),
+                ("n_records", C.c_int), ("n_samples", C.c_int), ("fea_records", C.c_void_p),
+                ("targ_records", C.c_void_p), ("mean", _fp), ("inv_std", _fp), ("sample_frame", C.POINTER(C.c_int)),
+                ("sample_seg", C.POINTER(C.c_int)), ("sample_row", C.POINTER(C.c_int))]
+
+
+class RawChunk:
+    """One chunk for the device-side reader: raw big-endian Pfile records + the sample table (bp_raw_chunk)."""
+
+    def __init__(self, fea_dim, fea_context, targ_offset, nat, fea_records, targ_records, mean, inv_std,
+                 sample_frame, sample_seg=None, sample_row=None):
+        self.fea_dim, self.fea_context, self.targ_offset, self.nat = int(fea_dim), int(fea_context), int(targ_offset), int(nat)
+        self.fea_records = np.ascontiguousarray(fea_records).view(np.uint32).reshape(-1, self.fea_dim + 2)
+        self.n_records = self.fea_records.shape[0]
+        self.targ_records = None if targ_records is None else np.ascontiguousarray(targ_records).view(np.uint32)
+        self.mean, self.inv_std = mean, inv_std
+        self.sample_frame = np.ascontiguousarray(sample_frame, dtype=np.int32)
+        self.sample_seg = self.sample_frame if sample_seg is None else np.ascontiguousarray(sample_seg, dtype=np.int32)
+        self.sample_row = None if sample_row is None else np.ascontiguousarray(sample_row, dtype=np.int32)
+
+
 class BpError(RuntimeError):
     pass
 
@@ -66,6 +89,10 @@ def load_library() -> C.CDLL:
     lib.bp_train_resident.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bp_forward_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.POINTER(C.c_double)]
     lib.bp_sync.argtypes = [C.c_void_p]
+    lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
+    lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
+    lib.bp_crossvalid_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp, _fp]
+    lib.bp_download_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp]
     lib.bp_host_alloc.argtypes = [C.c_size_t]
     lib.bp_host_alloc.restype = C.c_void_p
     lib.bp_host_free.argtypes = [C.c_void_p]
@@ -233,6 +260,51 @@ class BP_GPU:
                                        else _as_f32(targ))
         _check(load_library().bp_upload_chunk(self._h, int(n_frames), _ptr(x), _ptr(t)), "bp_upload_chunk")
 
+    def _raw_chunk(self, raw: "RawChunk"):
+        rc = BpRawChunk()
+        keep = []
+
+        def ptr(a, dtype, ctype):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data_as(ctype)
+
+        rc.fea_dim, rc.fea_context, rc.targ_offset, rc.nat = raw.fea_dim, raw.fea_context, raw.targ_offset, raw.nat
+        rc.n_records, rc.n_samples = raw.n_records, len(raw.sample_frame)
+        rc.fea_records = ptr(raw.fea_records, np.uint32, C.c_void_p)
+        rc.targ_records = ptr(raw.targ_records, np.uint32, C.c_void_p)
+        rc.mean = ptr(raw.mean, np.float32, _fp)
+        rc.inv_std = ptr(raw.inv_std, np.float32, _fp)
+        rc.sample_frame = ptr(raw.sample_frame, np.int32, C.POINTER(C.c_int))
+        rc.sample_seg = ptr(raw.sample_seg, np.int32, C.POINTER(C.c_int))
+        rc.sample_row = ptr(raw.sample_row, np.int32, C.POINTER(C.c_int))
+        return rc, keep
+
+    def upload_raw_chunk(self, raw: "RawChunk") -> None:
+        """Device-side reader: ship the chunk's Pfile records + sample table, assemble the samples on the GPU."""
+        rc, _keep = self._raw_chunk(raw)
+        _check(load_library().bp_upload_raw_chunk(self._h, C.byref(rc)), "bp_upload_raw_chunk")
+
+    def train_raw(self, raw: "RawChunk") -> None:
+        rc, _keep = self._raw_chunk(raw)
+        _check(load_library().bp_train_raw(self._h, C.byref(rc)), "bp_train_raw")
+
+    def crossvalid_raw(self, raw: "RawChunk", want_out: bool = False):
+        rc, _keep = self._raw_chunk(raw)
+        out = np.empty((len(raw.sample_frame), self.layersizes[-1]), dtype=np.float32) if want_out else None
+        sq = C.c_float(0)
+        _check(load_library().bp_crossvalid_raw(self._h, C.byref(rc), C.byref(sq), _ptr(out)), "bp_crossvalid_raw")
+        return float(sq.value), out
+
+    def download_chunk(self, first_row: int, n_rows: int, want_targ: bool = True):
+        x = np.empty((n_rows, self.layersizes[0]), dtype=np.float32)
+        t = np.empty((n_rows, self.layersizes[-1]), dtype=np.float32) if want_targ else None
+        _check(load_library().bp_download_chunk(self._h, int(first_row), int(n_rows), _ptr(x), _ptr(t)),
+               "bp_download_chunk")
+        return x, t
+
     def train_resident(self, first_bunch: int, n_bunches: int) -> None:
         _check(load_library().bp_train_resident(self._h, int(first_bunch), int(n_bunches)), "bp_train_resident")
 
@@ -266,7 +338,7 @@ class BP_GPU:
         ms = (C.c_float * 6)()
         n = C.c_uint64(0)
         _check(load_library().bp_get_profile(self._h, ms, C.byref(n)), "bp_get_profile")
-        names = ["fwd", "dx", "dw", "sgd", "allreduce_wait", "input_dropout"]
+        names = ["fwd", "dx", "dw", "sgd", "allreduce_wait", "sgd_upper"]
         return {k: float(v) for k, v in zip(names, ms)}, int(n.value)
 
     def train_losses(self, age: int = 0, max_n: int = 4096) -> np.ndarray:

@@ -25,11 +25,13 @@ struct SgdBiasRanges {
 // out of the 126 MB L2 (the three arenas of the C2 net are 176 MB).
 template <bool kHasWC>
 __global__ void __launch_bounds__(256)
-bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad, long long n4,
-              float nf, float momentum, float one_minus_m_lr, float weightcost, SgdBiasRanges br,
+bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad, long long begin4,
+              long long n4, float nf, float momentum, float one_minus_m_lr, float weightcost, SgdBiasRanges br,
               float4* __restrict__ w_lo, int stream_delta) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  // float4 elements [begin4, n4) of the arena: the update may be issued in two parts (upper layers early, see
+  // train_bunch), with the bias ranges staying absolute
+  for (long long i = begin4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 g = __ldcs(grad + i);  // gradient is dead after this read: streaming load
     float4 d = stream_delta ? __ldcs(delta + i) : delta[i];
     float4 x = w[i];

@@ -29,6 +29,7 @@
 #include "bp_gemm.cuh"
 #include "bp_gemm2.cuh"
 #include "bp_microbench.cuh"
+#include "bp_splice.cuh"
 
 namespace {
 
@@ -352,6 +353,7 @@ struct Rank {
                                 // exposed all-reduce time is that of the last, largest layers' gradients)
   cudaStream_t side = nullptr;  // weight-gradient GEMMs run here, concurrently with the dX chain on `compute`
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_upper = nullptr, ev_comm_upper = nullptr;  // dW / all-reduce of layers >= 2 complete
   cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
   float *w = nullptr, *dw = nullptr, *g = nullptr;
   float* w_lo = nullptr;   // split-precision low part of the weights (3xTF32 mode only)
@@ -364,13 +366,19 @@ struct Rank {
   float* out_dev = nullptr;
   long long out_cap_rows = 0;
   double* sqerr_dev = nullptr;
+  // device staging of a raw chunk (bp_upload_raw_chunk): Pfile records, sample table, norm vectors
+  uint32_t* raw_fea = nullptr;
+  uint32_t* raw_targ = nullptr;
+  int* raw_tab = nullptr;
+  float* raw_norm = nullptr;
+  size_t raw_fea_cap = 0, raw_targ_cap = 0, raw_tab_cap = 0, raw_norm_cap = 0;  // in elements
   float* splitk_ws = nullptr;  // kMaxSplits partial planes of the output-layer product (bunchsize x ldN_out each)
   void* nccl_comm = nullptr;
   uint64_t launches = 0, bunches = 0;
   uint32_t step = 0;
   bool profiling = false;
   static constexpr int kProfCap = 64;        // profiled bunches kept (ring)
-  std::vector<cudaEvent_t> pev;              // 6 events per profiled bunch, no host sync while recording
+  std::vector<cudaEvent_t> pev;              // 7 events per profiled bunch, no host sync while recording
   uint64_t prof_cnt = 0;
   // per-bunch sum of squared output error of the two most recent train calls (ring), so that a caller can read
   // call i-1's losses while call i computes (no compute-stream sync on the reading path)
@@ -438,7 +446,11 @@ int rank_destroy(Rank* r) {
   cudaFree(r->out_dev);
   cudaFree(r->sqerr_dev);
   cudaFree(r->splitk_ws);
-  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side})
+  cudaFree(r->raw_fea);
+  cudaFree(r->raw_targ);
+  cudaFree(r->raw_tab);
+  cudaFree(r->raw_norm);
+  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side, r->ev_upper, r->ev_comm_upper})
     if (e) cudaEventDestroy(e);
   for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
@@ -518,6 +530,8 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_side, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_upper, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_comm_upper, cudaEventDisableTiming));
     for (auto& e : r->ev_d) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&r->ev_t0));
     CU_TRY(cudaEventCreate(&r->ev_t1));
@@ -529,7 +543,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       CU_TRY(cudaEventCreateWithFlags(&c.consumed, cudaEventDisableTiming));
     }
     for (auto& e : r->loss_done) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    r->pev.assign(6 * Rank::kProfCap, nullptr);
+    r->pev.assign(7 * Rank::kProfCap, nullptr);
     for (auto& e : r->pev) CU_TRY(cudaEventCreate(&e));
 
     long long off = 0;
@@ -639,6 +653,91 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
   CU_TRY(cudaStreamWaitEvent(r->compute, r->passes == 3 ? c.split_done : c.uploaded, 0));
   // The caller may overwrite its buffers as soon as we return (BP_GPU::train semantics): wait for the DMA only.
   CU_TRY(cudaEventSynchronize(c.uploaded));
+  return BP_OK;
+}
+
+// Raw-chunk upload: the records travel as they lie in the Pfile, the samples are assembled by bp_splice_kernel.
+template <typename T>
+int grow_dev(Rank* r, T** ptr, size_t* cap, size_t need) {
+  if (need <= *cap) return BP_OK;
+  CU_TRY(cudaStreamSynchronize(r->copy));  // the previous splice may still be reading the old block
+  if (*ptr) CU_TRY(cudaFree(*ptr));
+  *ptr = nullptr;
+  *cap = 0;
+  CU_TRY(cudaMalloc(ptr, sizeof(T) * need));
+  *cap = need;
+  return BP_OK;
+}
+
+int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  // all_rows: this rank assembles every sample (cross-validation / decode run on one device, BP_GPU.cu:440-441)
+  const int G = all_rows ? 1 : r->cfg.world_size, B = r->cfg.bunchsize, lb = r->local_bunch;
+  const int full_rows = (rc->n_samples / B) * B;
+  const int rows = G == 1 ? rc->n_samples : (rc->n_samples / B) * lb;
+  if (rows <= 0) return fail(BP_EINVAL, "upload_raw: chunk of %d samples has no full bunch of %d", rc->n_samples, B);
+  const int nbuf = r->cur ^ 1;
+  ChunkBuf& c = r->chunk[nbuf];
+  BP_TRY(ensure_chunk(r, c, rows));
+  const int out_dim = r->Nout();
+  const size_t fea_words = (size_t)rc->n_records * (rc->fea_dim + 2);
+  const size_t targ_words = rc->targ_records ? (size_t)rc->n_records * (out_dim + 2) : 0;
+  BP_TRY(grow_dev(r, &r->raw_fea, &r->raw_fea_cap, fea_words));
+  if (targ_words) BP_TRY(grow_dev(r, &r->raw_targ, &r->raw_targ_cap, targ_words));
+  BP_TRY(grow_dev(r, &r->raw_tab, &r->raw_tab_cap, (size_t)3 * rc->n_samples));
+  BP_TRY(grow_dev(r, &r->raw_norm, &r->raw_norm_cap, (size_t)2 * rc->fea_dim));
+  if (c.consumed_valid) CU_TRY(cudaStreamWaitEvent(r->copy, c.consumed, 0));
+  const size_t ns = (size_t)rc->n_samples;
+  CU_TRY(cudaMemcpyAsync(r->raw_fea, rc->fea_records, fea_words * 4, cudaMemcpyHostToDevice, r->copy));
+  if (targ_words)
+    CU_TRY(cudaMemcpyAsync(r->raw_targ, rc->targ_records, targ_words * 4, cudaMemcpyHostToDevice, r->copy));
+  CU_TRY(cudaMemcpyAsync(r->raw_tab, rc->sample_frame, ns * 4, cudaMemcpyHostToDevice, r->copy));
+  if (rc->nat) CU_TRY(cudaMemcpyAsync(r->raw_tab + ns, rc->sample_seg, ns * 4, cudaMemcpyHostToDevice, r->copy));
+  if (rc->sample_row)
+    CU_TRY(cudaMemcpyAsync(r->raw_tab + 2 * ns, rc->sample_row, ns * 4, cudaMemcpyHostToDevice, r->copy));
+  CU_TRY(cudaMemcpyAsync(r->raw_norm, rc->mean, (size_t)rc->fea_dim * 4, cudaMemcpyHostToDevice, r->copy));
+  CU_TRY(cudaMemcpyAsync(r->raw_norm + rc->fea_dim, rc->inv_std, (size_t)rc->fea_dim * 4, cudaMemcpyHostToDevice,
+                         r->copy));
+  CU_TRY(cudaEventRecord(c.uploaded, r->copy));  // host buffers are consumed here
+  SpliceParams sp{};
+  sp.fea = r->raw_fea;
+  sp.targ = targ_words ? r->raw_targ : nullptr;
+  sp.mean = r->raw_norm;
+  sp.inv_std = r->raw_norm + rc->fea_dim;
+  sp.sample_frame = r->raw_tab;
+  sp.sample_seg = r->raw_tab + ns;
+  sp.sample_row = rc->sample_row ? r->raw_tab + 2 * ns : nullptr;
+  sp.dim = rc->fea_dim;
+  sp.ctx = rc->fea_context;
+  sp.nat = rc->nat ? 1 : 0;
+  sp.targ_offset = rc->targ_offset;
+  sp.out_dim = out_dim;
+  sp.n_records = rc->n_records;
+  sp.n_samples = rc->n_samples;
+  sp.x = c.x;
+  sp.ldx = r->ldx;
+  sp.t = c.t;
+  sp.world = G;
+  sp.rank = r->cfg.rank;
+  sp.B = B;
+  sp.lb = lb;
+  sp.full_rows = full_rows;
+  const int grid = std::min(rc->n_samples, r->num_sms * 16);
+  bp_splice_kernel<<<grid, 256, 0, r->copy>>>(sp);
+  CU_TRY(cudaGetLastError());
+  r->launches++;
+  if (r->passes == 3) {
+    bp_split_lo_kernel<<<r->num_sms * 8, 256, 0, r->copy>>>((const float4*)c.x, (float4*)c.x_lo,
+                                                            (long long)rows * r->ldx / 4);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+  }
+  CU_TRY(cudaEventRecord(c.split_done, r->copy));  // "rows assembled"
+  c.rows = rows;
+  c.has_targ = targ_words != 0;
+  r->cur = nbuf;
+  CU_TRY(cudaStreamWaitEvent(r->compute, c.split_done, 0));
+  CU_TRY(cudaEventSynchronize(c.uploaded));  // the caller may reuse its buffers (BP_GPU::train semantics)
   return BP_OK;
 }
 
@@ -764,7 +863,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
   const int n = r->local_bunch;
   const bool prof = r->profiling;
-  int pe = 6 * (int)(r->prof_cnt % Rank::kProfCap);
+  int pe = 7 * (int)(r->prof_cnt % Rank::kProfCap);
   auto mark = [&]() { if (prof) cudaEventRecord(r->pev[pe++], r->compute); };
   mark();                                               // 0
   BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, loss_slot));
@@ -814,8 +913,14 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     }
     return BP_OK;
   };
+  auto mark_upper = [&]() -> int {  // everything the layers >= 2 need for their update has been issued
+    CU_TRY(cudaEventRecord(r->ev_upper, r->side));
+    if (r->nccl_comm) CU_TRY(cudaEventRecord(r->ev_comm_upper, r->comm_stream));
+    return BP_OK;
+  };
   CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
   BP_TRY(launch_dw(r->L));
+  if (r->L == 2) BP_TRY(mark_upper());
   for (int l = r->L; l >= 2; --l) {
     LayerState& ls = r->layer[l];
     LayerState& lp = r->layer[l - 1];
@@ -834,38 +939,55 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
+    if (l - 1 == 1 && r->L > 2) BP_TRY(mark_upper());  // before dW_1 enters the side stream
     BP_TRY(launch_dw(l - 1));
   }
   mark();                                               // 2: dX chain issued/done on `compute`
+  const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
+  const float c1 = (1 - cf.momentum) * cf.lrate;
+  static const int sgd_stream = [] {
+    const char* e = getenv("BP_SGD_STREAM");
+    return e ? atoi(e) : 1;
+  }();
+  auto launch_sgd = [&](long long begin4, long long end4, int blocks_per_sm) -> int {
+    const int grid = r->num_sms * blocks_per_sm;
+    if (cf.weightcost != 0.0f)
+      bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4,
+                                                        end4, nf, cf.momentum, c1, cf.weightcost, r->bias_ranges,
+                                                        (float4*)r->w_lo, sgd_stream);
+    else
+      bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4,
+                                                         end4, nf, cf.momentum, c1, 0.0f, r->bias_ranges,
+                                                         (float4*)r->w_lo, sgd_stream);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+    return BP_OK;
+  };
+  // The update is HBM-bound, the first layer's gradient GEMM (the largest, and the last to become computable) is
+  // tensor-bound and reads neither weights nor deltas: once the dX chain is done the layers >= 2 are updated while dW_1
+  // still runs on the side stream.  The early launch leaves thread slots free so the GEMM's CTAs become resident.
+  static const int sgd_early_blocks = [] {
+    const char* e = getenv("BP_SGD_EARLY");  // 0 = one update launch after all gradients (as the reference orders it)
+    return e ? atoi(e) : 6;
+  }();
+  long long tail_end4 = r->arena_floats / 4;
+  if (sgd_early_blocks > 0 && r->L >= 2) {
+    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
+    if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
+    tail_end4 = r->layer[2].off / 4;
+    BP_TRY(launch_sgd(tail_end4, r->arena_floats / 4, sgd_early_blocks));
+  }
+  mark();                                               // 3: early update of layers >= 2 done
   CU_TRY(cudaEventRecord(r->ev_side, r->side));
   CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_side, 0));
-  mark();                                               // 3: all dW done
+  mark();                                               // 4: all dW done
   if (r->nccl_comm) {
     CU_TRY(cudaEventRecord(r->ev_comm, r->comm_stream));
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
   }
-  mark();                                               // 4: all-reduce waited
-  {
-    const long long n4 = r->arena_floats / 4;
-    const int grid = r->num_sms * 8;
-    const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
-    const float c1 = (1 - cf.momentum) * cf.lrate;
-    static const int sgd_stream = [] {
-      const char* e = getenv("BP_SGD_STREAM");
-      return e ? atoi(e) : 1;
-    }();
-    if (cf.weightcost != 0.0f)
-      bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
-                                                        cf.momentum, c1, cf.weightcost, r->bias_ranges,
-                                                        (float4*)r->w_lo, sgd_stream);
-    else
-      bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, n4, nf,
-                                                         cf.momentum, c1, 0.0f, r->bias_ranges, (float4*)r->w_lo,
-                                                         sgd_stream);
-    CU_TRY(cudaGetLastError());
-    r->launches++;
-  }
-  mark();                                               // 5: sgd done
+  mark();                                               // 5: all-reduce waited
+  BP_TRY(launch_sgd(0, tail_end4, 8));
+  mark();                                               // 6: sgd done
   r->step++;
   r->bunches++;
   if (prof) r->prof_cnt++;
@@ -1079,6 +1201,81 @@ int bp_upload_chunk(bp_handle* h, int n_frames, const float* in, const float* ta
   });
 }
 
+static int check_raw_chunk(bp_handle* h, const bp_raw_chunk* rc) {
+  if (!h || !rc) return fail(BP_EINVAL, "null argument");
+  Rank* r0 = h->ranks[0];
+  if (!rc->fea_records || !rc->mean || !rc->inv_std || !rc->sample_frame || (rc->nat && !rc->sample_seg))
+    return fail(BP_EINVAL, "upload_raw: null table");
+  if (rc->fea_dim <= 0 || rc->fea_context <= 0 || rc->n_records <= 0 || rc->n_samples <= 0)
+    return fail(BP_EINVAL, "upload_raw: fea_dim=%d context=%d records=%d samples=%d", rc->fea_dim, rc->fea_context,
+                rc->n_records, rc->n_samples);
+  if (rc->fea_dim * (rc->fea_context + (rc->nat ? 1 : 0)) != r0->K0())
+    return fail(BP_EINVAL, "upload_raw: fea_dim %d x (context %d + nat %d) != layersizes[0] %d", rc->fea_dim,
+                rc->fea_context, rc->nat ? 1 : 0, r0->K0());
+  if (rc->targ_records && (rc->targ_offset < 0 || rc->targ_offset >= rc->fea_context))
+    return fail(BP_EINVAL, "upload_raw: targ_offset %d outside the context window", rc->targ_offset);
+  for (int i = 0; i < rc->n_samples; ++i) {
+    const int f = rc->sample_frame[i];
+    if (f < 0 || f + rc->fea_context > rc->n_records)
+      return fail(BP_EINVAL, "upload_raw: sample %d window [%d,%d) outside the %d records", i, f,
+                  f + rc->fea_context, rc->n_records);
+    if (rc->nat && (rc->sample_seg[i] < 0 || rc->sample_seg[i] > f))
+      return fail(BP_EINVAL, "upload_raw: sample %d segment start %d not in [0,%d]", i, rc->sample_seg[i], f);
+    if (rc->sample_row && (rc->sample_row[i] < 0 || rc->sample_row[i] >= rc->n_samples))
+      return fail(BP_EINVAL, "upload_raw: sample %d row %d outside [0,%d)", i, rc->sample_row[i], rc->n_samples);
+  }
+  return BP_OK;
+}
+
+int bp_upload_raw_chunk(bp_handle* h, const bp_raw_chunk* rc) {
+  BP_TRY(check_raw_chunk(h, rc));
+  return for_each_rank(h, [&](int i) { return rank_upload_raw(h->ranks[i], rc, false); });
+}
+
+int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* rc, float* sum_sq_err, float* out) {
+  BP_TRY(check_raw_chunk(h, rc));
+  if (sum_sq_err && !rc->targ_records) return fail(BP_EINVAL, "bp_crossvalid_raw: squared error needs target records");
+  Rank* r = h->ranks[0];  // device 0 only, like bp_crossvalid
+  BP_TRY(rank_upload_raw(r, rc, true));
+  double s = 0.0;
+  BP_TRY(rank_forward_resident(r, 0, rc->n_samples, out, sum_sq_err ? &s : nullptr));
+  if (sum_sq_err) *sum_sq_err = (float)s;
+  return BP_OK;
+}
+
+int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
+  if (!h || !rc) return fail(BP_EINVAL, "null argument");
+  if (!rc->targ_records) return fail(BP_EINVAL, "bp_train_raw: no target records");
+  const int B = h->ranks[0]->cfg.bunchsize;
+  const int nb = rc->n_samples / B;
+  if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
+  if (nb == 0) return BP_OK;
+  BP_TRY(bp_upload_raw_chunk(h, rc));
+  return bp_train_resident(h, 0, nb);
+}
+
+int bp_download_chunk(bp_handle* h, int first_row, int n_rows, float* in, float* targ) {
+  if (!h || n_rows <= 0 || first_row < 0) return fail(BP_EINVAL, "bp_download_chunk: bad argument");
+  if (h->ranks.size() != 1) return fail(BP_EINVAL, "bp_download_chunk: single-rank handles only");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  ChunkBuf& c = r->chunk[r->cur];
+  if (!c.x || first_row + n_rows > c.rows)
+    return fail(BP_EINVAL, "bp_download_chunk: rows [%d,%d) exceed resident rows %d", first_row, first_row + n_rows,
+                c.rows);
+  CU_TRY(cudaStreamSynchronize(r->copy));
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  if (in)
+    CU_TRY(cudaMemcpy2D(in, (size_t)r->K0() * 4, c.x + (long long)first_row * r->ldx, r->ldx * 4, (size_t)r->K0() * 4,
+                        n_rows, cudaMemcpyDeviceToHost));
+  if (targ) {
+    if (!c.has_targ) return fail(BP_EINVAL, "bp_download_chunk: no resident targets");
+    CU_TRY(cudaMemcpy(targ, c.t + (long long)first_row * r->Nout(), (size_t)n_rows * r->Nout() * 4,
+                      cudaMemcpyDeviceToHost));
+  }
+  return BP_OK;
+}
+
 int bp_train_resident(bp_handle* h, int first_bunch, int n_bunches) {
   if (!h) return fail(BP_EINVAL, "null handle");
   return for_each_rank(h, [&](int i) { return rank_train_resident(h->ranks[i], first_bunch, n_bunches); });
@@ -1191,14 +1388,16 @@ int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled) {
   for (int i = 0; i < 6; ++i) ms[i] = 0.0f;
   const int nb = (int)std::min<uint64_t>(r->prof_cnt, Rank::kProfCap);
   for (int b = 0; b < nb; ++b) {
-    cudaEvent_t* e = &r->pev[6 * b];
+    cudaEvent_t* e = &r->pev[7 * b];
     float t;
-    // marks: 0 start | 1 fwd done | 2 dX done | 3 dW issued | 4 all-reduce waited | 5 SGD done
-    CU_TRY(cudaEventElapsedTime(&t, e[0], e[1])); ms[0] += t;
-    CU_TRY(cudaEventElapsedTime(&t, e[1], e[2])); ms[1] += t;
-    CU_TRY(cudaEventElapsedTime(&t, e[2], e[3])); ms[2] += t;
-    CU_TRY(cudaEventElapsedTime(&t, e[4], e[5])); ms[3] += t;
-    CU_TRY(cudaEventElapsedTime(&t, e[3], e[4])); ms[4] += t;
+    // marks: 0 start | 1 fwd done | 2 dX done | 3 early update (layers >= 2) done | 4 all dW done |
+    //        5 all-reduce waited | 6 update done
+    CU_TRY(cudaEventElapsedTime(&t, e[0], e[1])); ms[0] += t;   // forward
+    CU_TRY(cudaEventElapsedTime(&t, e[1], e[2])); ms[1] += t;   // dX chain (dW_L..dW_2 run beside it)
+    CU_TRY(cudaEventElapsedTime(&t, e[3], e[4])); ms[2] += t;   // exposed tail of the dW GEMMs
+    CU_TRY(cudaEventElapsedTime(&t, e[5], e[6])); ms[3] += t;   // final update launch
+    CU_TRY(cudaEventElapsedTime(&t, e[4], e[5])); ms[4] += t;   // exposed all-reduce
+    CU_TRY(cudaEventElapsedTime(&t, e[2], e[3])); ms[5] += t;   // early update, concurrent with dW_1
   }
   if (bunches_profiled) *bunches_profiled = (uint64_t)nb;
   r->prof_cnt = 0;
@@ -1420,10 +1619,10 @@ int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bun
     SgdBiasRanges br{};
     const float c1 = (1 - momentum) * lrate;
     if (weightcost != 0.0f)
-      bp_sgd_kernel<true><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum, c1,
+      bp_sgd_kernel<true><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, 0, n4, (float)bunch, momentum, c1,
                                             weightcost, br, nullptr, 1);
     else
-      bp_sgd_kernel<false><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, n4, (float)bunch, momentum,
+      bp_sgd_kernel<false><<<148 * 8, 256>>>((float4*)d, (float4*)w, (const float4*)g, 0, n4, (float)bunch, momentum,
                                              c1, 0.0f, br, nullptr, 1);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaDeviceSynchronize());

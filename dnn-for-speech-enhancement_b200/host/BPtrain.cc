@@ -4,7 +4,7 @@
 //   BPtrain fea_file=... norm_file=... targ_file=... outwts_file=... log_file=... initwts_file=...
 //           train_sent_range=a-b cv_sent_range=c-d fea_dim=.. fea_context=.. targ_offset=.. traincache=.. bunchsize=..
 //           layersizes=a,b,.. lrate=.. momentum=.. weightcost=.. dropoutflag=.. visible_omit=.. hid_omit=..
-//           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=..]
+//           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=.. reader=host|gpu]
 //
 // Success exit status is 1 and every error path is "log + exit(0)", as in the reference (BPtrain.cc:100; App. D Q10).
 // The Perl epoch driver (finetune_DNN_speech_enhancement_dropout_NAT.pl) works unmodified against this binary.
@@ -22,6 +22,25 @@ static void die(Interface* io, const char* what) {
   fflush(io->fp_log);
   printf("%s: %s\n", what, bp_last_error());
   exit(0);
+}
+
+// RawChunk (host planner) -> bp_raw_chunk (C-ABI)
+static bp_raw_chunk as_abi(const Interface* io, const RawChunk& rc) {
+  bp_raw_chunk c{};
+  c.fea_dim = io->para->fea_dim;
+  c.fea_context = io->para->fea_context;
+  c.targ_offset = io->para->targ_offset;
+  c.nat = io->nat_block() ? 1 : 0;
+  c.n_records = rc.n_records;
+  c.n_samples = rc.n_samples;
+  c.fea_records = rc.fea_records;
+  c.targ_records = rc.targ_records;
+  c.mean = io->norm_mean();
+  c.inv_std = io->norm_inv_std();
+  c.sample_frame = rc.sample_frame.data();
+  c.sample_seg = rc.sample_seg.data();
+  c.sample_row = rc.sample_row.data();
+  return c;
 }
 
 int main(int argc, char* argv[]) {
@@ -53,12 +72,18 @@ int main(int argc, char* argv[]) {
   for (unsigned int i = 0; i < io->total_chunks; ++i) chunk_index[i] = i;
   io->GetRandIndex(chunk_index.data(), io->total_chunks);
   unsigned long long trained_samples = 0;
+  RawChunk raw;  // reader=gpu: records + sample table of the current chunk
   const double t_train0 = time(NULL);
   for (unsigned int i = 0; i < io->total_chunks; ++i) {
-    const int n = io->Readchunk(chunk_index[i]);
+    const int n = para->reader_gpu ? io->ReadchunkRaw(chunk_index[i], &raw) : io->Readchunk(chunk_index[i]);
     fprintf(io->fp_log, "Starting chunk %d of %d containing %d samples.\n", i + 1, io->total_chunks, n);
     fflush(io->fp_log);
-    if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) die(io, "train failed");
+    if (n > 0 && para->reader_gpu) {
+      const bp_raw_chunk c = as_abi(io, raw);
+      if (bp_train_raw(trainer, &c) != BP_OK) die(io, "train failed");
+    } else if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) {
+      die(io, "train failed");
+    }
     trained_samples += n;
   }
 
@@ -76,9 +101,18 @@ int main(int argc, char* argv[]) {
   FILE* fdec = para->decode_FN[0] ? fopen(para->decode_FN, "wb") : nullptr;
   std::vector<float> dec;
   for (unsigned int i = 0; i < io->cv_total_chunks; ++i) {
-    const int n = io->Readchunk_cv(i);
+    const int n = para->reader_gpu ? io->Readchunk_cvRaw(i, &raw) : io->Readchunk_cv(i);
     printf("cur_chunk_samples=%d\n", n);
     if (n <= 0) continue;
+    if (para->reader_gpu) {  // one upload serves the score and the decode output
+      const bp_raw_chunk c = as_abi(io, raw);
+      float sq = 0.0f;
+      if (fdec) dec.resize(static_cast<size_t>(n) * para->layersizes[io->numlayers - 1]);
+      if (bp_crossvalid_raw(trainer, &c, &sq, fdec ? dec.data() : nullptr) != BP_OK) die(io, "CrossValid failed");
+      squared_err += sq;
+      if (fdec) fwrite(dec.data(), sizeof(float), dec.size(), fdec);
+      continue;
+    }
     float s = 0.0f;
     if (bp_crossvalid(trainer, n, para->indata, para->targ, &s) != BP_OK) die(io, "CrossValid failed");
     squared_err += s;
@@ -89,6 +123,7 @@ int main(int argc, char* argv[]) {
     }
   }
   if (fdec) fclose(fdec);
+  io->free_raw(&raw);
   const float cvacc = squared_err / io->cv_total_samples;
   fprintf(io->fp_log, "CV over. squared error: %f\n", cvacc);
   fflush(io->fp_log);

@@ -132,6 +132,10 @@ void Interface::Initial(int argc, char** argv) {
       setenv("BP_MATH", val, 1);
       continue;
     }
+    if (key == "reader") {  // host (default, the reference's Readchunk) | gpu (device-side splice, §8f-1)
+      para->reader_gpu = (strcmp(val, "gpu") == 0) ? 1 : 0;
+      continue;
+    }
     if (key == "seed") {
       para->seed = strtoull(val, nullptr, 0);
       continue;
@@ -416,6 +420,20 @@ void Interface::read_records(FILE* fp, int dim, long first_frame, int n_frames, 
   *first_sent = be_int(rec->data());
 }
 
+// The sentence segments that intersect the record block [first, first+n_frames); `sent` = sentence of record `first`.
+std::vector<Interface::Seg> Interface::segments(int first, int n_frames, int sent) const {
+  std::vector<Seg> segs;
+  int done = 0, frame = first, s = sent;
+  while (done != n_frames) {
+    const int len = (framesBeforeSent[s] > first + n_frames) ? (n_frames - done) : (framesBeforeSent[s] - frame);
+    segs.push_back({done, len});
+    frame = framesBeforeSent[s];
+    ++s;
+    done += len;
+  }
+  return segs;
+}
+
 // Sample assembly — reference Readchunk Interface.cc:689-861 / Readchunk_cv :864-1034, one implementation:
 // byte-swap + (x-mean)*dVar, 11-frame splice, NAT block (mean of the segment's first six frames, /6.0f, summed left to
 // right), target frame j+targ_offset, rows scattered through a Fisher-Yates permutation (train) or in order (CV).
@@ -449,19 +467,7 @@ int Interface::assemble(int chunk_index, const int* starts, unsigned int n_chunk
     }
   }
 
-  // walk the sentence segments that intersect this chunk
-  struct Seg { int begin, len; };
-  std::vector<Seg> segs;
-  {
-    int done = 0, frame = first, s = sent;
-    while (done != n_frames) {
-      const int len = (framesBeforeSent[s] > first + n_frames) ? (n_frames - done) : (framesBeforeSent[s] - frame);
-      segs.push_back({done, len});
-      frame = framesBeforeSent[s];
-      ++s;
-      done += len;
-    }
-  }
+  const std::vector<Seg> segs = segments(first, n_frames, sent);
 
   int cur = 0;
   for (const Seg& sg : segs) {
@@ -512,6 +518,73 @@ int Interface::Readchunk(int index) {
 
 int Interface::Readchunk_cv(int index) {
   return assemble(index, cv_chunk_frame_st, cv_total_chunks, cv_total_samples, cv_r.en, false);
+}
+
+// Device-reader variant of `assemble`: same chunk geometry, same shuffle (one GetRandIndex call per
+// chunk, so the lrand48 stream — hence every later chunk — is unchanged), but the records stay raw: the function only
+// reads them into (page-locked) buffers and writes the sample table that bp_upload_raw_chunk consumes.
+int Interface::assemble_raw(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples,
+                            int sent_end, bool shuffle, RawChunk* rc) {
+  const int dim = para->fea_dim, ctx = para->fea_context;
+  const int out_w = para->layersizes[numlayers - 1];
+  const int first = starts[chunk_index];
+  const bool last = static_cast<unsigned int>(chunk_index) == n_chunks - 1;
+  const int n_frames = (last ? framesBeforeSent[sent_end] : starts[chunk_index + 1]) - first;
+  const int samples = last ? static_cast<int>(n_samples) - para->traincache * chunk_index : para->traincache;
+  rc->n_records = rc->n_samples = 0;
+  if (n_frames <= 0 || samples <= 0) return 0;
+  std::vector<int> order(samples);
+  for (int i = 0; i < samples; ++i) order[i] = i;
+  if (shuffle) GetRandIndex(order.data(), samples);
+
+  auto grow = [&](void** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return;
+    if (*buf) (host_free ? host_free : free)(*buf);
+    *buf = host_alloc ? host_alloc(need) : malloc(need);
+    if (!*buf) fatal("cannot allocate %zu bytes for the raw chunk.\n", need);
+    *cap = need;
+  };
+  auto read_block = [&](FILE* fp, int width, void* dst) {
+    const long rec_bytes = 4L * (width + 2);
+    if (fseek(fp, kPfileHeaderBytes + first * rec_bytes, SEEK_SET) != 0) fatal("pfile cannot fseek to chunk.\n");
+    if (fread(dst, rec_bytes, n_frames, fp) != static_cast<size_t>(n_frames)) fatal("pfile read failed.\n");
+  };
+  grow(&rc->fea_records, &rc->fea_cap, static_cast<size_t>(n_frames) * (dim + 2) * 4);
+  grow(&rc->targ_records, &rc->targ_cap, static_cast<size_t>(n_frames) * (out_w + 2) * 4);
+  read_block(fp_data, dim, rc->fea_records);
+  read_block(fp_targ, out_w, rc->targ_records);
+  const int sent = be_int(static_cast<const float*>(rc->fea_records));
+
+  rc->sample_frame.resize(samples);
+  rc->sample_seg.resize(samples);
+  rc->sample_row.resize(samples);
+  int cur = 0;
+  for (const Seg& sg : segments(first, n_frames, sent))
+    for (int j = 0; j + ctx <= sg.len && cur < samples; ++j, ++cur) {
+      rc->sample_frame[cur] = sg.begin + j;
+      rc->sample_seg[cur] = sg.begin;
+      rc->sample_row[cur] = order[cur];
+    }
+  if (cur != samples) fatal("chunk %d: planned %d samples but found %d.\n", chunk_index, samples, cur);
+  rc->n_records = n_frames;
+  rc->n_samples = samples;
+  return samples;
+}
+
+int Interface::ReadchunkRaw(int index, RawChunk* rc) {
+  return assemble_raw(index, chunk_frame_st, total_chunks, total_samples, train_r.en, true, rc);
+}
+
+int Interface::Readchunk_cvRaw(int index, RawChunk* rc) {
+  return assemble_raw(index, cv_chunk_frame_st, cv_total_chunks, cv_total_samples, cv_r.en, false, rc);
+}
+
+void Interface::free_raw(RawChunk* rc) {
+  for (void** b : {&rc->fea_records, &rc->targ_records}) {
+    if (*b) (host_free ? host_free : free)(*b);
+    *b = nullptr;
+  }
+  rc->fea_cap = rc->targ_cap = 0;
 }
 
 // Uniform weights from drand48 (Interface.cc:1036-1042): vec[i] = drand48()*(max-min)+min, evaluated in double.

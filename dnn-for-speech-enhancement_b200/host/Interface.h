@@ -59,9 +59,20 @@ struct WorkPara {
 
   // extensions
   int nat = -1;            // -1 = infer from layersizes[0]
+  int reader_gpu = 0;      // reader=gpu: splice / normalise / shuffle on the device (default host, as the reference)
   int activation = 0;      // 0 relu, 1 sigmoid
   unsigned long long seed = 0x5eed5eedULL;
   char decode_FN[MAXLINE] = "";
+};
+
+// One chunk for the device-side reader: the Pfile records as they lie in the file + the sample table
+// (field for field the bp_raw_chunk of include/bp_gpu.h; buffers are owned and re-used by the Interface).
+struct RawChunk {
+  int n_records = 0, n_samples = 0;
+  void* fea_records = nullptr;   // n_records x (2+fea_dim) big-endian words (page-locked when host_alloc is set)
+  void* targ_records = nullptr;  // n_records x (2+layersizes[last]) words
+  size_t fea_cap = 0, targ_cap = 0;
+  std::vector<int> sample_frame, sample_seg, sample_row;
 };
 
 class Interface {
@@ -76,6 +87,13 @@ class Interface {
   void get_chunk_info_cv(char* range);
   int Readchunk(int index);
   int Readchunk_cv(int index);
+  // reader=gpu: same chunks, same shuffle, but samples are assembled on the device (bp_upload_raw_chunk)
+  int ReadchunkRaw(int index, RawChunk* rc);
+  int Readchunk_cvRaw(int index, RawChunk* rc);
+  void free_raw(RawChunk* rc);
+  const float* norm_mean() const { return mean.data(); }
+  const float* norm_inv_std() const { return dVar.data(); }
+  bool nat_block() const { return use_nat; }
   void GetRandIndex(int* vec, int len);
 
   WorkPara* para;
@@ -103,6 +121,12 @@ class Interface {
   struct Range {
     int st = 0, en = 0;
   };
+  struct Seg {
+    int begin, len;  // record index inside the chunk's block, frames
+  };
+  std::vector<Seg> segments(int first, int n_frames, int sent) const;
+  int assemble_raw(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,
+                   bool shuffle, RawChunk* rc);
   void fatal(const char* fmt, ...);
   Range parse_range(const char* range, const char* what);
   void plan_chunks(const Range& r, int* starts, unsigned int* n_chunks, unsigned int* n_samples);

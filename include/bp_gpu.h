@@ -97,6 +97,42 @@ int bp_forward_resident(bp_handle* h, int first_frame, int n_frames, float* out_
                         double* sum_sq_err /* may be NULL; needs resident targets */);
 int bp_sync(bp_handle* h);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device-side chunk reader.  Replaces the sample assembly of Interface::Readchunk /
+ * Readchunk_cv (Interface.cc:689-861, 864-1034): the caller passes the chunk's Pfile records exactly as they lie in
+ * the file plus a table that says which record window each sample is; byte-swap, (x-mean)*inv_std (:745-746), the
+ * fea_context-frame splice (:769-773), the NAT block = mean of the segment's first six frames (:776-779), the
+ * target pick at +targ_offset (:844-846) and the scatter through the shuffle permutation (:731-735) run on the
+ * device.  Rows are bit-identical with the host reader's.  Host traffic drops from 4*(layersizes[0]+layersizes[L])
+ * bytes per sample to ~4*(fea_dim+layersizes[L]+4) bytes per frame.
+ *
+ * Data-parallel handles (in-process group or one process per rank): every rank is given the same bp_raw_chunk and keeps
+ * rows [rank*B/G, (rank+1)*B/G) of every global bunch of B rows; the trailing partial bunch is dropped.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct bp_raw_chunk {
+  int fea_dim;              /* floats per feature record */
+  int fea_context;          /* frames spliced per sample */
+  int targ_offset;          /* target record = first context record + targ_offset */
+  int nat;                  /* 1 = append the NAT block (layersizes[0] = fea_dim*(fea_context+1)) */
+  int n_records;            /* records in fea_records (and targ_records) */
+  int n_samples;
+  const void* fea_records;  /* n_records x (2+fea_dim) big-endian 32-bit words: sentence id, frame id, features */
+  const void* targ_records; /* n_records x (2+layersizes[last]) words, or NULL (forward only) */
+  const float* mean;        /* fea_dim, norm file part 1 */
+  const float* inv_std;     /* fea_dim, norm file part 2 */
+  const int* sample_frame;  /* n_samples: index of the sample's first context record */
+  const int* sample_seg;    /* n_samples: index of the first record of its sentence segment (nat only) */
+  const int* sample_row;    /* n_samples: destination row (the shuffle permutation), or NULL for file order */
+} bp_raw_chunk;
+int bp_upload_raw_chunk(bp_handle* h, const bp_raw_chunk* chunk);  /* then bp_train_resident / bp_forward_resident */
+int bp_train_raw(bp_handle* h, const bp_raw_chunk* chunk);         /* = upload + train on floor(n_samples/B) bunches */
+/* CrossValid (+ optional decode output, n_samples x layersizes[last]) over a raw chunk; all rows on device 0. */
+int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* chunk, float* sum_sq_err /* may be NULL */,
+                      float* out /* may be NULL */);
+/* Reads rows of the resident chunk back (tests: bit-exactness of the device reader).  Single-rank handles. */
+int bp_download_chunk(bp_handle* h, int first_row, int n_rows, float* in /* may be NULL */,
+                      float* targ /* may be NULL */);
+
 /* Pinned host memory for true asynchronous DMA of chunks (the reference uses pageable new[] buffers). */
 void* bp_host_alloc(size_t bytes);
 void bp_host_free(void* p);
@@ -109,8 +145,9 @@ int bp_timer_stop(bp_handle* h, float* elapsed_ms);
 int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bunches);
 
 /* Per-kernel device time of the most recent bunch when profiling is on (CUDA events around each launch class):
- * ms[0] = forward GEMMs, ms[1] = dX GEMMs, ms[2] = dW GEMMs, ms[3] = SGD update, ms[4] = all-reduce wait,
- * ms[5] = reserved.  Sums over the last <= 64 profiled bunches; records events only, no host sync per bunch. */
+ * ms[0] = forward GEMMs, ms[1] = dX GEMMs (dW of the upper layers runs beside them), ms[2] = exposed tail of the dW
+ * GEMMs, ms[3] = final SGD update launch (layer 1, or everything when BP_SGD_EARLY=0), ms[4] = all-reduce wait,
+ * ms[5] = early SGD update of layers >= 2, which overlaps the first layer's dW GEMM.  Sums over the last <= 64 profiled bunches; records events only, no host sync per bunch. */
 int bp_set_profiling(bp_handle* h, int on);
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled);
 
