@@ -2,11 +2,16 @@
 // the code is new: table-driven argv parsing, one chunk planner and one sample assembler shared by train and CV.
 #include "Interface.h"
 
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace {
 
@@ -544,15 +549,35 @@ int Interface::assemble_raw(int chunk_index, const int* starts, unsigned int n_c
     if (!*buf) fatal("cannot allocate %zu bytes for the raw chunk.\n", need);
     *cap = need;
   };
+  // The two record blocks are the only bulk host work left per chunk (~1 KB per frame): read them with a few
+  // positional reads in parallel (page-cache copies run at 2-4 GB/s per thread), straight into the DMA buffers.
+  std::atomic<bool> ok{true};
+  std::vector<std::thread> readers;
   auto read_block = [&](FILE* fp, int width, void* dst) {
-    const long rec_bytes = 4L * (width + 2);
-    if (fseek(fp, kPfileHeaderBytes + first * rec_bytes, SEEK_SET) != 0) fatal("pfile cannot fseek to chunk.\n");
-    if (fread(dst, rec_bytes, n_frames, fp) != static_cast<size_t>(n_frames)) fatal("pfile read failed.\n");
+    const size_t rec_bytes = 4u * static_cast<size_t>(width + 2);
+    const size_t total = rec_bytes * static_cast<size_t>(n_frames);
+    const off_t base = static_cast<off_t>(kPfileHeaderBytes) + static_cast<off_t>(first) * rec_bytes;
+    const int parts = total > (8u << 20) ? 4 : 1;
+    const size_t per = (total + parts - 1) / parts;
+    const int fd = fileno(fp);
+    for (int k = 0; k < parts; ++k) {
+      const size_t b = std::min(total, per * k), e = std::min(total, per * (k + 1));
+      readers.emplace_back([=, &ok] {
+        size_t done = b;
+        while (done < e) {
+          const ssize_t got = pread(fd, static_cast<char*>(dst) + done, e - done, base + static_cast<off_t>(done));
+          if (got <= 0) { ok = false; return; }
+          done += static_cast<size_t>(got);
+        }
+      });
+    }
   };
   grow(&rc->fea_records, &rc->fea_cap, static_cast<size_t>(n_frames) * (dim + 2) * 4);
   grow(&rc->targ_records, &rc->targ_cap, static_cast<size_t>(n_frames) * (out_w + 2) * 4);
   read_block(fp_data, dim, rc->fea_records);
   read_block(fp_targ, out_w, rc->targ_records);
+  for (std::thread& t : readers) t.join();
+  if (!ok) fatal("pfile read failed.\n");
   const int sent = be_int(static_cast<const float*>(rc->fea_records));
 
   rc->sample_frame.resize(samples);
