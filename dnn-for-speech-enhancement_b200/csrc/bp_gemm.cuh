@@ -72,6 +72,11 @@ struct GemmParams {
   int passes;             // 1 = single-pass TF32; 3 = split precision (3xTF32): A*B + A_lo*B + A*B_lo, where X_lo =
                           // X - trunc_tf32(X) is kept as a second fp32 array by whoever writes X (~fp32 accuracy)
   float* out_lo;          // if non-null: out_lo[...] = v - trunc_tf32(v) for every v stored to `out` (same layout)
+  // data-parallel reduce-scatter fused into the epilogue (EPI_PLAIN, see bp_peer.cuh): the 32-column chunk starting at
+  // column nc goes to scatter[(chunk_base + nc/32) % scatter_n] (a peer's receive slab, same layout as `out`)
+  int scatter_n;
+  int chunk_base;
+  float* scatter[8];
   unsigned long long hint_a, hint_b;  // L2 eviction-priority policy for the A / B operand loads (0 = none)
   uint32_t dbg_flags;     // measurement aids: bit 0 skip the MMAs (TMA-only), bit 1 skip the loads (MMA-only)
   long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
@@ -112,7 +117,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
   const bool whole = nc + 32 <= p.N;  // warp-uniform: all 32 columns of the chunk are real
   if constexpr (kEpi == EPI_PLAIN) {
     if (m_ok) {
-      float* o = p.out + plane_off + size_t(nc) * p.ldo + m;
+      float* base = p.out + plane_off;
+      if (p.scatter_n > 0) base = p.scatter[(p.chunk_base + (nc >> 5)) % p.scatter_n];
+      float* o = base + size_t(nc) * p.ldo + m;
 #pragma unroll
       for (int j = 0; j < 32; ++j, o += p.ldo)
         if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);

@@ -29,6 +29,7 @@
 #include "bp_gemm.cuh"
 #include "bp_gemm2.cuh"
 #include "bp_microbench.cuh"
+#include "bp_peer.cuh"
 #include "bp_splice.cuh"
 
 namespace {
@@ -269,6 +270,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -286,6 +288,7 @@ int load_nccl() {
     g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
     g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.lib, "ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(g_nccl.lib, "ncclAllGather"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
     g_nccl.GetErrorString =
         reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
@@ -302,6 +305,7 @@ int load_nccl() {
   } while (0)
 constexpr int kNcclFloat32 = 7;  // ncclFloat32
 constexpr int kNcclSum = 0;      // ncclSum
+constexpr int kNcclInt8 = 0;     // ncclInt8 / ncclChar
 
 // ------------------------------------------------------------------------------------------------ per-rank state
 struct LayerState {
@@ -374,6 +378,21 @@ struct Rank {
   size_t raw_fea_cap = 0, raw_targ_cap = 0, raw_tab_cap = 0, raw_norm_cap = 0;  // in elements
   float* splitk_ws = nullptr;  // kMaxSplits partial planes of the output-layer product (bunchsize x ldN_out each)
   void* nccl_comm = nullptr;
+  // peer-memory data parallelism (bp_peer.cuh); dp_p2p = 1 once every rank has mapped every other rank's slabs
+  struct PeerMem {
+    float* w = nullptr;
+    float* w_lo = nullptr;
+    float* recv = nullptr;
+    unsigned long long* flags = nullptr;
+    bool ipc = false;  // pointers came from cudaIpcOpenMemHandle (close them on destroy)
+  };
+  int dp_p2p = 0;
+  float* recv = nullptr;                 // world_size slabs of arena_floats: recv + src*arena_floats
+  unsigned long long* flags = nullptr;   // [0..7] gradients of step s landed from src, [8..15] weights landed from src
+  PeerMem peer[kMaxPeers];
+  unsigned long long dp_step = 0;
+  PeerLayers peer_layers{};
+  int chunk_base[BP_MAXLAYER] = {};      // first 32-row ownership chunk of each layer
   uint64_t launches = 0, bunches = 0;
   uint32_t step = 0;
   bool profiling = false;
@@ -420,11 +439,14 @@ int ensure_chunk(Rank* r, ChunkBuf& c, long long rows) {
   return BP_OK;
 }
 
+void rank_p2p_release(Rank* r);
+
 int rank_destroy(Rank* r) {
   if (!r) return BP_OK;
   cudaSetDevice(r->cfg.device);
   cudaDeviceSynchronize();
   if (r->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(r->nccl_comm);
+  rank_p2p_release(r);
   for (auto& c : r->chunk) {
     cudaFree(c.x);
     cudaFree(c.x_lo);
@@ -558,6 +580,18 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       r->bias_ranges.begin4[r->bias_ranges.n] = (off + (long long)ls.K * ls.ldN) / 4;
       r->bias_ranges.end4[r->bias_ranges.n] = (off + (long long)(ls.K + 1) * ls.ldN) / 4;
       r->bias_ranges.n++;
+      {  // ownership geometry for the peer-memory exchange
+        PeerLayers& pl = r->peer_layers;
+        const LayerState& lp = r->layer[l - 1];
+        const int prev_rows = l == 1 ? 0 : (int)((lp.size + lp.ldN - 1) / lp.ldN);  // rows incl. the 64-float padding
+        r->chunk_base[l] = l == 1 ? 0 : r->chunk_base[l - 1] + (prev_rows + 31) / 32;
+        pl.begin4[pl.n] = off / 4;
+        pl.end4[pl.n] = (off + ls.size) / 4;
+        pl.row4[pl.n] = (int)(ls.ldN / 4);
+        pl.bias_row[pl.n] = ls.K;
+        pl.chunk_base[pl.n] = r->chunk_base[l];
+        pl.n++;
+      }
       off += ls.size;
     }
     r->arena_floats = off;
@@ -858,6 +892,151 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
   return BP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory DP
+// BP_DP: "nccl" = all-reduce + replicated update; "p2p" = peer-memory exchange or fail; unset = p2p when every peer
+// can be mapped, else nccl (with a note on stderr).
+inline int dp_mode_wanted() {
+  const char* e = getenv("BP_DP");
+  if (!e) return 1;
+  if (strcmp(e, "nccl") == 0) return 0;
+  return 2;
+}
+
+int rank_p2p_alloc(Rank* r) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  const size_t slab = sizeof(float) * (size_t)r->arena_floats * r->cfg.world_size;
+  CU_TRY(cudaMalloc(&r->recv, slab));
+  CU_TRY(cudaMemset(r->recv, 0, slab));
+  CU_TRY(cudaMalloc(&r->flags, sizeof(unsigned long long) * 2 * kMaxPeers));
+  CU_TRY(cudaMemset(r->flags, 0, sizeof(unsigned long long) * 2 * kMaxPeers));
+  CU_TRY(cudaDeviceSynchronize());
+  Rank::PeerMem& me = r->peer[r->cfg.rank];
+  me.w = r->w;
+  me.w_lo = r->w_lo;
+  me.recv = r->recv;
+  me.flags = r->flags;
+  return BP_OK;
+}
+
+void rank_p2p_release(Rank* r) {
+  for (auto& pm : r->peer) {
+    if (pm.ipc)
+      for (void* q : {(void*)pm.w, (void*)pm.w_lo, (void*)pm.recv, (void*)pm.flags})
+        if (q) cudaIpcCloseMemHandle(q);
+    pm = Rank::PeerMem{};
+  }
+  cudaFree(r->recv);
+  cudaFree(r->flags);
+  r->recv = nullptr;
+  r->flags = nullptr;
+  r->dp_p2p = 0;
+  cudaGetLastError();
+}
+
+// One process per rank: the slabs are exported as CUDA IPC handles, exchanged through the NCCL communicator that
+// exists anyway, and mapped with peer access.  Every rank takes the same decision (two agreement rounds), so either
+// all ranks use the peer-memory exchange or all use NCCL.
+struct IpcPack {
+  cudaIpcMemHandle_t w, w_lo, recv, flags;
+  int has_lo, ok, pad0, pad1;
+};
+
+int rank_p2p_connect_ipc(Rank* r) {
+  const int want = dp_mode_wanted();
+  if (want == 0) return BP_OK;
+  const int W = r->cfg.world_size, me = r->cfg.rank;
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  IpcPack mine{};
+  int ok = (W <= kMaxPeers) && g_nccl.AllGather != nullptr;
+  if (ok && rank_p2p_alloc(r) != BP_OK) ok = 0;
+  if (ok) {
+    ok = cudaIpcGetMemHandle(&mine.w, r->w) == cudaSuccess && cudaIpcGetMemHandle(&mine.recv, r->recv) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.flags, r->flags) == cudaSuccess &&
+         (!r->w_lo || cudaIpcGetMemHandle(&mine.w_lo, r->w_lo) == cudaSuccess);
+    cudaGetLastError();
+  }
+  mine.ok = ok;
+  mine.has_lo = r->w_lo != nullptr;
+  IpcPack* dev = nullptr;
+  CU_TRY(cudaMalloc(&dev, sizeof(IpcPack) * (W + 1)));
+  std::vector<IpcPack> all(W);
+  CU_TRY(cudaMemcpyAsync(dev + W, &mine, sizeof(IpcPack), cudaMemcpyHostToDevice, r->compute));
+  NCCL_TRY(g_nccl.AllGather(dev + W, dev, sizeof(IpcPack), kNcclInt8, r->nccl_comm, r->compute));
+  CU_TRY(cudaMemcpyAsync(all.data(), dev, sizeof(IpcPack) * W, cudaMemcpyDeviceToHost, r->compute));
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  bool all_ok = true;
+  for (const IpcPack& q : all) all_ok = all_ok && q.ok;
+  float bad = all_ok ? 0.0f : 1.0f;
+  if (all_ok) {
+    for (int p = 0; p < W && bad == 0.0f; ++p) {
+      if (p == me) continue;
+      Rank::PeerMem& pm = r->peer[p];
+      pm.ipc = true;
+      auto open = [&](void** dst, const cudaIpcMemHandle_t& hnd) {
+        if (cudaIpcOpenMemHandle(dst, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          *dst = nullptr;
+          bad = 1.0f;
+          cudaGetLastError();
+        }
+      };
+      open((void**)&pm.w, all[p].w);
+      open((void**)&pm.recv, all[p].recv);
+      open((void**)&pm.flags, all[p].flags);
+      if (all[p].has_lo) open((void**)&pm.w_lo, all[p].w_lo);
+    }
+  }
+  // second round: did everybody manage to map everybody?
+  float* dbad = reinterpret_cast<float*>(dev);
+  CU_TRY(cudaMemcpyAsync(dbad, &bad, sizeof(float), cudaMemcpyHostToDevice, r->compute));
+  NCCL_TRY(g_nccl.AllReduce(dbad, dbad, 1, kNcclFloat32, kNcclSum, r->nccl_comm, r->compute));
+  CU_TRY(cudaMemcpyAsync(&bad, dbad, sizeof(float), cudaMemcpyDeviceToHost, r->compute));
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  CU_TRY(cudaFree(dev));
+  if (bad == 0.0f) {
+    r->dp_p2p = 1;
+    if (me == 0 && getenv("BP_VERBOSE")) fprintf(stderr, "libbpgpu: gradient exchange over peer memory, %d ranks\n", W);
+    return BP_OK;
+  }
+  rank_p2p_release(r);
+  if (want == 2) return fail(BP_ECOMM, "BP_DP=p2p: peer memory of some rank cannot be mapped (CUDA IPC / peer access)");
+  if (me == 0) fprintf(stderr, "libbpgpu: peer memory not mappable on every rank, using NCCL all-reduce\n");
+  return BP_OK;
+}
+
+// One exchange after the local gradient GEMMs of a bunch: publish "my partial gradients have landed everywhere",
+// reduce + update the rows this rank owns and push them to every replica, publish "my rows have landed", wait for
+// everybody else's rows.  All on the compute stream; the spin waits are bounded (bp_peer.cuh).
+int peer_exchange(Rank* r) {
+  const bp_config& cf = r->cfg;
+  const int W = cf.world_size, me = cf.rank;
+  const unsigned long long step = ++r->dp_step;
+  PeerFlags fg{}, fw{};
+  PeerArenas pa{};
+  for (int p = 0; p < W; ++p) {
+    fg.slot[p] = r->peer[p].flags + me;
+    fw.slot[p] = r->peer[p].flags + kMaxPeers + me;
+    pa.w[p] = (float4*)r->peer[p].w;
+    pa.w_lo[p] = (float4*)r->peer[p].w_lo;
+  }
+  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fg, W, step);
+  const float nf = (float)cf.bunchsize;
+  const float c1 = (1 - cf.momentum) * cf.lrate;
+  const int grid = r->num_sms * 8;
+  if (cf.weightcost != 0.0f)
+    bp_peer_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
+                                                           r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                           cf.momentum, c1, cf.weightcost, r->flags, step);
+  else
+    bp_peer_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
+                                                            r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                            cf.momentum, c1, 0.0f, r->flags, step);
+  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fw, W, step);
+  bp_peer_wait_kernel<<<1, 32, 0, r->compute>>>(r->flags + kMaxPeers, W, step);
+  CU_TRY(cudaGetLastError());
+  r->launches += 4;
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ one train bunch
 int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
@@ -893,16 +1072,22 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     // Data-parallel ranks cut the gradient block into row slices (= column slices of the product, contiguous in the
     // arena) so that each slice's all-reduce runs while the next slice is still being computed; only the last
     // slice's reduction is exposed.  A single rank computes the block in one launch.
+    if (r->dp_p2p) {  // reduce-scatter fused into the epilogue: chunks go straight to their owners' receive slabs
+      p.scatter_n = cf.world_size;
+      p.chunk_base = r->chunk_base[l];
+      for (int o = 0; o < cf.world_size; ++o)
+        p.scatter[o] = r->peer[o].recv + (long long)cf.rank * r->arena_floats + ls.off;
+    }
     const int total = p.N;
     int slices = 1;
-    if (r->nccl_comm) slices = std::max(1, std::min(r->ar_slices, (total + kBlockN - 1) / kBlockN));
+    if (r->nccl_comm && !r->dp_p2p) slices = std::max(1, std::min(r->ar_slices, (total + kBlockN - 1) / kBlockN));
     const int per = ((total + slices - 1) / slices + kBlockN - 1) / kBlockN * kBlockN;
     for (int b0 = 0; b0 < total; b0 += per) {
       p.n_begin = b0;
       p.N = std::min(total, b0 + per);
       BP_TRY((launch_gemm<true, true, EPI_PLAIN>(r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
       r->launches++;
-      if (r->nccl_comm) {
+      if (r->nccl_comm && !r->dp_p2p) {
         float* gs = r->g + ls.off + (long long)b0 * ls.ldN;
         const size_t cnt = (p.N == total) ? (size_t)(ls.size - (long long)b0 * ls.ldN)
                                           : (size_t)(p.N - b0) * (size_t)ls.ldN;
@@ -915,7 +1100,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   };
   auto mark_upper = [&]() -> int {  // everything the layers >= 2 need for their update has been issued
     CU_TRY(cudaEventRecord(r->ev_upper, r->side));
-    if (r->nccl_comm) CU_TRY(cudaEventRecord(r->ev_comm_upper, r->comm_stream));
+    if (r->nccl_comm && !r->dp_p2p) CU_TRY(cudaEventRecord(r->ev_comm_upper, r->comm_stream));
     return BP_OK;
   };
   CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
@@ -971,7 +1156,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     return e ? atoi(e) : 6;
   }();
   long long tail_end4 = r->arena_floats / 4;
-  if (sgd_early_blocks > 0 && r->L >= 2) {
+  if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
     if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
     tail_end4 = r->layer[2].off / 4;
@@ -981,12 +1166,13 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   CU_TRY(cudaEventRecord(r->ev_side, r->side));
   CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_side, 0));
   mark();                                               // 4: all dW done
-  if (r->nccl_comm) {
+  if (r->nccl_comm && !r->dp_p2p) {
     CU_TRY(cudaEventRecord(r->ev_comm, r->comm_stream));
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
   }
   mark();                                               // 5: all-reduce waited
-  BP_TRY(launch_sgd(0, tail_end4, 8));
+  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
+  else BP_TRY(launch_sgd(0, tail_end4, 8));
   mark();                                               // 6: sgd done
   r->step++;
   r->bunches++;
@@ -1114,6 +1300,55 @@ int bp_create_ex(bp_handle** h, const bp_config* cfg, float* const* weights, flo
   return BP_OK;
 }
 
+// One process, one host thread per rank (BPtrain gpu_used=N): peer access is enabled directly.
+int group_p2p_connect(bp_handle* h) {
+  const int want = dp_mode_wanted();
+  const int W = (int)h->ranks.size();
+  if (want == 0 || W < 2) return BP_OK;
+  bool can = W <= kMaxPeers;
+  for (int i = 0; i < W && can; ++i)
+    for (int j = 0; j < W && can; ++j) {
+      int yes = 1;
+      if (i != j && (cudaDeviceCanAccessPeer(&yes, h->ranks[i]->cfg.device, h->ranks[j]->cfg.device) != cudaSuccess ||
+                     !yes))
+        can = false;
+    }
+  if (can) {
+    int rc = for_each_rank(h, [&](int i) -> int {
+      Rank* r = h->ranks[i];
+      CU_TRY(cudaSetDevice(r->cfg.device));
+      for (int j = 0; j < W; ++j) {
+        if (j == i) continue;
+        cudaError_t e = cudaDeviceEnablePeerAccess(h->ranks[j]->cfg.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(BP_ECOMM, "peer access %d->%d", i, j);
+        cudaGetLastError();
+      }
+      return rank_p2p_alloc(r);
+    });
+    can = rc == BP_OK;
+  }
+  if (!can) {
+    for (Rank* r : h->ranks) {
+      cudaSetDevice(r->cfg.device);
+      rank_p2p_release(r);
+    }
+    if (want == 2) return fail(BP_ECOMM, "BP_DP=p2p: the devices cannot access each other's memory");
+    fprintf(stderr, "libbpgpu: no peer access between the devices, using NCCL all-reduce\n");
+    return BP_OK;
+  }
+  for (int i = 0; i < W; ++i)
+    for (int j = 0; j < W; ++j) {
+      Rank::PeerMem& pm = h->ranks[i]->peer[j];
+      pm.w = h->ranks[j]->w;
+      pm.w_lo = h->ranks[j]->w_lo;
+      pm.recv = h->ranks[j]->recv;
+      pm.flags = h->ranks[j]->flags;
+    }
+  for (Rank* r : h->ranks) r->dp_p2p = 1;
+  if (getenv("BP_VERBOSE")) fprintf(stderr, "libbpgpu: gradient exchange over peer memory, %d ranks (one process)\n", W);
+  return BP_OK;
+}
+
 int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes, int bunchsize, float lrate,
               float momentum, float weightcost, float* const* weights, float* const* bias, int dropoutflag,
               float visible_omit, float hid_omit) {
@@ -1164,6 +1399,7 @@ int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes,
     }
     return BP_OK;
   });
+  if (rc == BP_OK) rc = group_p2p_connect(hh);
   if (rc != BP_OK) {
     std::string keep = g_err;
     bp_destroy(hh);
@@ -1440,7 +1676,7 @@ int bp_comm_init(bp_handle* h, const char id128[128]) {
   NcclApi::Id128 uid;
   memcpy(uid.b, id128, 128);
   NCCL_TRY(g_nccl.CommInitRank(&r->nccl_comm, r->cfg.world_size, uid, r->cfg.rank));
-  return BP_OK;
+  return rank_p2p_connect_ipc(r);
 }
 
 int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame, uint32_t unit, float p) {
