@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/bp_gpu.h"
+#include "DecodeWriter.h"
 #include "Interface.h"
 
 static double now_s() {  // the reference uses time(NULL) (1 s steps); the log lines keep their format
@@ -104,8 +105,25 @@ int main(int argc, char* argv[]) {
   fprintf(io->fp_log, "Starting CV.\n");
   io->get_chunk_info_cv(para->cv_sent_range);
   float squared_err = 0.0f;
-  FILE* fdec = para->decode_FN[0] ? fopen(para->decode_FN, "wb") : nullptr;
+  DecodeWriter decw;  // enhanced frames of the CV / decode pass (the reference drops them, BP_GPU.cu:445-473)
+  if (para->decode_FN[0]) {
+    std::string err;
+    if (!decw.open(para->decode_FN, para->decode_format, para->decode_normFN,
+                   para->layersizes[io->numlayers - 1], &err)) {
+      fprintf(io->fp_log, "%s\n", err.c_str());
+      printf("%s\n", err.c_str());
+      exit(0);
+    }
+  }
+  const bool fdec = decw.active();
   std::vector<float> dec;
+  std::vector<int> rel_sent;
+  auto write_decoded = [&](int n) {
+    rel_sent.resize(n);
+    const int s0 = io->sample_sent.empty() ? 0 : io->cv_first_sentence();
+    for (int k = 0; k < n; ++k) rel_sent[k] = io->sample_sent[k] - s0;
+    decw.append(dec.data(), n, rel_sent.data(), io->sample_frame_in_sent.data());
+  };
   for (unsigned int i = 0; i < io->cv_total_chunks; ++i) {
     const int n = para->reader_gpu ? io->Readchunk_cvRaw(i, &raw) : io->Readchunk_cv(i);
     printf("cur_chunk_samples=%d\n", n);
@@ -116,7 +134,7 @@ int main(int argc, char* argv[]) {
       if (fdec) dec.resize(static_cast<size_t>(n) * para->layersizes[io->numlayers - 1]);
       if (bp_crossvalid_raw(trainer, &c, &sq, fdec ? dec.data() : nullptr) != BP_OK) die(io, "CrossValid failed");
       squared_err += sq;
-      if (fdec) fwrite(dec.data(), sizeof(float), dec.size(), fdec);
+      if (fdec) write_decoded(n);
       continue;
     }
     float s = 0.0f;
@@ -125,10 +143,10 @@ int main(int argc, char* argv[]) {
     if (fdec) {  // decode extension: enhanced (normalised-domain) LPS frames, raw little-endian float32 rows
       dec.resize(static_cast<size_t>(n) * para->layersizes[io->numlayers - 1]);
       if (bp_forward(trainer, n, para->indata, dec.data()) != BP_OK) die(io, "forward failed");
-      fwrite(dec.data(), sizeof(float), dec.size(), fdec);
+      write_decoded(n);
     }
   }
-  if (fdec) fclose(fdec);
+  decw.close();
   io->free_raw(&raw);
   const float cvacc = squared_err / io->cv_total_samples;
   fprintf(io->fp_log, "CV over. squared error: %f\n", cvacc);

@@ -69,6 +69,8 @@ const ArgSpec kArgs[] = {
     ARG("init_randem_bias_min", kFloat, init_randem_bias_min),
     ARG("nat", kInt, nat),
     ARG("decode_file", kStr, decode_FN),
+    ARG("decode_format", kStr, decode_format),
+    ARG("decode_norm_file", kStr, decode_normFN),
 };
 #undef ARG
 
@@ -431,12 +433,18 @@ std::vector<Interface::Seg> Interface::segments(int first, int n_frames, int sen
   int done = 0, frame = first, s = sent;
   while (done != n_frames) {
     const int len = (framesBeforeSent[s] > first + n_frames) ? (n_frames - done) : (framesBeforeSent[s] - frame);
-    segs.push_back({done, len});
+    segs.push_back({done, len, s});
     frame = framesBeforeSent[s];
     ++s;
     done += len;
   }
   return segs;
+}
+
+void Interface::note_sample(int cur, const Seg& sg, int first, int j) {
+  const int f = first + sg.begin + j + para->targ_offset;  // global index of the target frame
+  sample_sent[cur] = sg.sent;
+  sample_frame_in_sent[cur] = f - (sg.sent == 0 ? 0 : framesBeforeSent[sg.sent - 1]);
 }
 
 // Sample assembly — reference Readchunk Interface.cc:689-861 / Readchunk_cv :864-1034, one implementation:
@@ -474,6 +482,8 @@ int Interface::assemble(int chunk_index, const int* starts, unsigned int n_chunk
 
   const std::vector<Seg> segs = segments(first, n_frames, sent);
 
+  sample_sent.assign(samples, 0);
+  sample_frame_in_sent.assign(samples, 0);
   int cur = 0;
   for (const Seg& sg : segs) {
     float nat[4096];
@@ -495,6 +505,7 @@ int Interface::assemble(int chunk_index, const int* starts, unsigned int n_chunk
       }
     }
     for (int j = 0; j + ctx <= sg.len && cur < samples; ++j, ++cur) {
+      note_sample(cur, sg, first, j);
       float* row = para->indata + static_cast<size_t>(order[cur]) * in_w;
       std::memcpy(row, fea.data() + static_cast<size_t>(sg.begin + j) * dim, sizeof(float) * dim * ctx);
       if (use_nat) std::memcpy(row + dim * ctx, natp, sizeof(float) * dim);
@@ -583,9 +594,12 @@ int Interface::assemble_raw(int chunk_index, const int* starts, unsigned int n_c
   rc->sample_frame.resize(samples);
   rc->sample_seg.resize(samples);
   rc->sample_row.resize(samples);
+  sample_sent.assign(samples, 0);
+  sample_frame_in_sent.assign(samples, 0);
   int cur = 0;
   for (const Seg& sg : segments(first, n_frames, sent))
     for (int j = 0; j + ctx <= sg.len && cur < samples; ++j, ++cur) {
+      note_sample(cur, sg, first, j);
       rc->sample_frame[cur] = sg.begin + j;
       rc->sample_seg[cur] = sg.begin;
       rc->sample_row[cur] = order[cur];

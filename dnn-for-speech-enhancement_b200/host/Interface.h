@@ -63,6 +63,8 @@ struct WorkPara {
   int activation = 0;      // 0 relu, 1 sigmoid
   unsigned long long seed = 0x5eed5eedULL;
   char decode_FN[MAXLINE] = "";
+  char decode_format[MAXLINE] = "raw";   // raw | pfile (DecodeWriter.h)
+  char decode_normFN[MAXLINE] = "";      // optional de-normalisation of the decode output
 };
 
 // One chunk for the device-side reader: the Pfile records as they lie in the file + the sample table
@@ -91,9 +93,13 @@ class Interface {
   int ReadchunkRaw(int index, RawChunk* rc);
   int Readchunk_cvRaw(int index, RawChunk* rc);
   void free_raw(RawChunk* rc);
+  // (sentence, frame-in-sentence) of the target frame of every sample of the chunk read last, in file order (= row
+  // order for CV chunks, which are not shuffled): what a decode writer needs to label its rows
+  std::vector<int> sample_sent, sample_frame_in_sent;
   const float* norm_mean() const { return mean.data(); }
   const float* norm_inv_std() const { return dVar.data(); }
   bool nat_block() const { return use_nat; }
+  int cv_first_sentence() const { return cv_r.st; }
   void GetRandIndex(int* vec, int len);
 
   WorkPara* para;
@@ -123,7 +129,9 @@ class Interface {
   };
   struct Seg {
     int begin, len;  // record index inside the chunk's block, frames
+    int sent;        // sentence the segment belongs to
   };
+  void note_sample(int cur, const Seg& sg, int first, int j);
   std::vector<Seg> segments(int first, int n_frames, int sent) const;
   int assemble_raw(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,
                    bool shuffle, RawChunk* rc);

@@ -30,6 +30,20 @@ def write_pfile(path, sentences):
         f.write(starts.tobytes())
 
 
+def read_pfile(path):
+    """Returns (list of float32 arrays [T_i x dim], sentence ids [n_frames], frame ids [n_frames])."""
+    raw = open(path, "rb").read()
+    hdr = raw[:PFILE_HEADER_SIZE].split(b"\0", 1)[0].decode()
+    fields = {ln.split()[0]: ln.split()[1:] for ln in hdr.splitlines() if ln.startswith("-") and len(ln.split()) > 1}
+    n_sent, n_frames, dim = int(fields["-num_sentences"][0]), int(fields["-num_frames"][0]), int(fields["-num_features"][0])
+    rec = np.frombuffer(raw, dtype=">u4", count=n_frames * (2 + dim), offset=PFILE_HEADER_SIZE).reshape(n_frames, 2 + dim)
+    starts = np.frombuffer(raw, dtype=">u4", count=n_sent + 1, offset=PFILE_HEADER_SIZE + 4 * n_frames * (2 + dim))
+    assert len(raw) == PFILE_HEADER_SIZE + 4 * (n_frames * (2 + dim) + n_sent + 1)
+    data = rec[:, 2:].astype(">u4").view(">f4").astype(np.float32)
+    sents = [data[int(starts[i]):int(starts[i + 1])] for i in range(n_sent)]
+    return sents, rec[:, 0].astype(np.int64), rec[:, 1].astype(np.int64)
+
+
 def write_norm(path, mean, inv_std):
     with open(path, "w") as f:
         f.write(f"vec {len(mean)}\n")

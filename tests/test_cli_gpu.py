@@ -80,3 +80,30 @@ def test_bptrain_device_reader_equals_host_reader(gpus):
         assert _cv(f"{d}/host.log") == _cv(f"{d}/gpu.log")
         assert open(f"{d}/host.dec", "rb").read() == open(f"{d}/gpu.dec", "rb").read()
         assert os.path.getsize(f"{d}/gpu.dec") > 0
+
+
+@pytest.mark.skipif(not os.path.exists(OURS), reason="BPtrain not built")
+def test_bptrain_decode_pfile_lines_up_with_targets():
+    """decode_format=pfile: the enhanced frames come out as a Pfile whose (sentence, frame) ids are
+    those of the clean-target frames they estimate, holding the same values as the raw decode output."""
+    T = importlib.import_module("dnn-for-speech-enhancement_b200.tools.pfile")
+    with tempfile.TemporaryDirectory() as d:
+        feas, targs, mu, ivar = T.synth_corpus(40, 129, 129, seed=3, min_len=8, max_len=60)
+        T.write_pfile(f"{d}/fea.pfile", feas)
+        T.write_pfile(f"{d}/targ.pfile", targs)
+        T.write_norm(f"{d}/fea.norm", mu, ivar)
+        for tag, extra in (("raw", [f"decode_file={d}/raw.dec", "reader=gpu"]),
+                           ("pf", [f"decode_file={d}/pf.dec", "decode_format=pfile", "reader=host"])):
+            o = subprocess.run([OURS] + _args(d, tag, extra), cwd=d, capture_output=True, text=True, timeout=600)
+            assert o.returncode == 1, o.stdout + o.stderr
+        raw = np.fromfile(f"{d}/raw.dec", dtype="<f4").reshape(-1, 129)
+        sents, sid, fid = T.read_pfile(f"{d}/pf.dec")
+    assert np.array_equal(np.vstack([s for s in sents if len(s)]), raw)
+    # CV range is sentences 30-39 (see _args): every sentence of T >= 11 frames yields frames 5 .. T-6
+    want_sid, want_fid = [], []
+    for k, s in enumerate(range(30, 40)):
+        n = feas[s].shape[0]
+        for j in range(max(0, n - 10)):
+            want_sid.append(k)
+            want_fid.append(j + 5)
+    assert sid.tolist() == want_sid and fid.tolist() == want_fid
