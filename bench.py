@@ -265,7 +265,7 @@ def main():
         t_wait = time.perf_counter()
         while not sampler.rows and time.perf_counter() - t_wait < 3.0:
             time.sleep(0.01)
-        run_resident(W)
+    run_resident(W)  # EVERY rank: a bunch is a collective step (gradient exchange), ranks must run the same count
     launches0 = g.counters()[0]
     barrier()
     sampler.in_region = True

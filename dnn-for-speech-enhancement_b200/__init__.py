@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
     lib.bp_train_resident.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bp_forward_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.POINTER(C.c_double)]
     lib.bp_sync.argtypes = [C.c_void_p]
+    lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_crossvalid_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp, _fp]
@@ -317,6 +318,12 @@ class BP_GPU:
 
     def sync(self) -> None:
         _check(load_library().bp_sync(self._h), "bp_sync")
+
+    def begin_epoch(self, lrate: float, momentum: float, weightcost: float, reset_dropout_step: bool = True) -> None:
+        """Epoch boundary inside one process: zero momentum deltas, new hyper-parameters, weights stay on the device —
+        the state a fresh reference process starts from (BP_GPU.cu:10, 137-138) minus the .wts round-trip."""
+        _check(load_library().bp_begin_epoch(self._h, lrate, momentum, weightcost, int(reset_dropout_step)),
+               "bp_begin_epoch")
 
     def timer_start(self) -> None:
         _check(load_library().bp_timer_start(self._h), "bp_timer_start")

@@ -189,6 +189,60 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
   }
 }
 
+// EPI_DX with the Y operand (aux) software-pipelined: kernDsigmoid + kernVecMul (DevFunc.cu:81-97, 244-250) need
+// Y[frame][unit] for every accumulator element; loading it only after the accumulator is complete put ~2.5 us of
+// exposed global-load latency per 32-column chunk at the end of every dX GEMM (isolated 2048x1024x2048: dX 28.4 us vs
+// 18.4 us for the forward product of the same size, profiles/r1d).  The epilogue warps are idle during the main loop, so
+// they fetch the first two chunks then, and chunk c+2 while chunk c+1 is processed.
+struct DxPrefetch {
+  float y[2][32];
+  __device__ __forceinline__ void load(const GemmParams& p, int slot, int m, bool m_ok, int nc) {
+    if (!m_ok || nc >= p.N) return;
+    const float* a = p.aux + size_t(nc) * p.ldaux + m;
+    const bool whole = nc + 32 <= p.N;
+#pragma unroll
+    for (int j = 0; j < 32; ++j, a += p.ldaux) y[slot][j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
+  }
+  __device__ __forceinline__ void start(const GemmParams& p, int m, bool m_ok, int n0) {
+    load(p, 0, m, m_ok, n0);
+    load(p, 1, m, m_ok, n0 + 32);
+  }
+};
+
+__device__ __forceinline__ void gemm_dx_store(const GemmParams& p, const uint32_t (&v)[32], const float (&yv)[32], int m,
+                                              bool m_ok, int nc) {
+  if (!m_ok) return;
+  const bool whole = nc + 32 <= p.N;
+  float* o = p.out + size_t(nc) * p.ldo + m;
+#pragma unroll
+  for (int j = 0; j < 32; ++j, o += p.ldo)
+    if (whole || nc + j < p.N) {
+      const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
+      *o = dv;
+      if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
+    }
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void gemm_dx_epilogue(const GemmParams& p, DxPrefetch& pre, uint32_t taddr, int m, bool m_ok,
+                                                 int n0) {
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N / 32; c += 2) {
+    const int nc = n0 + c * 32;
+    if (nc >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + uint32_t(c * 32), v);
+    tmem_ld_wait();
+    gemm_dx_store(p, v, pre.y[0], m, m_ok, nc);
+    if (c + 2 < BLOCK_N / 32) pre.load(p, 0, m, m_ok, nc + 64);
+    if (nc + 32 >= p.N) break;
+    tmem_ld32(taddr + uint32_t((c + 1) * 32), v);
+    tmem_ld_wait();
+    gemm_dx_store(p, v, pre.y[1], m, m_ok, nc + 32);
+    if (c + 3 < BLOCK_N / 32) pre.load(p, 1, m, m_ok, nc + 96);
+  }
+}
+
 template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -365,25 +419,31 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile % num_m_tiles) * BLOCK_M;
       const int n0 = p.n_begin + (tile / num_m_tiles) * BLOCK_N;
       const size_t plane_off = size_t(t / num_tiles) * size_t(p.split_stride);
+      const int m = m0 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      DxPrefetch pre;
+      if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);  // under the main loop (see gemm_dx_epilogue)
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
       if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool m_ok = m < p.M;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
       if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
+      if constexpr (kEpi == EPI_DX) {
+        gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(taddr + uint32_t(c * 32), v);
-        tmem_ld_wait();
-        gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local, plane_off);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int nc = n0 + c * 32;
+          if (nc >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + uint32_t(c * 32), v);
+          tmem_ld_wait();
+          gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local, plane_off);
+        }
       }
       tc_fence_before();
       __syncwarp();

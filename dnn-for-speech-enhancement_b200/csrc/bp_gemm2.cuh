@@ -20,6 +20,17 @@
 //   * tempty[b] (leader only, count 8): one arrival per epilogue warp of BOTH CTAs (the peer's arrive remotely).
 //   The peer CTA's warp 1 only allocates / frees TMEM.  Everything else (3-D tensor maps, descriptors, warp-uniform
 //   role loops, elect.sync, one polling lane, PDL, 3xTF32 passes, column slices) is as in bp_gemm.cuh.
+//
+// Multicast clusters (CP = 2 or 4 pairs per cluster).  The ncu captures of the pair kernels show the L2 -> SM path, not
+// the tensor pipe, as the binding roof: 4.0-5.2 KB/clk chip-wide against a ~6.3 KB/clk cap (profiles/r1c, B300_MICROARCH
+// "LTS throughput cap"), i.e. ~42 B/clk/SM where a 256 x 128 pair tile of fp32 operands asks for 96.  CP pairs of one
+// cluster therefore work on CP neighbouring N tiles of the SAME 256 rows of A, and every CTA fetches only 1/CP of its A
+// block and multicasts it to the CTAs of the same parity in all pairs (cp.async.bulk.tensor ... .cta_group::2
+// .multicast::cluster; each destination's bytes complete on ITS pair leader's full barrier).  Per CTA and k-block the L2
+// traffic drops from 32 KB + B to 32/CP KB + B.  Protocol changes: empty[s] counts CP arrivals — every pair leader's
+// commit is multicast to ALL CTAs of the cluster, because a CTA's A slice is written into every pair's shared memory;
+// tfull commits go to the own pair only; tempty arrivals go to the own pair's leader.  Pairs whose columns lie beyond N
+// run the same protocol on zero-filled boxes and store nothing.
 #pragma once
 #include "bp_gemm.cuh"
 
@@ -37,11 +48,16 @@ constexpr size_t gemm2_smem_bytes() {
   return size_t(gemm2_stages<PAIR_N>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
+// A-slice boxes of the multicast variant (host side builds the tensor maps with these, see make_map1):
+//   MN-major A: {32, 64 k-rows, (128/CP)/32 mn-chunks}      slice pi = mn-chunks [pi*4/CP, (pi+1)*4/CP) of the 128-row block
+//   K-major  A: {32, 128 rows (CP=2) | 64 rows (CP=4), 1 k-chunk}   slice pi = k-chunk pi/(CP/2), row part pi%(CP/2)
+// In both layouts slice pi occupies bytes [pi, pi+1) * A_BYTES/CP of the stage's A block.
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                 const GemmParams p) {
+  static_assert(CP == 1 || CP == 2 || CP == 4, "pairs per cluster");
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = PAIR_N, kStages = gemm2_stages<PAIR_N>();
   static_assert(PAIR_N == 128 || PAIR_N == 256, "PAIR_N");
   constexpr int HALF_N = BLOCK_N / 2;                    // B columns staged by each CTA
@@ -70,26 +86,29 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kPollLane = 1;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();    // rank in the cluster of 2*CP CTAs
+  const uint32_t rank = crank & 1u;            // position in my pair (0 = leader)
+  const uint32_t pi = crank >> 1;              // my pair's index in the cluster
   const bool leader = rank == 0;
 
   const int num_m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);            // pair tiles along M
-  const int num_n_tiles = (p.N - p.n_begin + BLOCK_N - 1) / BLOCK_N;
+  const int num_n_tiles = (p.N - p.n_begin + CP * BLOCK_N - 1) / (CP * BLOCK_N);  // cluster tiles along N
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_it = num_kb * (p.passes == 3 ? 3 : 1);
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int pair = blockIdx.x / (2 * CP), num_pairs = gridDim.x / (2 * CP);  // cluster index / count
+  constexpr uint16_t kAllCtas = uint16_t((1u << (2 * CP)) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CP);  // one multicast commit per pair of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (used in the pair leader only)
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -112,7 +131,7 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t ph = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;       // my 128 rows of A
-      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N + int(rank) * HALF_N;  // my half of B
+      const int n0 = p.n_begin + ((t / num_m_tiles) * CP + int(pi)) * BLOCK_N + int(rank) * HALF_N;  // my half of B
       for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
         if (kb == num_kb) { kb = 0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? &tmAlo : &tmA;
@@ -123,10 +142,21 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);  // both CTAs' bytes land on the leader's barrier
-          const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
           const int b1 = kBMN ? kb * BLOCK_K : n0, b2 = kBMN ? n0 / 32 : kb * (BLOCK_K / 32);
-          tma_load_3d_2sm(sa, mapA, &full[s], 0, a1, a2);
-          tma_load_3d_2sm(sb, mapB, &full[s], 0, b1, b2);
+          if constexpr (CP == 1) {
+            const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
+            if (p.hint_a) tma_load_3d_2sm_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
+            else tma_load_3d_2sm(sa, mapA, &full[s], 0, a1, a2);
+          } else {
+            // my 1/CP of the A block, to the CTAs of my parity in every pair of the cluster
+            constexpr uint16_t kParityMask = CP == 2 ? 0x5 : 0x55;
+            constexpr int kRowParts = CP / 2;  // K-major: row parts per k-chunk
+            const int a1 = kAMN ? kb * BLOCK_K : m0 + int(pi % kRowParts) * (BLOCK_M / kRowParts);
+            const int a2 = kAMN ? m0 / 32 + int(pi) * (BLOCK_M / 32 / CP) : kb * (BLOCK_K / 32) + int(pi / kRowParts);
+            tma_load_3d_2sm_mc(sa + pi * (A_BYTES / CP), mapA, &full[s], 0, a1, a2, uint16_t(kParityMask << rank));
+          }
+          if (p.hint_b) tma_load_3d_2sm_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
+          else tma_load_3d_2sm(sb, mapB, &full[s], 0, b1, b2);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -161,8 +191,8 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               umma_tf32_2sm(d_tmem, a_lo + (a_off >> 4), kAMN ? kDescHiMN : kDescHiK, b_lo + (b_off >> 4),
                             kBMN ? kDescHiMN : kDescHiK, idesc, (k != 0 || kb != 0) ? 1u : 0u);
             }
-            umma_commit_2sm(&empty[s], 0x3);                      // slot s is free again in BOTH CTAs
-            if (kb == num_it - 1) umma_commit_2sm(&tfull[as], 0x3);  // accumulators complete in both CTAs
+            umma_commit_2sm(&empty[s], kAllCtas);                 // this pair is done with slot s: tell every CTA
+            if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u << (2 * pi)));  // accumulators complete
           }
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -179,31 +209,39 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float sq_local = 0.0f;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;  // my 128 accumulator rows
-      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;                // all 256 columns of the pair tile
+      const int n0 = p.n_begin + ((t / num_m_tiles) * CP + int(pi)) * BLOCK_N;  // all columns of my pair's tile
+      const int m = m0 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      // EPI_DX: the Y values of the first two column chunks are fetched BEFORE waiting for the accumulator, i.e. under
+      // the main loop, and the following chunks two steps ahead of their use (see gemm_dx_epilogue).
+      DxPrefetch pre;
+      if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool m_ok = m < p.M;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
       if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
+      if constexpr (kEpi == EPI_DX) {
+        gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(taddr + uint32_t(c * 32), v);
-        tmem_ld_wait();
-        gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int nc = n0 + c * 32;
+          if (nc >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + uint32_t(c * 32), v);
+          tmem_ld_wait();
+          gemm_epilogue_chunk<kEpi>(p, v, m, m_ok, nc, bias, sq_local);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(&tempty[as]);
-        else mbar_arrive_remote(&tempty[as], 0);
+        else mbar_arrive_remote(&tempty[as], crank & ~1u);
       }
       as ^= 1;
       if (as == 0) aph ^= 1u;

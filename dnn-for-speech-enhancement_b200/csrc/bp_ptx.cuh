@@ -155,6 +155,26 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Same load with an L2 eviction-priority hint (kEvictLast keeps the weights resident across the bunch).
+__device__ __forceinline__ void tma_load_3d_2sm_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                     int c1, int c2, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+// Same load, MULTICAST: the box lands at the same CTA-relative shared-memory offset in every CTA of `cta_mask`, and each
+// destination's bytes complete on the barrier (same offset) of that destination's pair leader — the CTA of its pair with
+// the parity of the barrier address passed here (even, see leader_addr).
+__device__ __forceinline__ void tma_load_3d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                   int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
 // mbarrier.arrive on the same barrier in CTA `rank` of the cluster.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(

@@ -87,8 +87,10 @@ int get_encode() {
 //                    SWIZZLE_128B.
 //   MN-major operand (M/N dim contiguous):       rows = exact K extent,   chunks = ceil(MN/32); box {32, 64, box_mn/32};
 //                    SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands).
+//   A-slice maps of the multicast clusters (bp_gemm2.cuh): MN-major box_outer = 128/CP; K-major box_outer = 128 or 64
+//   rows with k_chunks = 1 (one 32-wide k-chunk per box instead of the whole 64-deep stage).
 int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
-              int box_outer, bool mn_major) {
+              int box_outer, bool mn_major, int k_chunks = GEMM_BLOCK_K / 32) {
   BP_TRY(get_encode());
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 31) != 0)
     return fail(BP_EINVAL, "tensor map: base not 16-byte aligned or ld %% 32 != 0 (ld=%lld)", ld);
@@ -97,7 +99,7 @@ int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, lo
   cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(chunks)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128};
   cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? GEMM_BLOCK_K : box_outer),
-                       static_cast<cuuint32_t>(mn_major ? box_outer / 32 : GEMM_BLOCK_K / 32)};
+                       static_cast<cuuint32_t>(mn_major ? box_outer / 32 : k_chunks)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -115,10 +117,29 @@ struct MapPair {
   CUtensorMap lo;
 };
 int make_map(MapPair* mp, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
-             long long ld, int box_outer, bool mn_major) {
-  BP_TRY(make_map1(&mp->m, base, contiguous_extent, rows, ld, box_outer, mn_major));
-  if (lo_base) BP_TRY(make_map1(&mp->lo, lo_base, contiguous_extent, rows, ld, box_outer, mn_major));
+             long long ld, int box_outer, bool mn_major, int k_chunks = GEMM_BLOCK_K / 32) {
+  BP_TRY(make_map1(&mp->m, base, contiguous_extent, rows, ld, box_outer, mn_major, k_chunks));
+  if (lo_base) BP_TRY(make_map1(&mp->lo, lo_base, contiguous_extent, rows, ld, box_outer, mn_major, k_chunks));
   else mp->lo = mp->m;
+  return BP_OK;
+}
+
+// The A operand of a product: the whole-block map (128 rows per box) plus the 1/2 and 1/4 slice maps the multicast
+// clusters load (slice[0]: CP = 2, slice[1]: CP = 4).
+struct AMaps {
+  MapPair full;
+  MapPair slice[2];
+};
+int make_a_maps(AMaps* am, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
+                long long ld, bool mn_major) {
+  BP_TRY(make_map(&am->full, base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, mn_major));
+  if (mn_major) {
+    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, true));
+    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 4, true));
+  } else {
+    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, false, 1));
+    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, false, 1));
+  }
   return BP_OK;
 }
 
@@ -169,36 +190,70 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
   return BP_OK;
 }
 
-// CTA-pair (cta_group::2) variant: 256 x 256 pair tiles, cluster of 2.  Same tensor maps (boxes of 128 rows/columns).
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
-int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N>;
-  constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
-  static thread_local int configured_dev = -1;
-  static thread_local int max_pairs = 0;
-  int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_pairs = num_sms / 2;
+// CTA-pair (cta_group::2) variant: 256 x PAIR_N pair tiles, CP pairs per cluster sharing their A rows by TMA multicast
+// (CP = 1: plain pairs).  `a` is the A map the kernel loads with: the whole-block map for CP = 1, the slice map else.
+// Clusters that can be co-resident (GPC granularity) per (PAIR_N, CP), filled by the first launch of each shape.
+int g_max_clusters[2][3] = {{0, 0, 0}, {0, 0, 0}};
+inline int& max_clusters_slot(int pair_n, int cp) { return g_max_clusters[pair_n == 256][cp == 1 ? 0 : cp == 2 ? 1 : 2]; }
+
+// Occupancy depends on the cluster size and the shared-memory size only, so one instantiation per (PAIR_N, CP) answers
+// for all of them.  Called once per device before the first kernel choice (rank_create / bp_debug_gemm).
+template <int PAIR_N, int CP>
+void query_cluster_capacity(int num_sms) {
+  auto kern = bp_gemm2_kernel<true, false, EPI_FWD_HID, PAIR_N, CP>;
+  constexpr int kCluster = 2 * CP;
+  int cap = num_sms / kCluster;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm2_smem_bytes<PAIR_N>()) ==
+      cudaSuccess) {
     cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3(num_sms / 2 * 2);
+    qc.gridDim = dim3(num_sms / kCluster * kCluster);
     qc.blockDim = dim3(GEMM_THREADS);
-    qc.dynamicSmemBytes = smem;
+    qc.dynamicSmemBytes = gemm2_smem_bytes<PAIR_N>();
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.x = kCluster;
     qa[0].val.clusterDim.y = 1;
     qa[0].val.clusterDim.z = 1;
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) max_pairs = std::min(n, num_sms / 2);
-    else cudaGetLastError();
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) cap = std::min(n, cap);
+  }
+  cudaGetLastError();
+  max_clusters_slot(PAIR_N, CP) = cap;
+}
+void init_cluster_capacity(int num_sms) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (g_max_clusters[0][0] > 0) return;
+  query_cluster_capacity<128, 2>(num_sms);
+  query_cluster_capacity<128, 4>(num_sms);
+  query_cluster_capacity<256, 1>(num_sms);
+  query_cluster_capacity<256, 2>(num_sms);
+  query_cluster_capacity<256, 4>(num_sms);
+  query_cluster_capacity<128, 1>(num_sms);
+  if (getenv("BP_VERBOSE"))
+    fprintf(stderr, "libbpgpu: co-resident clusters  128-wide pairs x1/x2/x4: %d %d %d   256-wide: %d %d %d\n",
+            g_max_clusters[0][0], g_max_clusters[0][1], g_max_clusters[0][2], g_max_clusters[1][0],
+            g_max_clusters[1][1], g_max_clusters[1][2]);
+}
+
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP>
+int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP>;
+  constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
+  constexpr int kCluster = 2 * CP;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_dev = dev;
   }
+  init_cluster_capacity(num_sms);
+  const int max_clusters = max_clusters_slot(PAIR_N, CP);
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const int nt = (p.N - p.n_begin + PAIR_N - 1) / PAIR_N;
+  const int nt = (p.N - p.n_begin + CP * PAIR_N - 1) / (CP * PAIR_N);
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   static const bool use_pdl = [] {
@@ -206,19 +261,20 @@ int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& 
     return e ? atoi(e) != 0 : true;
   }();
   static const bool use_hints = [] {
-    const char* e = getenv("BP_TMA_HINT");
+    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
     return e ? atoi(e) != 0 : true;
   }();
   GemmParams q = p;
-  (void)use_hints;  // the pair kernel issues plain loads (cta_group::2 loads carry no cache-hint operand here)
+  if (!use_hints || CP > 1) q.hint_a = 0;  // the multicast A-slice load carries no hint
+  if (!use_hints) q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(std::min(tiles, std::min(max_pairs, num_sms / 2)) * 2);
+  cfg.gridDim = dim3(std::min(tiles, std::min(max_clusters, num_sms / kCluster)) * kCluster);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -229,22 +285,37 @@ int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& 
   return BP_OK;
 }
 
-// Kernel choice per product.  BP_PAIRS: 0 = lone CTAs only, 1 = automatic (default), 2 = 256-wide pairs always,
-// 3 = 128-wide pairs whenever the narrow B map exists.  Automatic: 256 x 256 pair tiles if they fill >= 60 % of the SM
-// pairs, else 256 x 128 pair tiles under the same condition, else 128 x 128 tiles on lone CTAs.
-inline int pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
+// Kernel choice per product: {pair_n, cp}; pair_n = 0 -> 128 x 128 tiles on lone CTAs.
+//   BP_PAIRS: 0 = lone CTAs only, 1 = automatic (default), 2 = 256-wide pairs always, 3 = 128-wide pairs whenever the
+//             narrow B map exists.
+//   BP_MC:    pairs per multicast cluster when a pair kernel is chosen: 1 = none (default), 2, 4 (experimental, see
+//             measured no gain on K-major A, MN-major A slices not yet correct).
+// Automatic: 256 x 256 pair tiles if they fill >= 60 % of the SM pairs, else 256 x 128 pair tiles under the same
+// condition, else 128 x 128 tiles on lone CTAs.  Measured in isolation on the B200 (scripts/gpu_mc_probe.py, r1d):
+// 2048x1024x2048 fwd 18.4 us on 128-wide pairs vs 25.9 us on 256-wide ones (64 CTAs); 2048x2049x1024 dW 17.6 us on
+// 256-wide pairs vs 19.5 us on 128-wide ones — the rule picks the faster one in every product of C2/C3/C5.
+struct KernelChoice {
+  int pair_n;
+  int cp;
+};
+inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
   static const int mode = [] {
     const char* e = getenv("BP_PAIRS");
     return e ? atoi(e) : 1;
   }();
-  if (mode == 0) return 0;
-  if (mode == 2) return 256;
-  if (mode == 3) return have_b64 ? 128 : 0;
+  static const int cp = [] {
+    const char* e = getenv("BP_MC");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4) ? v : 1;
+  }();
+  if (mode == 0) return {0, 1};
+  if (mode == 2) return {256, cp};
+  if (mode == 3) return {have_b64 ? 128 : 0, cp};
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
   const int n = p.N - p.n_begin;
-  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return 256;
-  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return 128;
-  return 0;
+  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return {256, cp};
+  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return {128, cp};
+  return {0, 1};
 }
 
 // Tile width along N.  The B-operand tensor map's box must match (kBoxN below is what make_map is called with).
@@ -254,12 +325,20 @@ constexpr int kMaxSplits = 8;  // split-K planes of the output-layer product (se
 // b = B operand map with 128-wide boxes (lone CTAs and 256-wide pairs); b64 = the same operand with 64-wide boxes
 // (128-wide pairs: each CTA stages 64 B columns), or null.
 template <bool kAMN, bool kBMN, int kEpi>
-int launch_gemm(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p,
+int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
                 const MapPair* b64 = nullptr) {
-  const int k = pick_kernel(p, num_sms, b64 != nullptr);
-  if (k == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256>(st, num_sms, a, b, p);
-  if (k == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128>(st, num_sms, a, *b64, p);
-  return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a, b, p);
+  const KernelChoice k = pick_kernel(p, num_sms, b64 != nullptr);
+  if (k.pair_n == 256) {
+    if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
+    if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
+    return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+  }
+  if (k.pair_n == 128) {
+    if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
+    if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
+    return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
+  }
+  return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (lazy dlopen)
@@ -320,14 +399,14 @@ struct LayerState {
   float* d_lo = nullptr;
   long long ldd = 0;
   // tensor maps that do not depend on the chunk
-  MapPair w_fwd;       // W^T as MN-major A: {N, K}, box {32,32}
-  MapPair w_dx;        // W as K-major A:    {N, K}, box {32,128}
+  AMaps w_fwd;         // W^T as MN-major A: {N, K}
+  AMaps w_dx;          // W as K-major A:    {N, K}
   MapPair yprev_fwd;   // Y_{l-1} as K-major B (l >= 2): {K, rows}, box {32,kBlockN}
   MapPair yprev_fwd64; // same, 64-row boxes (128-wide CTA pairs)
   MapPair d_dx64;      // D_l as K-major B, 64-row boxes
   MapPair yprev_dw;    // Y_{l-1}^T as MN-major B (l >= 2): {K+1, bunch}, box {32,32}
   MapPair d_dx;        // D_l as K-major B: {N, bunch}, box {32,kBlockN}
-  MapPair d_dw;        // D_l^T as MN-major A: {N, bunch}, box {32,32}
+  AMaps d_dw;          // D_l^T as MN-major A: {N, bunch}
 };
 
 struct ChunkBuf {
@@ -636,11 +715,11 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
       LayerState& ls = r->layer[l];
       const float* wl = r->w + ls.off;
       const float* wlo = r->w_lo ? r->w_lo + ls.off : nullptr;
-      BP_TRY(make_map(&ls.w_fwd, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, true));
-      BP_TRY(make_map(&ls.w_dx, wl, wlo, ls.N, ls.K, ls.ldN, GEMM_BLOCK_M, false));
+      BP_TRY(make_a_maps(&ls.w_fwd, wl, wlo, ls.N, ls.K, ls.ldN, true));
+      BP_TRY(make_a_maps(&ls.w_dx, wl, wlo, ls.N, ls.K, ls.ldN, false));
       BP_TRY(make_map(&ls.d_dx, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, kBlockN, false));
       BP_TRY(make_map(&ls.d_dx64, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, 64, false));
-      BP_TRY(make_map(&ls.d_dw, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, GEMM_BLOCK_M, true));
+      BP_TRY(make_a_maps(&ls.d_dw, ls.d, ls.d_lo, ls.N, r->local_bunch, ls.ldd, true));
       if (l >= 2) {
         LayerState& lp = r->layer[l - 1];
         BP_TRY(make_map(&ls.yprev_fwd, lp.y, lp.y_lo, ls.K, rows, lp.ldy, kBlockN, false));
@@ -876,7 +955,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
         g.out = r->splitk_ws;
         g.out_lo = nullptr;
         g.ldo = ls.ldN;
-        BP_TRY((launch_gemm_bn<true, false, EPI_PLAIN, kBlockN>(r->compute, r->gemm_sms(), ls.w_fwd, *bmap, g)));
+        BP_TRY((launch_gemm_bn<true, false, EPI_PLAIN, kBlockN>(r->compute, r->gemm_sms(), ls.w_fwd.full, *bmap, g)));
         r->launches++;
         p.k_splits = splits;
         p.split_stride = g.split_stride;
@@ -1529,6 +1608,21 @@ int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
   return bp_train_resident(h, 0, nb);
 }
 
+int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, int reset_dropout_step) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  return for_each_rank(h, [&](int i) -> int {
+    Rank* r = h->ranks[i];
+    CU_TRY(cudaSetDevice(r->cfg.device));
+    r->cfg.lrate = lrate;
+    r->cfg.momentum = momentum;
+    r->cfg.weightcost = weightcost;
+    if (reset_dropout_step) r->step = 0;
+    // stream order: after the last bunch of the previous epoch, before the first of the next
+    CU_TRY(cudaMemsetAsync(r->dw, 0, sizeof(float) * (size_t)r->arena_floats, r->compute));
+    return BP_OK;
+  });
+}
+
 int bp_forward_resident(bp_handle* h, int first_frame, int n_frames, float* out_host, double* sum_sq_err) {
   if (!h) return fail(BP_EINVAL, "null handle");
   return rank_forward_resident(h->ranks[0], first_frame, n_frames, out_host, sum_sq_err);
@@ -1739,8 +1833,9 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       CU_TRY(cudaGetLastError());
       CU_TRY(cudaDeviceSynchronize());
     }
-    MapPair ma, mb;
-    BP_TRY(make_map(&ma, dA, dAlo, a_cols, a_rows, dlda, GEMM_BLOCK_M, amn));
+    AMaps ma;
+    MapPair mb;
+    BP_TRY(make_a_maps(&ma, dA, dAlo, a_cols, a_rows, dlda, amn));
     BP_TRY(make_map(&mb, dB, dBlo, b_cols, b_rows, dldb, kBlockN, bmn));
     MapPair mb64;
     BP_TRY(make_map(&mb64, dB, dBlo, b_cols, b_rows, dldb, 64, bmn));

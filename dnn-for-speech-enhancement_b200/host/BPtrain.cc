@@ -5,6 +5,11 @@
 //           train_sent_range=a-b cv_sent_range=c-d fea_dim=.. fea_context=.. targ_offset=.. traincache=.. bunchsize=..
 //           layersizes=a,b,.. lrate=.. momentum=.. weightcost=.. dropoutflag=.. visible_omit=.. hid_omit=..
 //           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=.. reader=host|gpu]
+//           [epochs=N epoch_first=1 momentum_step=0.04 momentum_max=0.9 seed_step=345  with %d in outwts_file/log_file]
+//
+// epochs=N (> 1) runs the Perl driver's loop (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-249) inside this
+// process: weights stay on the device between epochs, every epoch still writes its own .wts and log, and the files are
+// byte-identical to N chained single-epoch invocations (tests/test_cli_gpu.py).
 //
 // Success exit status is 1 and every error path is "log + exit(0)", as in the reference (BPtrain.cc:100; App. D Q10).
 // The Perl epoch driver (finetune_DNN_speech_enhancement_dropout_NAT.pl) works unmodified against this binary.
@@ -50,29 +55,9 @@ static bp_raw_chunk as_abi(const Interface* io, const RawChunk& rc) {
   return c;
 }
 
-int main(int argc, char* argv[]) {
-  const double t_start = now_s();
-
-  Interface* io = new Interface;
-  io->host_alloc = bp_host_alloc;  // page-locked chunk buffers -> asynchronous H2D overlapping the next Readchunk
-  io->host_free = bp_host_free;
-  io->Initial(argc, argv);
+// One epoch: training pass over the shuffled chunks, weight dump, CV pass (BPtrain.cc:36-92).
+static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
   WorkPara* para = io->para;
-
-  if (para->activation == 1) setenv("BP_ACTIVATION", "sigmoid", 1);
-  {
-    char buf[64];
-    snprintf(buf, sizeof buf, "%llu", para->seed);
-    setenv("BP_SEED", buf, 1);
-  }
-  bp_handle* trainer = nullptr;
-  if (bp_create(&trainer, para->gpu_used, io->numlayers, para->layersizes, para->bunchsize, para->lrate,
-                para->momentum, para->weightcost, para->weights, para->bias, para->dropoutflag, para->visible_omit,
-                para->hid_omit) != BP_OK)
-    die(io, "GPU trainer creation failed");
-
-  io->get_pfile_info();
-
   // ---- train (BPtrain.cc:36-54)
   io->get_chunk_info(para->train_sent_range);
   std::vector<int> chunk_index(io->total_chunks);
@@ -152,10 +137,45 @@ int main(int argc, char* argv[]) {
   fprintf(io->fp_log, "CV over. squared error: %f\n", cvacc);
   fflush(io->fp_log);
 
-  const double t_total = now_s() - t_start;
+  const double t_total = now_s() - t_epoch0;
   fprintf(io->fp_log, "Total cost time: %.1f s.\n", t_total);
   if (t_train > 0)  // added line: throughput of the training pass, reader included
     fprintf(io->fp_log, "Training throughput: %.0f frames/sec.\n", trained_samples / t_train);
+  fflush(io->fp_log);
+}
+
+int main(int argc, char* argv[]) {
+  const double t_start = now_s();
+
+  Interface* io = new Interface;
+  io->host_alloc = bp_host_alloc;  // page-locked chunk buffers -> asynchronous H2D overlapping the next Readchunk
+  io->host_free = bp_host_free;
+  io->Initial(argc, argv);
+  WorkPara* para = io->para;
+
+  if (para->activation == 1) setenv("BP_ACTIVATION", "sigmoid", 1);
+  {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%llu", para->seed);
+    setenv("BP_SEED", buf, 1);
+  }
+  bp_handle* trainer = nullptr;
+  if (bp_create(&trainer, para->gpu_used, io->numlayers, para->layersizes, para->bunchsize, para->lrate,
+                para->momentum, para->weightcost, para->weights, para->bias, para->dropoutflag, para->visible_omit,
+                para->hid_omit) != BP_OK)
+    die(io, "GPU trainer creation failed");
+
+  io->get_pfile_info();
+
+  run_epoch(io, trainer, t_start);
+  for (int epoch = 1; epoch < para->epochs; ++epoch) {
+    // what a fresh process started by the Perl driver would begin with (bp_gpu.h: bp_begin_epoch), minus the weight
+    // round-trip through the .wts file
+    const double t0 = now_s();
+    const float m = io->begin_epoch(epoch);
+    if (bp_begin_epoch(trainer, para->lrate, m, para->weightcost, 1) != BP_OK) die(io, "begin_epoch failed");
+    run_epoch(io, trainer, t0);
+  }
 
   printf("all finish!\n");
   bp_destroy(trainer);

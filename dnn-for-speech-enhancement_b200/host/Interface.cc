@@ -71,7 +71,20 @@ const ArgSpec kArgs[] = {
     ARG("decode_file", kStr, decode_FN),
     ARG("decode_format", kStr, decode_format),
     ARG("decode_norm_file", kStr, decode_normFN),
+    ARG("epochs", kInt, epochs),
+    ARG("epoch_first", kInt, epoch_first),
+    ARG("momentum_step", kFloat, momentum_step),
+    ARG("momentum_max", kFloat, momentum_max),
+    ARG("seed_step", kInt, seed_step),
 };
+
+// "%d" in a file-name pattern -> the epoch number (the Perl driver's mlp.$i.wts / mlp.$i.log, .pl:134-135).
+std::string epoch_name(const char* pattern, int number) {
+  std::string s(pattern);
+  const size_t pos = s.find("%d");
+  if (pos != std::string::npos) s.replace(pos, 2, std::to_string(number));
+  return s;
+}
 #undef ARG
 
 }  // namespace
@@ -111,6 +124,76 @@ void Interface::fatal(const char* fmt, ...) {
   exit(0);
 }
 
+// Parameter echo, byte-compatible with reference Interface.cc:267-298 (logs were machine-read, .pl:113-121).
+void Interface::echo_parameters() {
+  fprintf(fp_log, "parameters input:\n");
+  fprintf(fp_log, "fea_file:             %s\n", para->fea_FN);
+  fprintf(fp_log, "norm_file:            %s\n", para->fea_normFN);
+  fprintf(fp_log, "targ_file:            %s\n", para->targ_FN);
+  fprintf(fp_log, "outwts_file:          %s\n", para->out_weightFN);
+  fprintf(fp_log, "log_file:		          %s\n", para->log_FN);
+  fprintf(fp_log, "initwts_file:         %s\n", para->init_weightFN);
+  fprintf(fp_log, "train_sent_range:     %s\n", para->train_sent_range);
+  fprintf(fp_log, "cv_sent_range:        %s\n", para->cv_sent_range);
+  fprintf(fp_log, "fea_dim:		          %d\n", para->fea_dim);
+  fprintf(fp_log, "fea_context:		      %d\n", para->fea_context);
+  fprintf(fp_log, "bunchsize:		        %d\n", para->bunchsize);
+  fprintf(fp_log, "gpu_used:		          %d\n", para->gpu_used);
+  fprintf(fp_log, "train_cache:		      %d\n", para->traincache);
+  fprintf(fp_log, "init_randem_seed:		  %d\n", para->init_randem_seed);
+  fprintf(fp_log, "targ_offset:		      %d\n", para->targ_offset);
+  fprintf(fp_log, "dropoutflag:		      %d\n", para->dropoutflag);
+  fprintf(fp_log, "init_randem_weight_max:		  %f\n", para->init_randem_weight_max);
+  fprintf(fp_log, "init_randem_weight_min:		  %f\n", para->init_randem_weight_min);
+  fprintf(fp_log, "init_randem_bias_max:		    %f\n", para->init_randem_bias_max);
+  fprintf(fp_log, "init_randem_bias_min:		    %f\n", para->init_randem_bias_min);
+  fprintf(fp_log, "momentum:		                %f\n", para->momentum);
+  fprintf(fp_log, "weightcost:		              %f\n", para->weightcost);
+  fprintf(fp_log, "learnrate:		              %f\n", para->lrate);
+  fprintf(fp_log, "visible_omit:		      %f\n", para->visible_omit);
+  fprintf(fp_log, "hid_omit:		      %f\n", para->hid_omit);
+  fprintf(fp_log, "layersizes:		              ");
+  for (int j = 0; j < numlayers; ++j) fprintf(fp_log, "%d,", para->layersizes[j]);
+  fprintf(fp_log, "\n");
+  fprintf(fp_log, "Please check...\n");
+}
+
+// Momentum of epoch offset e as the Perl driver would hand it over: accumulated in double, printed with %.15g (Perl's
+// number -> string rule), parsed with atof and narrowed to float (.pl:137,219 -> Interface.cc:176).
+float Interface::epoch_momentum(int e) const {
+  double m = base_momentum_d;
+  for (int i = 0; i < e; ++i) m = m + momentum_step_d;
+  if (e > 0 && m > momentum_max_d) m = momentum_max_d;
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.15g", m);
+  return static_cast<float>(atof(buf));
+}
+
+// Epoch boundary of the in-process loop: what a fresh process started by the Perl driver would see.
+float Interface::begin_epoch(int e) {
+  const int number = para->epoch_first + e;
+  para->momentum = epoch_momentum(e);
+  para->init_randem_seed = base_seed + e * para->seed_step;
+  if (e > 0) {
+    fclose(fp_log);
+    fclose(fp_out);
+    const std::string prev = epoch_name(para->out_weight_pattern, number - 1);
+    snprintf(para->init_weightFN, MAXLINE, "%s", prev.c_str());  // for the echo only: the weights never left the device
+    snprintf(para->out_weightFN, MAXLINE, "%s", epoch_name(para->out_weight_pattern, number).c_str());
+    snprintf(para->log_FN, MAXLINE, "%s", epoch_name(para->log_pattern, number).c_str());
+    if (!(fp_log = fopen(para->log_FN, "wt"))) {
+      printf("can not open output log file: %s\n", para->log_FN);
+      exit(0);
+    }
+    if (!(fp_out = fopen(para->out_weightFN, "wb"))) fatal("can not open output weights file: %s\n", para->out_weightFN);
+    echo_parameters();
+    fprintf(fp_log, "Loading Norm file...\nNorm file loaded.\nLoading Init weight file...\nInit weight file loaded.\n");
+    srand48(para->init_randem_seed);  // a new process seeds once, then shuffles (Interface.cc:338)
+    fflush(fp_log);
+  }
+  return para->momentum;
+}
+
 // Interface::Initial — reference Interface.cc:69-404: parse key=value args, open files, echo parameters, load norm
 // file, allocate + initialise weights (random via drand48 or MAT-v4 file), check the input width, allocate chunk buffers.
 void Interface::Initial(int argc, char** argv) {
@@ -147,6 +230,10 @@ void Interface::Initial(int argc, char** argv) {
       para->seed = strtoull(val, nullptr, 0);
       continue;
     }
+    // the momentum schedule is evaluated in double, as the Perl driver does (no `continue`: the table stores the floats)
+    if (key == "momentum") base_momentum_d = atof(val);
+    if (key == "momentum_step") momentum_step_d = atof(val);
+    if (key == "momentum_max") momentum_max_d = atof(val);
     for (const ArgSpec& a : kArgs) {
       if (key != a.key) continue;
       char* base = reinterpret_cast<char*>(para) + a.offset;
@@ -163,45 +250,26 @@ void Interface::Initial(int argc, char** argv) {
     // unknown keys (e.g. numlayers= sent by the Perl driver) are accepted and ignored, like the reference
   }
 
+  // in-process epochs: remember the command-line values, expand "%d" for the first epoch
+  snprintf(para->out_weight_pattern, MAXLINE, "%s", para->out_weightFN);
+  snprintf(para->log_pattern, MAXLINE, "%s", para->log_FN);
+  base_seed = para->init_randem_seed;
+  if (para->epochs < 1) para->epochs = 1;
+  if (para->epochs > 1 || strstr(para->out_weightFN, "%d") || strstr(para->log_FN, "%d")) {
+    snprintf(para->out_weightFN, MAXLINE, "%s", epoch_name(para->out_weight_pattern, para->epoch_first).c_str());
+    snprintf(para->log_FN, MAXLINE, "%s", epoch_name(para->log_pattern, para->epoch_first).c_str());
+  }
   if (!(fp_log = fopen(para->log_FN, "wt"))) {
     printf("can not open output log file: %s\n", para->log_FN);
     exit(0);
   }
+  if (para->epochs > 1 && (!strstr(para->out_weight_pattern, "%d") || !strstr(para->log_pattern, "%d")))
+    fatal("epochs > 1 needs %%d (the epoch number) in outwts_file and log_file\n");
   if (!(fp_data = fopen(para->fea_FN, "rb"))) fatal("can not open feature file: %s\n", para->fea_FN);
   if (!(fp_targ = fopen(para->targ_FN, "rb"))) fatal("can not open target file: %s\n", para->targ_FN);
   if (!(fp_out = fopen(para->out_weightFN, "wb"))) fatal("can not open output weights file: %s\n", para->out_weightFN);
 
-  // Parameter echo, byte-compatible with reference Interface.cc:267-298 (logs were machine-read, .pl:113-121).
-  fprintf(fp_log, "parameters input:\n");
-  fprintf(fp_log, "fea_file:             %s\n", para->fea_FN);
-  fprintf(fp_log, "norm_file:            %s\n", para->fea_normFN);
-  fprintf(fp_log, "targ_file:            %s\n", para->targ_FN);
-  fprintf(fp_log, "outwts_file:          %s\n", para->out_weightFN);
-  fprintf(fp_log, "log_file:		          %s\n", para->log_FN);
-  fprintf(fp_log, "initwts_file:         %s\n", para->init_weightFN);
-  fprintf(fp_log, "train_sent_range:     %s\n", para->train_sent_range);
-  fprintf(fp_log, "cv_sent_range:        %s\n", para->cv_sent_range);
-  fprintf(fp_log, "fea_dim:		          %d\n", para->fea_dim);
-  fprintf(fp_log, "fea_context:		      %d\n", para->fea_context);
-  fprintf(fp_log, "bunchsize:		        %d\n", para->bunchsize);
-  fprintf(fp_log, "gpu_used:		          %d\n", para->gpu_used);
-  fprintf(fp_log, "train_cache:		      %d\n", para->traincache);
-  fprintf(fp_log, "init_randem_seed:		  %d\n", para->init_randem_seed);
-  fprintf(fp_log, "targ_offset:		      %d\n", para->targ_offset);
-  fprintf(fp_log, "dropoutflag:		      %d\n", para->dropoutflag);
-  fprintf(fp_log, "init_randem_weight_max:		  %f\n", para->init_randem_weight_max);
-  fprintf(fp_log, "init_randem_weight_min:		  %f\n", para->init_randem_weight_min);
-  fprintf(fp_log, "init_randem_bias_max:		    %f\n", para->init_randem_bias_max);
-  fprintf(fp_log, "init_randem_bias_min:		    %f\n", para->init_randem_bias_min);
-  fprintf(fp_log, "momentum:		                %f\n", para->momentum);
-  fprintf(fp_log, "weightcost:		              %f\n", para->weightcost);
-  fprintf(fp_log, "learnrate:		              %f\n", para->lrate);
-  fprintf(fp_log, "visible_omit:		      %f\n", para->visible_omit);
-  fprintf(fp_log, "hid_omit:		      %f\n", para->hid_omit);
-  fprintf(fp_log, "layersizes:		              ");
-  for (int j = 0; j < numlayers; ++j) fprintf(fp_log, "%d,", para->layersizes[j]);
-  fprintf(fp_log, "\n");
-  fprintf(fp_log, "Please check...\n");
+  echo_parameters();
 
   if (numlayers < 2 || para->fea_dim <= 0 || para->fea_context <= 0 || para->traincache <= 0 || para->bunchsize <= 0)
     fatal("layersizes / fea_dim / fea_context / traincache / bunchsize missing or invalid\n");

@@ -65,6 +65,16 @@ struct WorkPara {
   char decode_FN[MAXLINE] = "";
   char decode_format[MAXLINE] = "raw";   // raw | pfile (DecodeWriter.h)
   char decode_normFN[MAXLINE] = "";      // optional de-normalisation of the decode output
+  // epochs > 1: the Perl driver's loop (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-249) inside one process.
+  // Epoch e (1-based, numbered from epoch_first) uses momentum min(momentum_max, momentum + (e-1)*momentum_step),
+  // init_randem_seed + (e-1)*seed_step, and the outwts_file / log_file names with "%d" replaced by its number.
+  int epochs = 1;
+  int epoch_first = 1;
+  float momentum_step = 0.04f;   // .pl:137
+  float momentum_max = 0.9f;     // .pl:219
+  int seed_step = 345;           // .pl:136
+  char out_weight_pattern[MAXLINE] = "";  // the names as given on the command line
+  char log_pattern[MAXLINE] = "";
 };
 
 // One chunk for the device-side reader: the Pfile records as they lie in the file + the sample table
@@ -83,6 +93,9 @@ class Interface {
   ~Interface();
 
   void Initial(int argc, char** argv);
+  // epochs > 1: switch log / weight files, RNG seed and momentum to epoch `e` (0-based offset from epoch_first);
+  // e = 0 is what Initial() already set up.  Returns the epoch's momentum.
+  float begin_epoch(int e);
   void Writeweights();
   void get_pfile_info();
   void get_chunk_info(char* range);
@@ -136,6 +149,10 @@ class Interface {
   int assemble_raw(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,
                    bool shuffle, RawChunk* rc);
   void fatal(const char* fmt, ...);
+  void echo_parameters();
+  float epoch_momentum(int e) const;
+  double base_momentum_d = 0.0, momentum_step_d = 0.04, momentum_max_d = 0.9;  // schedule in double (Perl arithmetic)
+  int base_seed = 0;
   Range parse_range(const char* range, const char* what);
   void plan_chunks(const Range& r, int* starts, unsigned int* n_chunks, unsigned int* n_samples);
   int assemble(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,

@@ -83,6 +83,14 @@ int bp_forward(bp_handle* h, int n_frames, const float* in, float* out);
 /* BP_GPU::returnWeights (BP_GPU.cu:910-923): fills caller-owned arrays, same indexing as bp_create. */
 int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias);
 
+/* Epoch boundary inside one process.  The reference runs one epoch per process and its Perl
+ * driver re-invokes the binary with a new momentum (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-165, 214-249):
+ * every new process starts with zero momentum deltas (BP_GPU.cu:137-138 + zero-fill :938-940), the constructor's
+ * lrate / momentum / weightcost (BP_GPU.cu:10) and — here — dropout step 0.  bp_begin_epoch puts a live trainer into
+ * exactly that state without the weight round-trip through a .wts file: weights stay on the device, deltas are zeroed,
+ * the three hyper-parameters are replaced, and the dropout step counter restarts iff reset_dropout_step != 0. */
+int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, int reset_dropout_step);
+
 /* Last error message of the calling thread ("" if none). */
 const char* bp_last_error(void);
 

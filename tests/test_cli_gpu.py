@@ -107,3 +107,45 @@ def test_bptrain_decode_pfile_lines_up_with_targets():
             want_sid.append(k)
             want_fid.append(j + 5)
     assert sid.tolist() == want_sid and fid.tolist() == want_fid
+
+
+@pytest.mark.skipif(not os.path.exists(OURS), reason="BPtrain not built")
+@pytest.mark.parametrize("reader", ["host", "gpu"])
+def test_bptrain_in_process_epochs_equal_chained_invocations(reader):
+    """epochs=3 (the Perl driver's loop folded into one process) must write, for every epoch, the very
+    bytes that three chained single-epoch invocations write when they follow the Perl schedule
+    (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-165: initwts = previous epoch's file, momentum += 0.04,
+    init_randem_seed += 345), dropout on, so that masks, shuffles, momentum reset and hyper-parameters are all covered."""
+    T = importlib.import_module("dnn-for-speech-enhancement_b200.tools.pfile")
+    drop = ["dropoutflag=1", "visible_omit=0.1", "hid_omit=0.2", f"reader={reader}", "traincache=1500"]
+
+    def args(d, out, log, init, extra):
+        a = [x for x in _args(d, "x", drop + list(extra))
+             if not x.startswith(("outwts_file=", "log_file=", "initwts_file="))
+             and x not in ("traincache=3000", "dropoutflag=0", "visible_omit=0", "hid_omit=0")]
+        return a + [f"outwts_file={out}", f"log_file={log}", f"initwts_file={init}"]
+
+    with tempfile.TemporaryDirectory() as d:
+        feas, targs, mu, ivar = T.synth_corpus(40, 129, 129, seed=4, min_len=30, max_len=90)
+        T.write_pfile(f"{d}/fea.pfile", feas)
+        T.write_pfile(f"{d}/targ.pfile", targs)
+        T.write_norm(f"{d}/fea.norm", mu, ivar)
+        # (a) chained processes, as the Perl script drives them
+        momentum, seed, init = 0.5, 7, ""
+        for e in (1, 2, 3):
+            if e > 1:
+                momentum, seed, init = momentum + 0.04, seed + 345, f"{d}/chain.{e - 1}.wts"
+            # Perl interpolates numbers with %.15g
+            extra = [f"momentum={momentum:.15g}", f"init_randem_seed={seed}"]
+            a = args(d, f"{d}/chain.{e}.wts", f"{d}/chain.{e}.log", init, extra)  # later keys win (argv order)
+            o = subprocess.run([OURS] + a, cwd=d, capture_output=True, text=True, timeout=600)
+            assert o.returncode == 1, o.stdout + o.stderr
+        # (b) one process
+        o = subprocess.run([OURS] + args(d, f"{d}/one.%d.wts", f"{d}/one.%d.log", "", ["epochs=3"]), cwd=d,
+                           capture_output=True, text=True, timeout=600)
+        assert o.returncode == 1, o.stdout + o.stderr
+        for e in (1, 2, 3):
+            assert open(f"{d}/one.{e}.wts", "rb").read() == open(f"{d}/chain.{e}.wts", "rb").read(), f"epoch {e}"
+            assert _cv(f"{d}/one.{e}.log") == _cv(f"{d}/chain.{e}.log")
+            assert "Total cost time:" in open(f"{d}/one.{e}.log").read()
+        assert "momentum:		                0.580000" in open(f"{d}/one.3.log").read()
