@@ -145,6 +145,42 @@ def cpu_port_run(sizes, bunch, train, n_samples_bunches, dropout=(0, 0.0, 0.0)):
     return x.shape[0] / dt, cores, what, dt
 
 
+def isolated_dominant_gemm(bp, sizes, lb, reps=20):
+    """The dominant product of the workload (a hidden layer's forward affine, units x frames x fan-in) launched alone,
+    back to back `reps` times on its own stream and timed with CUDA events inside the library (bp_debug_gemm):
+    operands L2-resident, no neighbours — the kernel's own ceiling, next to the in-pipeline figure of `roofline`."""
+    import ctypes as C
+    lib = bp.load_library()
+    M, N, K = sizes[2], lb, sizes[1]
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((K, M), dtype=np.float32)
+    B = rng.standard_normal((N, K), dtype=np.float32)
+    bias = np.zeros(M, np.float32)
+    out = np.empty((N, M), np.float32)
+    fp = C.POINTER(C.c_float)
+    ms = C.c_float(0)
+    old = os.environ.get("BP_DBG_REPS")
+    try:
+        # the device idles while the operands are generated: a first, longer burst brings the clocks back up (without
+        # it the 20 timed launches ran at ~2/3 of the sustained rate: 28.5 us against 18.1 us for the same product)
+        for n_launch in (400, reps):
+            os.environ["BP_DBG_REPS"] = str(n_launch)
+            rc = lib.bp_debug_gemm(0, M, N, K, A.ctypes.data_as(fp), M, B.ctypes.data_as(fp), K,
+                                   out.ctypes.data_as(fp), M, bias.ctypes.data_as(fp), None, 0, 1.0, 0, 0,
+                                   C.byref(ms))
+            if rc != 0:
+                break
+    finally:
+        if old is None:
+            os.environ.pop("BP_DBG_REPS", None)
+        else:
+            os.environ["BP_DBG_REPS"] = old
+    if rc != 0 or ms.value <= 0:
+        return None
+    return {"product": f"forward affine {M} units x {N} frames x {K} fan-in (bias + ReLU epilogue)", "launches": reps,
+            "us_per_launch": ms.value * 1e3, "tflops": 2.0 * M * N * K / (ms.value * 1e-3) / 1e12}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,7 +366,7 @@ def main():
     peaks, peak_src = load_peaks()
     traffic = {}
     try:  # DRAM bytes of the committed ncu --set full capture (profiles/), per bunch / per launch
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
     except Exception:
         pass
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -350,6 +386,14 @@ def main():
                             "traffic": traffic.get("gemm_dram_bytes_per_bunch") if args.workload == "C2" else None,
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2 (kind::tf32 issues at half the bf16 rate)",
                             "per_class_ms": {k: v / nprof for k, v in prof.items()}}
+        if world == 1 and len(sizes) > 3:
+            try:
+                iso = isolated_dominant_gemm(bp, sizes, lb)
+                if iso:
+                    iso["frac"] = iso["tflops"] / tf32_peak
+                    line["roofline"]["isolated_dominant_kernel"] = iso
+            except Exception as e:  # a measurement aid must not hide the bench line
+                line["roofline"]["isolated_dominant_kernel"] = {"error": str(e)}
         sgd_ms = prof["sgd"] / nprof
         # algorithmic minimum 20 B/parameter over the parameters the timed launch updates: layer 1
         # when the upper layers were updated early, else all of them

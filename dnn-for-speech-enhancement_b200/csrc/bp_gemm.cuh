@@ -193,7 +193,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
 // Y[frame][unit] for every accumulator element; loading it only after the accumulator is complete put ~2.5 us of
 // exposed global-load latency per 32-column chunk at the end of every dX GEMM (isolated 2048x1024x2048: dX 28.4 us vs
 // 18.4 us for the forward product of the same size, profiles/r1d).  The epilogue warps are idle during the main loop, so
-// they fetch the first two chunks then, and chunk c+2 while chunk c+1 is processed.
+// they fetch the first two chunks then, and chunk c+2 while chunk c+1 is processed.  (Four chunks ahead — a whole
+// 128-wide tile, 206 registers — is faster still with a warm L2, 24.7 us, but slower inside the bunch, where Y comes
+// from HBM: dX class 0.101 vs 0.082 ms, ncu 43.5 vs 34.1 us per launch; two it is.)
 struct DxPrefetch {
   float y[2][32];
   __device__ __forceinline__ void load(const GemmParams& p, int slot, int m, bool m_ok, int nc) {

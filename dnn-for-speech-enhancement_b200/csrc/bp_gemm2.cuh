@@ -182,8 +182,11 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (elect_one()) {
-            const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + (sa >> 4);
-            const uint32_t b_lo = (kBMN ? kDescLoMN : kDescLoK) + (sb >> 4);
+            // 14-bit start-address field: the shared-window address of a CTA with cluster rank >= 2 carries its rank
+            // above bit 24, which would spill into the LBO field (bits 16-29) — harmless for K-major operands, whose
+            // LBO is ignored, and the cause of the wrong MN-major products of pairs 1.. in the first multicast runs
+            const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + ((sa >> 4) & 0x3FFFu);
+            const uint32_t b_lo = (kBMN ? kDescLoMN : kDescLoK) + ((sb >> 4) & 0x3FFFu);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 8; ++k) {
               const uint32_t a_off = kAMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kAsub + uint32_t(k % 4) * 32u;

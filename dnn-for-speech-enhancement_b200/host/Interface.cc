@@ -77,6 +77,9 @@ const ArgSpec kArgs[] = {
     ARG("momentum_max", kFloat, momentum_max),
     ARG("seed_step", kInt, seed_step),
 };
+#undef ARG
+
+}  // namespace
 
 // "%d" in a file-name pattern -> the epoch number (the Perl driver's mlp.$i.wts / mlp.$i.log, .pl:134-135).
 std::string epoch_name(const char* pattern, int number) {
@@ -85,9 +88,6 @@ std::string epoch_name(const char* pattern, int number) {
   if (pos != std::string::npos) s.replace(pos, 2, std::to_string(number));
   return s;
 }
-#undef ARG
-
-}  // namespace
 
 Interface::Interface() { para = new WorkPara(); }
 
@@ -160,13 +160,16 @@ void Interface::echo_parameters() {
 
 // Momentum of epoch offset e as the Perl driver would hand it over: accumulated in double, printed with %.15g (Perl's
 // number -> string rule), parsed with atof and narrowed to float (.pl:137,219 -> Interface.cc:176).
-float Interface::epoch_momentum(int e) const {
-  double m = base_momentum_d;
-  for (int i = 0; i < e; ++i) m = m + momentum_step_d;
-  if (e > 0 && m > momentum_max_d) m = momentum_max_d;
+float epoch_momentum_value(double base, double step, double max, int e) {
+  double m = base;
+  for (int i = 0; i < e; ++i) m = m + step;
+  if (e > 0 && m > max) m = max;
   char buf[64];
   snprintf(buf, sizeof buf, "%.15g", m);
   return static_cast<float>(atof(buf));
+}
+float Interface::epoch_momentum(int e) const {
+  return epoch_momentum_value(base_momentum_d, momentum_step_d, momentum_max_d, e);
 }
 
 // Epoch boundary of the in-process loop: what a fresh process started by the Perl driver would see.

@@ -87,6 +87,10 @@ struct RawChunk {
   std::vector<int> sample_frame, sample_seg, sample_row;
 };
 
+// Pure helpers of the in-process epoch loop (tested on the CPU against the Perl driver's own arithmetic).
+float epoch_momentum_value(double base, double step, double max, int e);
+std::string epoch_name(const char* pattern, int number);
+
 class Interface {
  public:
   Interface();
