@@ -78,6 +78,11 @@ struct GemmParams {
   int chunk_base;
   float* scatter[8];
   unsigned long long hint_a, hint_b;  // L2 eviction-priority policy for the A / B operand loads (0 = none)
+  int stream_out;         // EPI_PLAIN: store with st.global.cs (evict-first), BP_DW_STREAM=1 (default off; untested A/B)
+  int l2_prefetch;        // > 0: the producer also issues cp.async.bulk.prefetch.tensor (L2 only) for the k-block this
+                          // many steps ahead of the one it loads, and for the first ones before griddepcontrol.wait
+                          // (BP_L2_PREFETCH; an L2 prefetch of data a predecessor is still writing is harmless — L2 is
+                          // the point of coherence)
   uint32_t dbg_flags;     // measurement aids: bit 0 skip the MMAs (TMA-only), bit 1 skip the loads (MMA-only)
   long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
                           // [256..511] loads issued, [512..767] stage full seen, [768..1023] MMAs issued,
@@ -120,9 +125,15 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
       float* base = p.out + plane_off;
       if (p.scatter_n > 0) base = p.scatter[(p.chunk_base + (nc >> 5)) % p.scatter_n];
       float* o = base + size_t(nc) * p.ldo + m;
+      if (p.stream_out) {  // gradient tile: read once by the update, should not displace the weights in L2
 #pragma unroll
-      for (int j = 0; j < 32; ++j, o += p.ldo)
-        if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j, o += p.ldo)
+          if (whole || nc + j < p.N) __stcs(o, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j, o += p.ldo)
+          if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
+      }
     }
   } else if constexpr (kEpi == EPI_FWD_HID) {
     if (m_ok) {
@@ -356,6 +367,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else tma_load_3d(sa, mapA, &full[s], 0, a1, a2);
             if (p.hint_b) tma_load_3d_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
             else tma_load_3d(sb, mapB, &full[s], 0, b1, b2);
+            if (p.l2_prefetch > 0 && kb + p.l2_prefetch < kb1) {
+              const int kp = kb + p.l2_prefetch;
+              tma_prefetch_l2_3d(mapA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
+              tma_prefetch_l2_3d(mapB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
+            }
           }
           if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[256 + kb] = clock64();
         }

@@ -122,6 +122,18 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (CP == 1 && p.l2_prefetch > 0 && warp == 0 && pair < num_tiles) {
+    // Under the previous kernel's tail (PDL): pull the first k-blocks of my first tile towards L2.
+    if (elect_one()) {
+      const int m0 = (pair % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;
+      const int n0 = p.n_begin + (pair / num_m_tiles) * BLOCK_N + int(rank) * HALF_N;
+      for (int kp = 0; kp < p.l2_prefetch && kp < num_kb; ++kp) {
+        tma_prefetch_l2_3d(&tmA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
+        tma_prefetch_l2_3d(&tmB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
+      }
+    }
+    __syncwarp();
+  }
   griddep_wait();
   griddep_launch_dependents();
 
@@ -157,6 +169,11 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.hint_b) tma_load_3d_2sm_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
           else tma_load_3d_2sm(sb, mapB, &full[s], 0, b1, b2);
+          if (CP == 1 && p.l2_prefetch > 0 && kb + p.l2_prefetch < num_kb) {  // run ahead of the ring, into L2 only
+            const int kp = kb + p.l2_prefetch;
+            tma_prefetch_l2_3d(mapA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
+            tma_prefetch_l2_3d(mapB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }

@@ -135,6 +135,13 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// Box of a tiled tensor map -> L2 only (no shared memory, no barrier): lets the producer run further ahead of its
+// shared-memory ring than the ring is deep.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

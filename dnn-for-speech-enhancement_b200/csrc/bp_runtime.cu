@@ -169,7 +169,12 @@ int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair
     const char* e = getenv("BP_PDL");  // programmatic dependent launch between consecutive GEMMs (default on)
     return e ? atoi(e) != 0 : true;
   }();
+  static const int l2_prefetch = [] {
+    const char* e = getenv("BP_L2_PREFETCH");
+    return e ? std::max(0, atoi(e)) : 0;
+  }();
   GemmParams q = p;
+  q.l2_prefetch = l2_prefetch;
   q.dbg_flags |= env_flags;
   static const bool use_hints = [] {
     const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
@@ -264,7 +269,12 @@ int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& 
     const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
     return e ? atoi(e) != 0 : true;
   }();
+  static const int l2_prefetch = [] {
+    const char* e = getenv("BP_L2_PREFETCH");  // k-blocks of L2-only prefetch ahead of the ring (default off; untested A/B)
+    return e ? std::max(0, atoi(e)) : 0;
+  }();
   GemmParams q = p;
+  q.l2_prefetch = l2_prefetch;
   if (!use_hints || CP > 1) q.hint_a = 0;  // the multicast A-slice load carries no hint
   if (!use_hints) q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
@@ -1141,6 +1151,11 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.out = r->g + ls.off;
     p.ldo = ls.ldN;
     p.passes = r->passes;
+    static const int dw_stream = [] {
+      const char* e = getenv("BP_DW_STREAM");
+      return e ? atoi(e) : 0;
+    }();
+    p.stream_out = dw_stream;
     MapPair xmap;
     const MapPair* bmap = &ls.yprev_dw;
     if (l == 1) {
