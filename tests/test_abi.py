@@ -64,3 +64,35 @@ def test_dropout_mask_host_function_matches_oracle(bp, oracle):
         step, layer, f, u = (int(v) for v in rng.integers(0, 5000, size=4))
         p = float(rng.uniform(0, 1))
         assert bp.dropout_mask(seed, step, layer, f, u, p) == oracle.dropout_mask(seed, step, layer, f, u, p)
+
+
+def test_cli_fails_loudly_without_a_gpu(tmp_path):
+    """On a box without a CUDA device the BPtrain CLI must not compute anything on the CPU: the reference's error
+    convention (message into the log, exit status 0 — e.g. BP_GPU.cu:20-24) with the library's ENODEV message."""
+    import importlib
+    import subprocess
+    try:
+        import ctypes
+        if ctypes.CDLL("libcuda.so.1").cuInit(0) == 0:
+            pytest.skip("a CUDA device is present")
+    except OSError:
+        pass
+    exe = os.path.join(ROOT, "dnn-for-speech-enhancement_b200", "bin", "BPtrain")
+    if not os.path.exists(exe):
+        pytest.skip("BPtrain not built")
+    T = importlib.import_module("dnn-for-speech-enhancement_b200.tools.pfile")
+    d = str(tmp_path)
+    feas, targs, mu, ivar = T.synth_corpus(6, 129, 129, seed=1, min_len=20, max_len=40)
+    T.write_pfile(f"{d}/fea.pfile", feas)
+    T.write_pfile(f"{d}/targ.pfile", targs)
+    T.write_norm(f"{d}/fea.norm", mu, ivar)
+    args = [f"fea_file={d}/fea.pfile", f"norm_file={d}/fea.norm", f"targ_file={d}/targ.pfile", f"outwts_file={d}/o.wts",
+            f"log_file={d}/o.log", "initwts_file=", "train_sent_range=0-3", "cv_sent_range=4-5", "fea_dim=129",
+            "fea_context=11", "targ_offset=5", "traincache=500", "bunchsize=32", "layersizes=1548,64,129",
+            "gpu_used=1", "init_randem_seed=3", "momentum=0.5", "weightcost=0", "lrate=1", "dropoutflag=0",
+            "visible_omit=0", "hid_omit=0"]
+    r = subprocess.run([exe] + args, cwd=d, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0                                   # every error path is exit(0), success is 1
+    log = open(f"{d}/o.log").read()
+    assert "GPU trainer creation failed" in log and "no CPU fallback" in log
+    assert os.path.getsize(f"{d}/o.wts") == 0                  # nothing was trained, nothing was written
