@@ -52,7 +52,10 @@ constexpr size_t gemm2_smem_bytes() {
 //   MN-major A: {32, 64 k-rows, (128/CP)/32 mn-chunks}      slice pi = mn-chunks [pi*4/CP, (pi+1)*4/CP) of the 128-row block
 //   K-major  A: {32, 128 rows (CP=2) | 64 rows (CP=4), 1 k-chunk}   slice pi = k-chunk pi/(CP/2), row part pi%(CP/2)
 // In both layouts slice pi occupies bytes [pi, pi+1) * A_BYTES/CP of the stage's A block.
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1>
+// kTrace: separate instantiation (bp_debug_gemm with BP_DBG_TRACE only) in which the leader CTA of pair 0 records a
+// clock64 timeline of its first tile into p.dbg_trace, same slots as bp_gemm_kernel's (see GemmParams::dbg_trace); the
+// product kernels (kTrace = false) contain none of it.
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1, bool kTrace = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
@@ -98,6 +101,11 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_it = num_kb * (p.passes == 3 ? 3 : 1);
   const int pair = blockIdx.x / (2 * CP), num_pairs = gridDim.x / (2 * CP);  // cluster index / count
   constexpr uint16_t kAllCtas = uint16_t((1u << (2 * CP)) - 1u);
+  bool tracing = false;
+  if constexpr (kTrace) {
+    tracing = p.dbg_trace != nullptr && blockIdx.x == 0;
+    if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -151,6 +159,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);
         __syncwarp();
         if (elect_one()) {
+          if constexpr (kTrace) {
+            if (tracing && it < 256 && t == pair) p.dbg_trace[it] = clock64();
+          }
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);  // both CTAs' bytes land on the leader's barrier
@@ -173,6 +184,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int kp = kb + p.l2_prefetch;
             tma_prefetch_l2_3d(mapA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
             tma_prefetch_l2_3d(mapB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
+          }
+          if constexpr (kTrace) {
+            if (tracing && it < 256 && t == pair) p.dbg_trace[256 + it] = clock64();
           }
         }
         __syncwarp();
@@ -199,6 +213,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (elect_one()) {
+            if constexpr (kTrace) {
+              if (tracing && kb < 256 && t == pair) p.dbg_trace[512 + kb] = clock64();
+            }
             // 14-bit start-address field: the shared-window address of a CTA with cluster rank >= 2 carries its rank
             // above bit 24, which would spill into the LBO field (bits 16-29) — harmless for K-major operands, whose
             // LBO is ignored, and the cause of the wrong MN-major products of pairs 1.. in the first multicast runs
@@ -213,6 +230,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             umma_commit_2sm(&empty[s], kAllCtas);                 // this pair is done with slot s: tell every CTA
             if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u << (2 * pi)));  // accumulators complete
+            if constexpr (kTrace) {
+              if (tracing && kb < 256 && t == pair) p.dbg_trace[768 + kb] = clock64();
+            }
           }
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -238,6 +258,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
+      if constexpr (kTrace) {
+        if (tracing && threadIdx.x == 64 && t == pair) p.dbg_trace[1024] = clock64();
+      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
@@ -259,6 +282,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
+      if constexpr (kTrace) {
+        if (tracing && threadIdx.x == 64 && t == pair) p.dbg_trace[1025] = clock64();
+      }
       if (lane == 0) {
         if (leader) mbar_arrive(&tempty[as]);
         else mbar_arrive_remote(&tempty[as], crank & ~1u);

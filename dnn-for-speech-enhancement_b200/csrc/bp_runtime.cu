@@ -243,9 +243,9 @@ void init_cluster_capacity(int num_sms) {
             g_max_clusters[1][1], g_max_clusters[1][2]);
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP, bool kTrace = false>
 int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP>;
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP, kTrace>;
   constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
   constexpr int kCluster = 2 * CP;
   static thread_local int configured_dev = -1;
@@ -341,11 +341,13 @@ int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, 
   if (k.pair_n == 256) {
     if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
     if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
+    if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1, true>(st, num_sms, a.full, b, p);
     return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
   }
   if (k.pair_n == 128) {
     if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
     if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
+    if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
     return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
   }
   return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
@@ -1894,7 +1896,7 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       CU_TRY(cudaMemcpy(t.data(), dtrace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       cudaFree(dtrace);
       const long long t0 = t[1026];
-      const int nkb = std::min(256, (K + 31) / 32);
+      const int nkb = std::min(256, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
       printf("trace (cycles since CTA start): kb | slot_free  loads_issued  full_seen  mma_issued\n");
       for (int kb = 0; kb < nkb; ++kb)
         if (kb < 24 || kb >= nkb - 4)
