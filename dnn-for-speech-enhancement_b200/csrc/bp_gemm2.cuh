@@ -40,12 +40,15 @@ namespace bp {
 // PAIR_N = 128 (for products too small to fill the machine with 256-wide pair tiles, e.g. 2048 x 1024 outputs):
 // 48 KB stages x 4, each CTA stages 64 B columns; 96 KB of shared-memory traffic per 512 pipe cycles -> 67 % roof
 // instead of the lone CTA's 50 %.
-template <int PAIR_N>
-__host__ __device__ constexpr int gemm2_stages() { return PAIR_N == 256 ? 3 : 4; }
+// kStagesOv (experiment, BP_STAGES=2): a 2-deep ring of 48 KB stages makes a 128-wide pair CTA small enough (97 KB,
+// 256 TMEM columns) for two CTAs per SM, so that the next kernel's main loop (PDL) or the side stream's dW can run under
+// this kernel's fill, epilogue and drain — at the price of less latency tolerance in the ring.  0 = the defaults.
+template <int PAIR_N, int kStagesOv = 0>
+__host__ __device__ constexpr int gemm2_stages() { return kStagesOv > 0 ? kStagesOv : (PAIR_N == 256 ? 3 : 4); }
 
-template <int PAIR_N>
+template <int PAIR_N, int kStagesOv = 0>
 constexpr size_t gemm2_smem_bytes() {
-  return size_t(gemm2_stages<PAIR_N>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
+  return size_t(gemm2_stages<PAIR_N, kStagesOv>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
 }
 
 // A-slice boxes of the multicast variant (host side builds the tensor maps with these, see make_map1):
@@ -55,13 +58,14 @@ constexpr size_t gemm2_smem_bytes() {
 // kTrace: separate instantiation (bp_debug_gemm with BP_DBG_TRACE only) in which the leader CTA of pair 0 records a
 // clock64 timeline of its first tile into p.dbg_trace, same slots as bp_gemm_kernel's (see GemmParams::dbg_trace); the
 // product kernels (kTrace = false) contain none of it.
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1, bool kTrace = false>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1, bool kTrace = false, int kStagesOv = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                 const GemmParams p) {
   static_assert(CP == 1 || CP == 2 || CP == 4, "pairs per cluster");
-  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = PAIR_N, kStages = gemm2_stages<PAIR_N>();
+  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = PAIR_N;
+  constexpr int kStages = gemm2_stages<PAIR_N, kStagesOv>();
   static_assert(PAIR_N == 128 || PAIR_N == 256, "PAIR_N");
   constexpr int HALF_N = BLOCK_N / 2;                    // B columns staged by each CTA
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 4;    // my 128 rows of A

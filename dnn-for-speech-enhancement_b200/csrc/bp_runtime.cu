@@ -243,10 +243,10 @@ void init_cluster_capacity(int num_sms) {
             g_max_clusters[1][1], g_max_clusters[1][2]);
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP, bool kTrace = false>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP, bool kTrace = false, int kStagesOv = 0>
 int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP, kTrace>;
-  constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP, kTrace, kStagesOv>;
+  constexpr size_t smem = gemm2_smem_bytes<PAIR_N, kStagesOv>();
   constexpr int kCluster = 2 * CP;
   static thread_local int configured_dev = -1;
   int dev = 0;
@@ -348,6 +348,12 @@ int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, 
     if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
     if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
     if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
+    static const int stages = [] {
+      const char* e = getenv("BP_STAGES");  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
+      return e ? atoi(e) : 0;
+    }();
+    if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
+    if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
     return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
   }
   return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);

@@ -1,6 +1,10 @@
 # First GPU call of the next round: A/B (one box) of the switches prepared but not yet measured at the end of round 1.
 #   BP_L2_PREFETCH=k   producer issues L2-only TMA prefetches k k-blocks ahead of its shared-memory ring (+ under PDL)
 #   BP_DW_STREAM=1     gradient tiles stored with st.global.cs (evict-first)
-# Each line: frames/s, ms per bunch, per-class ms.  Keep what wins by > 1 % twice.
+#   BP_STAGES=2|3      128-wide pair kernels with a 2- / 3-deep ring (2: two CTAs per SM, fill/drain overlap)
+# Each line: frames/s, ms per bunch, per-class ms.  Keep what wins by > 1 % twice.  Then the timeline of fwd vs dX.
 bash scripts/gpu_ab.sh "BP_L2_PREFETCH=0" "BP_L2_PREFETCH=4" "BP_L2_PREFETCH=8" "BP_L2_PREFETCH=16" \
-                       "BP_DW_STREAM=1" "BP_DW_STREAM=1 BP_L2_PREFETCH=8" "BP_L2_PREFETCH=0"
+                       "BP_DW_STREAM=1" "BP_DW_STREAM=1 BP_L2_PREFETCH=8" "BP_STAGES=2" "BP_STAGES=2 BP_L2_PREFETCH=8" \
+                       "BP_STAGES=3" "BP_L2_PREFETCH=0"
+for s in 0 2; do echo "== isolated, BP_STAGES=$s"; BP_STAGES=$s timeout 60 python scripts/gpu_mc_probe.py quick 2>&1 | tail -7; done
+timeout 120 python scripts/gpu_pair_trace.py 2>&1 | head -150
