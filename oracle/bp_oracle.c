@@ -81,123 +81,180 @@ static float tf32_cond(float x, int mode) {
   memcpy(&x, &u, 4);
   return x;
 }
-static float* cond_copy(const float* src, size_t n, int mode) {
-  float* d = (float*)malloc(n * sizeof(float));
-  if (mode == 0) memcpy(d, src, n * sizeof(float));
-  else
-    for (size_t i = 0; i < n; ++i) d[i] = tf32_cond(src[i], mode);
-  return d;
-}
 /* kernSigmoid / kernDsigmoid bodies (ReLU at HEAD DevFunc.cu:74-77, 92-95; sigmoid variant :52, :62). */
 static float act_f(float x, int act) { return act == 0 ? (x > 0 ? x : 0.0f) : 1.0f / (1.0f + expf(-x)); }
 static float dact_f(float y, int act) { return act == 0 ? (y > 0 ? 1.0f : 0.0f) : (1.0f - y) * y; }
+
+/* ------------------------------------------------------------------------------------------------ GEMM core
+ * C[m][j] = init[j] (or 0), then C[m][j] = fmaf(A(m,r), Bm(r,j), C[m][j]) for r = 0, 1, ..., R-1 IN THAT ORDER: every
+ * output element is the same chain of single-rounded fused multiply-adds a one-thread triple loop would produce (the
+ * arithmetic of a textbook fp32 SGEMM).  Only the ORDER OF ELEMENTS is blocked for the cache hierarchy, never the order
+ * of the terms of one element: R is cut into blocks of KC whose partial sums pass through C in fp32 (a store + load of
+ * a float is exact), B is packed once into NR-wide column panels, A into MR-tall row panels per work item, and an
+ * MR x NR register tile walks the panels.  A(m,r) = A[m*as_m + r*as_r], Bm(r,j) = B[r*bs_r + j*bs_j]; both operands are
+ * conditioned (tf32 mode) while they are packed.  tests/test_oracle.py pins this routine against the naive loops. */
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define ORC_SIMD 1
+#else
+#define ORC_SIMD 0
+#endif
+#define ORC_MR 6
+#define ORC_NR 16
+#define ORC_KC 256
+#define ORC_MC 192 /* rows per work item (multiple of MR) */
+#define ORC_NC 256 /* columns per work item (multiple of NR) */
+
+/* register tile: C[MR x NR] += Ap[kc x MR] (r-major) * Bp[kc x NR] (r-major), ascending r */
+static inline void micro_tile(int kc, const float* Ap, const float* Bp, float* C, size_t ldc, int mr, int nr) {
+#if ORC_SIMD
+  if (mr == ORC_MR && nr == ORC_NR) {
+    __m256 c[ORC_MR][2];
+    for (int m = 0; m < ORC_MR; ++m) {
+      c[m][0] = _mm256_loadu_ps(C + m * ldc);
+      c[m][1] = _mm256_loadu_ps(C + m * ldc + 8);
+    }
+    for (int r = 0; r < kc; ++r) {
+      const __m256 b0 = _mm256_loadu_ps(Bp + (size_t)r * ORC_NR);
+      const __m256 b1 = _mm256_loadu_ps(Bp + (size_t)r * ORC_NR + 8);
+#pragma GCC unroll 6
+      for (int m = 0; m < ORC_MR; ++m) {
+        const __m256 a = _mm256_broadcast_ss(Ap + (size_t)r * ORC_MR + m);
+        c[m][0] = _mm256_fmadd_ps(a, b0, c[m][0]);
+        c[m][1] = _mm256_fmadd_ps(a, b1, c[m][1]);
+      }
+    }
+    for (int m = 0; m < ORC_MR; ++m) {
+      _mm256_storeu_ps(C + m * ldc, c[m][0]);
+      _mm256_storeu_ps(C + m * ldc + 8, c[m][1]);
+    }
+    return;
+  }
+#endif
+  for (int m = 0; m < mr; ++m)
+    for (int j = 0; j < nr; ++j) {
+      float c = C[m * ldc + j];
+      for (int r = 0; r < kc; ++r) c = fmaf(Ap[(size_t)r * ORC_MR + m], Bp[(size_t)r * ORC_NR + j], c);
+      C[m * ldc + j] = c;
+    }
+}
+
+static void gemm_core(int M, int R, int N, const float* A, size_t as_m, size_t as_r, const float* B, size_t bs_r,
+                      size_t bs_j, const float* init, float* C, size_t ldc, int tf32) {
+  if (M <= 0 || N <= 0) return;
+  const int npan = (N + ORC_NR - 1) / ORC_NR;
+  const size_t npad = (size_t)npan * ORC_NR;
+  const int nkb = (R + ORC_KC - 1) / ORC_KC;
+  /* Bp: k-block kb starts at kb*KC*npad; inside it panel p holds [kc][NR] (columns beyond N are zero, never stored) */
+  float* Bp = (float*)malloc(((size_t)(R > 0 ? R : 1)) * npad * sizeof(float));
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int kb = 0; kb < nkb; ++kb)
+    for (int p = 0; p < npan; ++p) {
+      const int r0 = kb * ORC_KC, kc = (R - r0 < ORC_KC) ? R - r0 : ORC_KC;
+      float* dst = Bp + (size_t)r0 * npad + (size_t)p * kc * ORC_NR;
+      for (int r = 0; r < kc; ++r)
+        for (int j = 0; j < ORC_NR; ++j) {
+          const int col = p * ORC_NR + j;
+          dst[(size_t)r * ORC_NR + j] = col < N ? tf32_cond(B[(size_t)(r0 + r) * bs_r + (size_t)col * bs_j], tf32) : 0.0f;
+        }
+    }
+  const int nic = (M + ORC_MC - 1) / ORC_MC, njc = (N + ORC_NC - 1) / ORC_NC;
+#pragma omp parallel
+  {
+    float* Ap = (float*)malloc((size_t)ORC_MC * ORC_KC * sizeof(float));
+#pragma omp for collapse(2) schedule(dynamic, 1)
+    for (int ic = 0; ic < nic; ++ic)
+      for (int jc = 0; jc < njc; ++jc) {
+        const int m0 = ic * ORC_MC, mc = (M - m0 < ORC_MC) ? M - m0 : ORC_MC;
+        const int j0 = jc * ORC_NC, nc = (N - j0 < ORC_NC) ? N - j0 : ORC_NC;
+        for (int m = 0; m < mc; ++m) {
+          float* c = C + (size_t)(m0 + m) * ldc + j0;
+          for (int j = 0; j < nc; ++j) c[j] = init ? init[j0 + j] : 0.0f;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int r0 = kb * ORC_KC, kc = (R - r0 < ORC_KC) ? R - r0 : ORC_KC;
+          for (int mb = 0; mb < mc; mb += ORC_MR) { /* pack (and condition) this block of A: [mb/MR][r][MR] */
+            const int mr = (mc - mb < ORC_MR) ? mc - mb : ORC_MR;
+            float* dst = Ap + (size_t)(mb / ORC_MR) * kc * ORC_MR;
+            for (int r = 0; r < kc; ++r)
+              for (int m = 0; m < ORC_MR; ++m)
+                dst[(size_t)r * ORC_MR + m] =
+                    m < mr ? tf32_cond(A[(size_t)(m0 + mb + m) * as_m + (size_t)(r0 + r) * as_r], tf32) : 0.0f;
+          }
+          for (int jb = 0; jb < nc; jb += ORC_NR) {
+            const int nr = (nc - jb < ORC_NR) ? nc - jb : ORC_NR;
+            const float* bp = Bp + (size_t)r0 * npad + (size_t)((j0 + jb) / ORC_NR) * kc * ORC_NR;
+            for (int mb = 0; mb < mc; mb += ORC_MR) {
+              const int mr = (mc - mb < ORC_MR) ? mc - mb : ORC_MR;
+              micro_tile(kc, Ap + (size_t)(mb / ORC_MR) * kc * ORC_MR, bp, C + (size_t)(m0 + mb) * ldc + j0 + jb, ldc,
+                         mr, nr);
+            }
+          }
+        }
+      }
+    free(Ap);
+  }
+  free(Bp);
+}
+
+/* Same contraction with every sum carried in double ("truth" variant for tolerance studies; small cases only). */
+static void gemm_core_dbl(int M, int R, int N, const float* A, size_t as_m, size_t as_r, const float* B, size_t bs_r,
+                          size_t bs_j, const float* init, float* C, size_t ldc, int tf32) {
+#pragma omp parallel for schedule(static)
+  for (int m = 0; m < M; ++m)
+    for (int j = 0; j < N; ++j) {
+      double acc = 0.0;
+      for (int r = 0; r < R; ++r)
+        acc += (double)tf32_cond(A[(size_t)m * as_m + (size_t)r * as_r], tf32) *
+               (double)tf32_cond(B[(size_t)r * bs_r + (size_t)j * bs_j], tf32);
+      C[(size_t)m * ldc + j] = (float)(acc + (init ? (double)init[j] : 0.0));
+    }
+}
+
+/* Test hooks (tests/test_oracle.py): the blocked routine and the one-thread triple loop it must equal bit for bit.
+ * A is M x R, B is R x N, both row-major and dense. */
+void orc_gemm(int M, int R, int N, const float* A, const float* B, const float* init, float* C, int tf32) {
+  gemm_core(M, R, N, A, (size_t)R, 1, B, (size_t)N, 1, init, C, (size_t)N, tf32);
+}
+void orc_gemm_naive(int M, int R, int N, const float* A, const float* B, const float* init, float* C, int tf32) {
+  for (int m = 0; m < M; ++m)
+    for (int j = 0; j < N; ++j) {
+      float c = init ? init[j] : 0.0f;
+      for (int r = 0; r < R; ++r)
+        c = fmaf(tf32_cond(A[(size_t)m * R + r], tf32), tf32_cond(B[(size_t)r * N + j], tf32), c);
+      C[(size_t)m * N + j] = c;
+    }
+}
 
 /* X[B x N] = bias (kernMultiCopy, DevFunc.cu:166-182), then X += Y[B x K] * W[K x N] (SgemmNN, BP_GPU.cu:557-558).
  * W is the reference's w[in*N + out].  Sum over k in ascending order, one fma per term. */
 static void gemm_fwd(int B, int K, int N, const float* Y, const float* W, const float* bias, float* X, int tf32,
                      int dbl) {
-  float* Yc = cond_copy(Y, (size_t)B * K, tf32);
-  float* Wc = cond_copy(W, (size_t)K * N, tf32);
-#pragma omp parallel for schedule(static)
-  for (int f = 0; f < B; ++f) {
-    float* x = X + (size_t)f * N;
-    const float* y = Yc + (size_t)f * K;
-    if (!dbl) {
-      for (int j = 0; j < N; ++j) x[j] = bias[j];
-      for (int k = 0; k < K; ++k) {
-        const float a = y[k];
-        const float* w = Wc + (size_t)k * N;
-        for (int j = 0; j < N; ++j) x[j] = fmaf(a, w[j], x[j]);
-      }
-    } else {
-      double* acc = (double*)calloc((size_t)N, sizeof(double));
-      for (int k = 0; k < K; ++k) {
-        const double a = y[k];
-        const float* w = Wc + (size_t)k * N;
-        for (int j = 0; j < N; ++j) acc[j] += a * (double)w[j];
-      }
-      for (int j = 0; j < N; ++j) x[j] = (float)(acc[j] + (double)bias[j]);
-      free(acc);
-    }
-  }
-  free(Yc);
-  free(Wc);
+  (dbl ? gemm_core_dbl : gemm_core)(B, K, N, Y, (size_t)K, 1, W, (size_t)N, 1, bias, X, (size_t)N, tf32);
 }
 
-/* E[B x K] = D[B x N] * W^T (SgemmTN with beta 0, BP_GPU.cu:636). */
+/* E[B x K] = D[B x N] * W^T (SgemmTN with beta 0, BP_GPU.cu:636): sum over n ascending. */
 static void gemm_dx(int B, int K, int N, const float* D, const float* W, float* E, int tf32, int dbl) {
-  float* Dc = cond_copy(D, (size_t)B * N, tf32);
-  float* Wt = (float*)malloc((size_t)K * N * sizeof(float)); /* Wt[n][k] = cond(W[k][n]) */
-#pragma omp parallel for schedule(static)
-  for (int n = 0; n < N; ++n)
-    for (int k = 0; k < K; ++k) Wt[(size_t)n * K + k] = tf32_cond(W[(size_t)k * N + n], tf32);
-#pragma omp parallel for schedule(static)
-  for (int f = 0; f < B; ++f) {
-    float* e = E + (size_t)f * K;
-    const float* d = Dc + (size_t)f * N;
-    if (!dbl) {
-      for (int k = 0; k < K; ++k) e[k] = 0.0f;
-      for (int n = 0; n < N; ++n) {
-        const float a = d[n];
-        const float* w = Wt + (size_t)n * K;
-        for (int k = 0; k < K; ++k) e[k] = fmaf(a, w[k], e[k]);
-      }
-    } else {
-      double* acc = (double*)calloc((size_t)K, sizeof(double));
-      for (int n = 0; n < N; ++n) {
-        const double a = d[n];
-        const float* w = Wt + (size_t)n * K;
-        for (int k = 0; k < K; ++k) acc[k] += a * (double)w[k];
-      }
-      for (int k = 0; k < K; ++k) e[k] = (float)acc[k];
-      free(acc);
-    }
-  }
-  free(Dc);
-  free(Wt);
+  (dbl ? gemm_core_dbl : gemm_core)(B, N, K, D, (size_t)N, 1, W, 1, (size_t)N, NULL, E, (size_t)K, tf32);
 }
 
-/* G[K x N] = Y^T[K x B] * D[B x N] (SgemmNT with beta 0, BP_GPU.cu:642); gb[n] = sum_f D[f][n] in frame order
- * (kernAccSumrow with alpha 0, beta 1: BP_GPU.cu:647, DevFunc.cu:234-240). */
+/* G[K x N] = Y^T[K x B] * D[B x N] (SgemmNT with beta 0, BP_GPU.cu:642): sum over frames ascending; gb[n] =
+ * sum_f D[f][n] in frame order (kernAccSumrow with alpha 0, beta 1: BP_GPU.cu:647, DevFunc.cu:234-240). */
 static void gemm_dw(int B, int K, int N, const float* Y, const float* D, float* G, float* gb, int tf32, int dbl) {
-  float* Yc = cond_copy(Y, (size_t)B * K, tf32);
-  float* Dc = cond_copy(D, (size_t)B * N, tf32);
-#pragma omp parallel for schedule(static)
-  for (int k = 0; k < K; ++k) {
-    float* g = G + (size_t)k * N;
-    if (!dbl) {
-      for (int j = 0; j < N; ++j) g[j] = 0.0f;
-      for (int f = 0; f < B; ++f) {
-        const float a = Yc[(size_t)f * K + k];
-        const float* d = Dc + (size_t)f * N;
-        for (int j = 0; j < N; ++j) g[j] = fmaf(a, d[j], g[j]);
-      }
-    } else {
-      double* acc = (double*)calloc((size_t)N, sizeof(double));
-      for (int f = 0; f < B; ++f) {
-        const double a = Yc[(size_t)f * K + k];
-        const float* d = Dc + (size_t)f * N;
-        for (int j = 0; j < N; ++j) acc[j] += a * (double)d[j];
-      }
-      for (int j = 0; j < N; ++j) g[j] = (float)acc[j];
-      free(acc);
-    }
-  }
+  (dbl ? gemm_core_dbl : gemm_core)(K, B, N, Y, 1, (size_t)K, D, (size_t)N, 1, NULL, G, (size_t)N, tf32);
   /* The CUDA path obtains the bias gradient from the same GEMM through an all-ones input column, so in tf32 mode the
    * addends are the conditioned D values; in literal mode they are D itself. */
-  for (int j = 0; j < N; ++j) {
-    if (!dbl) {
-      float s = 0.0f * 0.0f + 1.0f * Dc[j];
-      for (int f = 1; f < B; ++f) s += 1.0f * Dc[(size_t)f * N + j];
-      gb[j] = s;
-    } else {
+  if (!dbl) {
+    for (int j = 0; j < N; ++j) gb[j] = 0.0f * 0.0f + 1.0f * tf32_cond(D[j], tf32);
+    for (int f = 1; f < B; ++f)
+      for (int j = 0; j < N; ++j) gb[j] += 1.0f * tf32_cond(D[(size_t)f * N + j], tf32);
+  } else {
+    for (int j = 0; j < N; ++j) {
       double s = 0.0;
-      for (int f = 0; f < B; ++f) s += (double)Dc[(size_t)f * N + j];
+      for (int f = 0; f < B; ++f) s += (double)tf32_cond(D[(size_t)f * N + j], tf32);
       gb[j] = (float)s;
     }
   }
-  free(Yc);
-  free(Dc);
 }
 
 /* kernUpdatedelta (DevFunc.cu:313-318) then kernAccSum with beta 1 (DevFunc.cu:270-277):
@@ -246,6 +303,7 @@ void orc_train_bunch(const orc_cfg* c, float** weights, float** bias, float** dw
     float* x = (float*)malloc((size_t)B * N * sizeof(float));
     gemm_fwd(B, K, N, y[l - 1], weights[l], bias[l], x, c->tf32, c->accum_double);
     if (l != L) { /* :560-562 */
+#pragma omp parallel for schedule(static)
       for (size_t i = 0; i < (size_t)B * N; ++i) x[i] = act_f(x[i], c->activation);
     } /* else linear output (:564-571) */
     y[l] = x;
@@ -260,8 +318,10 @@ void orc_train_bunch(const orc_cfg* c, float** weights, float** bias, float** dw
     float* d = (float*)malloc((size_t)B * N * sizeof(float));
     if (l == L) { /* kernSubClean DevFunc.cu:253-268: (2.0f/rows)*(out - clean) */
       const float s = 2.0f / c->bunchsize;
+#pragma omp parallel for schedule(static)
       for (size_t i = 0; i < (size_t)B * N; ++i) d[i] = s * (y[L][i] - targ[i]);
     } else { /* kernDsigmoid + kernVecMul :614-615 (on the post-dropout y) */
+#pragma omp parallel for schedule(static)
       for (size_t i = 0; i < (size_t)B * N; ++i) d[i] = dact_f(y[l][i], c->activation) * dedy[i];
       free(dedy);
       dedy = NULL;
@@ -316,13 +376,16 @@ void orc_forward(const orc_cfg* c, float** weights, float** bias, int n_frames, 
       if (c->dropoutflag == 1) {
         const float keep = 1.0f - ((l == 1) ? c->visible_omit : c->hid_omit);
         Ws = (float*)malloc((size_t)K * N * sizeof(float));
+#pragma omp parallel for schedule(static)
         for (size_t j = 0; j < (size_t)K * N; ++j) Ws[j] = W[j] * keep; /* kernWeightMultiP DevFunc.cu:20-33 */
         W = Ws;
       }
       float* x = (l == L) ? out + (size_t)i * N : (float*)malloc((size_t)n * N * sizeof(float));
       gemm_fwd(n, K, N, prev, W, bias[l], x, c->tf32, c->accum_double);
-      if (l != L)
+      if (l != L) {
+#pragma omp parallel for schedule(static)
         for (size_t j = 0; j < (size_t)n * N; ++j) x[j] = act_f(x[j], c->activation);
+      }
       free(Ws);
       free(owned);
       owned = (l == L) ? NULL : x;

@@ -44,6 +44,9 @@ def lib():
         L.orc_dropout_mask.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
         L.orc_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_philox.restype = None
+        for fn in (L.orc_gemm, L.orc_gemm_naive):
+            fn.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int]
+            fn.restype = None
         _lib = L
     return _lib
 
@@ -115,6 +118,19 @@ class Net:
 
 def sgd(delta, w, grad, n, momentum, lr, wc):
     lib().orc_sgd(delta.size, _p(delta), _p(w), _p(grad), int(n), momentum, lr, wc)
+
+
+def gemm(A, B, init=None, tf32=0, naive=False):
+    """C = init + A @ B through the oracle's blocked GEMM core (or the naive triple loop it must equal bit for bit)."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    M, R = A.shape
+    N = B.shape[1]
+    out = np.empty((M, N), dtype=np.float32)
+    ini = None if init is None else np.ascontiguousarray(init, dtype=np.float32)
+    (lib().orc_gemm_naive if naive else lib().orc_gemm)(M, R, N, _p(A), _p(B), _p(ini) if ini is not None else None,
+                                                        _p(out), int(tf32))
+    return out
 
 
 def dropout_mask(seed, step, tensor, frame, unit, p):
