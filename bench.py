@@ -433,16 +433,19 @@ def main():
                     line["roofline"]["isolated_dominant_kernel"] = iso
             except Exception as e:  # a measurement aid must not hide the bench line
                 line["roofline"]["isolated_dominant_kernel"] = {"error": str(e)}
-        sgd_ms = max(prof["sgd"] / nprof, 1e-9)
-        # algorithmic minimum 20 B/parameter over the parameters the timed launch updates: layer 1
-        # when the upper layers were updated early, else all of them
-        early = prof["sgd_upper"] > 0.0 and len(sizes) > 2
-        sgd_bytes = 20.0 * ((sizes[0] + 1) * sizes[1] if early else n_params(sizes))
-        line["roofline_sgd"] = {"bound": "hbm", "kernel": "bp_sgd_kernel (final launch)", "achieved": sgd_bytes / (sgd_ms * 1e-3) / 1e9,
-                                "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": sgd_bytes / (sgd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                "traffic": traffic.get("sgd_dram_bytes_per_launch") if args.workload == "C2" else None,
-                                "peak_source": peak_src}
+        if prof["sgd"] / nprof < 0.003:   # BP_FUSED_UPDATE=1: the dW epilogues applied the update; no launch to time
+            line["roofline_sgd"] = None
+        else:
+            sgd_ms = prof["sgd"] / nprof
+            # algorithmic minimum 20 B/parameter over the parameters the timed launch updates: layer 1
+            # when the upper layers were updated early, else all of them
+            early = prof["sgd_upper"] > 0.0 and len(sizes) > 2
+            sgd_bytes = 20.0 * ((sizes[0] + 1) * sizes[1] if early else n_params(sizes))
+            line["roofline_sgd"] = {"bound": "hbm", "kernel": "bp_sgd_kernel (final launch)", "achieved": sgd_bytes / (sgd_ms * 1e-3) / 1e9,
+                                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": sgd_bytes / (sgd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                    "traffic": traffic.get("sgd_dram_bytes_per_launch") if args.workload == "C2" else None,
+                                    "peak_source": peak_src}
     else:
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
         ach = fl / (ms / K * 1e-3) / 1e12

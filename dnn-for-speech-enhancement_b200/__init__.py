@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
     lib.bp_train_resident.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bp_forward_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.POINTER(C.c_double)]
     lib.bp_sync.argtypes = [C.c_void_p]
+    lib.bp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
@@ -315,6 +316,10 @@ class BP_GPU:
         _check(load_library().bp_forward_resident(self._h, int(first_frame), int(n_frames), _ptr(out),
                                                   C.byref(sq) if want_sqerr else None), "bp_forward_resident")
         return out, (float(sq.value) if want_sqerr else None)
+
+    def set_option(self, name: str, value: int) -> None:
+        """Run-time switch of an experimental code path (bp_set_option), e.g. ``set_option("fused_update", 1)``."""
+        _check(load_library().bp_set_option(self._h, name.encode(), int(value)), "bp_set_option")
 
     def sync(self) -> None:
         _check(load_library().bp_sync(self._h), "bp_sync")

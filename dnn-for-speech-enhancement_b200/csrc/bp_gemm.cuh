@@ -46,6 +46,8 @@ enum Epi : int {
   EPI_FWD_HID = 1,    // y = act(scale*acc + bias[m]) (+dropout)  (hidden layer forward)
   EPI_FWD_OUT = 2,    // o = scale*acc + bias[m]; optional out2 = o; optional out = gscale*(o - targ); optional sqerr
   EPI_DX = 3,         // out = act'(aux) * acc                    (back-prop through the non-linearity)
+  EPI_DW_SGD = 4,     // acc = gradient tile, consumed in place: momentum-SGD update of the same tile of the weight and
+                      // delta arenas (kernUpdatedelta + kernAccSum, DevFunc.cu:313-318, 270-277); no gradient is stored
 };
 
 struct GemmParams {
@@ -87,6 +89,17 @@ struct GemmParams {
   long long* dbg_trace;   // if non-null, CTA 0 records clock64() per k-block: [0..255] producer slot free,
                           // [256..511] loads issued, [512..767] stage full seen, [768..1023] MMAs issued,
                           // [1024] accumulator ready seen by epilogue, [1025] epilogue done, [1026] CTA start
+  // EPI_DW_SGD (single GPU, BP_FUSED_UPDATE=1): the epilogue of the weight-gradient product applies the update to its
+  // own tile — element (m,n) of the product is parameter upd_w[n*ldo + m] (same layout as `out`).  Replaces the
+  // gradient store (4 B/param) + bp_sgd_kernel (20 B/param) by 16 B/param inside the GEMM, under the next tile's MMAs.
+  float* upd_w;
+  float* upd_delta;
+  float* upd_w_lo;        // 3xTF32: low part of the new weights, or null
+  float upd_nf;           // `n` of kernUpdatedelta (global bunch), int promoted to float
+  float upd_inv_nf;       // 1/upd_nf if that is exact (power of two: g*2^-k == g/2^k bit for bit), else 0 -> divide
+  float upd_momentum, upd_c1, upd_wc;  // c1 = (1-momentum)*lr
+  int upd_bias_col;       // product column that is the bias row of the block (weight cost does not apply, BP_GPU.cu:648)
+  int upd_prefetch;       // 1: epilogue warps pull their tile's delta/w lines into L2 while the main loop runs
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -234,6 +247,85 @@ __device__ __forceinline__ void gemm_dx_store(const GemmParams& p, const uint32_
       *o = dv;
       if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
     }
+}
+
+// EPI_DW_SGD: momentum-SGD update applied by the weight-gradient GEMM's own epilogue.  Operation for operation the
+// arithmetic of bp_sgd_kernel (bp_elementwise.cuh), so fused and unfused runs give identical bits:
+//   t = g/n (+ wc*w);  delta = m*delta - c1*t;  w = delta + w          one rounding per operation, no contraction.
+// Every parameter is read and written by exactly one thread of one CTA, once per launch.  Like EPI_DX's Y operand the
+// delta/w values of a 32-column chunk are fetched one chunk ahead of their use (the first chunk before the accumulator
+// is waited for), and the whole tile's lines are pulled into L2 while the main loop runs (upd_prefetch).
+struct SgdPrefetch {
+  float d[2][32], x[2][32];
+  __device__ __forceinline__ void load(const GemmParams& p, int slot, int m, bool m_ok, int nc) {
+    if (!m_ok || nc >= p.N) return;
+    const size_t off = size_t(nc) * p.ldo + m;
+    const float* pd = p.upd_delta + off;
+    const float* px = p.upd_w + off;   // plain loads: this kernel writes the arena (never the non-coherent path)
+    const bool whole = nc + 32 <= p.N;
+#pragma unroll
+    for (int j = 0; j < 32; ++j, pd += p.ldo, px += p.ldo) {
+      const bool ok = whole || nc + j < p.N;
+      d[slot][j] = ok ? __ldcs(pd) : 0.0f;   // deltas are touched by nobody else until the next update: streamed
+      x[slot][j] = ok ? *px : 0.0f;
+    }
+  }
+};
+
+__device__ __forceinline__ void gemm_sgd_l2_prefetch(const GemmParams& p, int m_base, int n0, int block_n, int lane) {
+  if (!p.upd_prefetch || m_base >= p.M) return;
+  for (int c = 0; c < block_n; c += 32) {
+    const int n = n0 + c + lane;   // lane j <-> the line of row n0+c+j that holds columns [m_base, m_base+32)
+    if (n < p.N) {
+      const size_t off = size_t(n) * p.ldo + m_base;
+      prefetch_l2(p.upd_delta + off);
+      prefetch_l2(p.upd_w + off);
+    }
+  }
+}
+
+__device__ __forceinline__ void gemm_sgd_store(const GemmParams& p, const uint32_t (&v)[32], const float (&dv)[32],
+                                               const float (&xv)[32], int m, bool m_ok, int nc) {
+  if (!m_ok) return;
+  const bool whole = nc + 32 <= p.N;
+  const size_t off = size_t(nc) * p.ldo + m;
+  float* pd = p.upd_delta + off;
+  float* px = p.upd_w + off;
+  float* pl = p.upd_w_lo != nullptr ? p.upd_w_lo + off : nullptr;
+  const bool has_wc = p.upd_wc != 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j, pd += p.ldo, px += p.ldo) {
+    if (whole || nc + j < p.N) {
+      const float g = __uint_as_float(v[j]);
+      float t = p.upd_inv_nf != 0.0f ? __fmul_rn(g, p.upd_inv_nf) : __fdiv_rn(g, p.upd_nf);
+      if (has_wc) t = __fadd_rn(t, __fmul_rn(nc + j == p.upd_bias_col ? 0.0f : p.upd_wc, xv[j]));
+      const float nd = __fsub_rn(__fmul_rn(p.upd_momentum, dv[j]), __fmul_rn(p.upd_c1, t));
+      const float xn = __fadd_rn(nd, xv[j]);
+      __stcs(pd, nd);
+      *px = xn;
+      if (pl != nullptr) pl[size_t(j) * p.ldo] = tf32_lo(xn);
+    }
+  }
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void gemm_sgd_epilogue(const GemmParams& p, SgdPrefetch& pre, uint32_t taddr, int m, bool m_ok,
+                                                  int n0) {
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N / 32; c += 2) {
+    const int nc = n0 + c * 32;
+    if (nc >= p.N) break;
+    uint32_t v[32];
+    pre.load(p, 1, m, m_ok, nc + 32);          // next chunk's delta/w in flight while this one is processed
+    tmem_ld32(taddr + uint32_t(c * 32), v);
+    tmem_ld_wait();
+    gemm_sgd_store(p, v, pre.d[0], pre.x[0], m, m_ok, nc);
+    if (nc + 32 >= p.N) break;
+    if (c + 2 < BLOCK_N / 32) pre.load(p, 0, m, m_ok, nc + 64);
+    tmem_ld32(taddr + uint32_t((c + 1) * 32), v);
+    tmem_ld_wait();
+    gemm_sgd_store(p, v, pre.d[1], pre.x[1], m, m_ok, nc + 32);
+  }
 }
 
 template <int BLOCK_N>
@@ -441,6 +533,11 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool m_ok = m < p.M;
       DxPrefetch pre;
       if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);  // under the main loop (see gemm_dx_epilogue)
+      SgdPrefetch upd;
+      if constexpr (kEpi == EPI_DW_SGD) {
+        upd.load(p, 0, m, m_ok, n0);
+        gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
+      }
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
       if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
@@ -452,6 +549,8 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
+      } else if constexpr (kEpi == EPI_DW_SGD) {
+        gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {

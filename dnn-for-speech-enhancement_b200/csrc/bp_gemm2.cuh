@@ -260,6 +260,11 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // the main loop, and the following chunks two steps ahead of their use (see gemm_dx_epilogue).
       DxPrefetch pre;
       if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);
+      SgdPrefetch upd;  // EPI_DW_SGD: the update's delta/w operands, same software pipeline (see gemm_sgd_epilogue)
+      if constexpr (kEpi == EPI_DW_SGD) {
+        upd.load(p, 0, m, m_ok, n0);
+        gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
+      }
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
       if constexpr (kTrace) {
@@ -273,6 +278,8 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
+      } else if constexpr (kEpi == EPI_DW_SGD) {
+        gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {

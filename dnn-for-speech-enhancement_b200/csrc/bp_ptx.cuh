@@ -143,6 +143,11 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// L2-only prefetch of the 128-byte line holding *p (fire and forget, no register, no L1 allocation).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

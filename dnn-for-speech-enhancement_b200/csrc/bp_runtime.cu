@@ -338,25 +338,31 @@ template <bool kAMN, bool kBMN, int kEpi>
 int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
                 const MapPair* b64 = nullptr) {
   const KernelChoice k = pick_kernel(p, num_sms, b64 != nullptr);
-  if (k.pair_n == 256) {
-    if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
-    if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
-    if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1, true>(st, num_sms, a.full, b, p);
-    return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+  if constexpr (kEpi == EPI_DW_SGD) {  // fused update: plain pairs / lone CTAs only (no multicast, trace or stage variants)
+    if (k.pair_n == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+    if (k.pair_n == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
+    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
+  } else {
+    if (k.pair_n == 256) {
+      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
+      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
+      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1, true>(st, num_sms, a.full, b, p);
+      return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+    }
+    if (k.pair_n == 128) {
+      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
+      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
+      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
+      static const int stages = [] {
+        const char* e = getenv("BP_STAGES");  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
+        return e ? atoi(e) : 0;
+      }();
+      if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
+      if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
+      return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
+    }
+    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
   }
-  if (k.pair_n == 128) {
-    if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
-    if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
-    if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
-    static const int stages = [] {
-      const char* e = getenv("BP_STAGES");  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
-      return e ? atoi(e) : 0;
-    }();
-    if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
-    if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
-    return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
-  }
-  return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (lazy dlopen)
@@ -449,6 +455,10 @@ struct Rank {
   int dw_bn = 128;              // N-tile of the weight-gradient GEMM
   int ar_slices = 1;            // data-parallel: slices per layer gradient (BP_AR_SLICES; >1 measured slower: many
                                 // small all-reduces are latency-bound)
+  int fused_update = 0;         // single GPU: the dW GEMM's epilogue applies the momentum-SGD update to its own tile
+                                // (EPI_DW_SGD) instead of storing the gradient for bp_sgd_kernel.  BP_FUSED_UPDATE=1 /
+                                // bp_set_option("fused_update"); default off until measured on the B200
+  int fused_prefetch = 1;       // ... with the tile's delta/w lines pulled into L2 under the main loop
   int comm_sms = 0;             // data-parallel: SMs the persistent GEMMs leave free so that NCCL's kernels can run
                                 // next to them instead of behind them (BP_COMM_SMS; 16/32 measured no better: the
                                 // exposed all-reduce time is that of the last, largest layers' gradients)
@@ -643,6 +653,8 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
   if (const char* e = getenv("BP_AR_SLICES")) r->ar_slices = std::max(1, atoi(e));
   if (const char* e = getenv("BP_COMM_SMS")) r->comm_sms = std::max(0, std::min(64, atoi(e)));
+  if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
+  if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -1149,9 +1161,12 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   // update has not touched it yet).  So dW_l is launched on the side stream as soon as dE/dX_l exists and runs
   // concurrently with the rest of the dX chain, filling the SMs a 128-tile GEMM leaves idle on a 148-SM part.
   // Last layer first, so its all-reduce starts earliest.
-  auto launch_dw = [&](int l) -> int {
+  // Fused update (single GPU, off by default): dW_l's epilogue rewrites W_l in place, so it may only start when the dX
+  // product that reads W_l (the one producing dE/dX_{l-1}) is complete — `after` is then ev_d[l-1] instead of ev_d[l].
+  const bool fused = r->fused_update && !r->nccl_comm && !r->dp_p2p && cf.world_size == 1;
+  auto launch_dw = [&](int l, cudaEvent_t after) -> int {
     LayerState& ls = r->layer[l];
-    CU_TRY(cudaStreamWaitEvent(r->side, r->ev_d[l], 0));
+    CU_TRY(cudaStreamWaitEvent(r->side, after, 0));
     GemmParams p{};
     p.M = ls.N;
     p.N = ls.K + 1;  // + the all-ones column -> row K of the gradient block = bias gradient
@@ -1180,6 +1195,22 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
       for (int o = 0; o < cf.world_size; ++o)
         p.scatter[o] = r->peer[o].recv + (long long)cf.rank * r->arena_floats + ls.off;
     }
+    if (fused) {
+      p.out = nullptr;  // the gradient never reaches memory
+      p.upd_w = r->w + ls.off;
+      p.upd_delta = r->dw + ls.off;
+      p.upd_w_lo = r->w_lo ? r->w_lo + ls.off : nullptr;
+      p.upd_nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
+      p.upd_inv_nf = (cf.bunchsize & (cf.bunchsize - 1)) == 0 ? 1.0f / (float)cf.bunchsize : 0.0f;
+      p.upd_momentum = cf.momentum;
+      p.upd_c1 = (1 - cf.momentum) * cf.lrate;
+      p.upd_wc = cf.weightcost;
+      p.upd_bias_col = ls.K;
+      p.upd_prefetch = r->fused_prefetch;
+      BP_TRY((launch_gemm<true, true, EPI_DW_SGD>(r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
+      r->launches++;
+      return BP_OK;
+    }
     const int total = p.N;
     int slices = 1;
     if (r->nccl_comm && !r->dp_p2p) slices = std::max(1, std::min(r->ar_slices, (total + kBlockN - 1) / kBlockN));
@@ -1205,10 +1236,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     if (r->nccl_comm && !r->dp_p2p) CU_TRY(cudaEventRecord(r->ev_comm_upper, r->comm_stream));
     return BP_OK;
   };
-  CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
-  BP_TRY(launch_dw(r->L));
-  if (r->L == 2) BP_TRY(mark_upper());
-  for (int l = r->L; l >= 2; --l) {
+  auto launch_dx = [&](int l) -> int {  // dE/dX_{l-1} = act'(Y_{l-1}) .* (dE/dX_l W_l^T), then ev_d[l-1]
     LayerState& ls = r->layer[l];
     LayerState& lp = r->layer[l - 1];
     GemmParams p{};
@@ -1226,8 +1254,24 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     BP_TRY((launch_gemm<false, false, EPI_DX>(r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
     r->launches++;
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
-    if (l - 1 == 1 && r->L > 2) BP_TRY(mark_upper());  // before dW_1 enters the side stream
-    BP_TRY(launch_dw(l - 1));
+    return BP_OK;
+  };
+  CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
+  if (fused) {
+    // dW_l (which rewrites W_l) follows the dX product that read W_l; it still overlaps the rest of the dX chain.
+    for (int l = r->L; l >= 2; --l) {
+      BP_TRY(launch_dx(l));
+      BP_TRY(launch_dw(l, r->ev_d[l - 1]));
+    }
+    BP_TRY(launch_dw(1, r->ev_d[1]));
+  } else {
+    BP_TRY(launch_dw(r->L, r->ev_d[r->L]));
+    if (r->L == 2) BP_TRY(mark_upper());
+    for (int l = r->L; l >= 2; --l) {
+      BP_TRY(launch_dx(l));
+      if (l - 1 == 1 && r->L > 2) BP_TRY(mark_upper());  // before dW_1 enters the side stream
+      BP_TRY(launch_dw(l - 1, r->ev_d[l - 1]));
+    }
   }
   mark();                                               // 2: dX chain issued/done on `compute`
   const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
@@ -1258,7 +1302,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     return e ? atoi(e) : 6;
   }();
   long long tail_end4 = r->arena_floats / 4;
-  if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p) {
+  if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p && !fused) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
     if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
     tail_end4 = r->layer[2].off / 4;
@@ -1274,7 +1318,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   }
   mark();                                               // 5: all-reduce waited
   if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
-  else BP_TRY(launch_sgd(0, tail_end4, 8));
+  else if (!fused) BP_TRY(launch_sgd(0, tail_end4, 8)); // fused: the dW epilogues have already applied the update
   mark();                                               // 6: sgd done
   r->step++;
   r->bunches++;
@@ -1672,6 +1716,16 @@ int bp_forward(bp_handle* h, int n_frames, const float* in, float* out) {
 int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias) {
   if (!h || !weights || !bias) return fail(BP_EINVAL, "bp_return_weights: null argument");
   return rank_return_weights(h->ranks[0], weights, bias);  // device 0, BP_GPU.cu:915
+}
+
+int bp_set_option(bp_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(BP_EINVAL, "bp_set_option: null argument");
+  for (Rank* r : h->ranks) {
+    if (strcmp(name, "fused_update") == 0) r->fused_update = value != 0;
+    else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
+    else return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
+  }
+  return BP_OK;
 }
 
 int bp_sync(bp_handle* h) {

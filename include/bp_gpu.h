@@ -91,6 +91,15 @@ int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias);
  * the three hyper-parameters are replaced, and the dropout step counter restarts iff reset_dropout_step != 0. */
 int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, int reset_dropout_step);
 
+/* Run-time switches of experimental / measurement code paths (defaults come from the environment variable of the same
+ * meaning at bp_create time).  Results are unaffected; only scheduling and fusion change.  Known names:
+ *   "fused_update"   1: on a single GPU the weight-gradient GEMM's epilogue applies kernUpdatedelta + kernAccSum
+ *                       (DevFunc.cu:313-318, 270-277) to its own tile instead of storing the gradient for a separate
+ *                       update kernel — bit-identical weights, 16 instead of 24 B/parameter (BP_FUSED_UPDATE)
+ *   "fused_prefetch" 1: ... with the tile's delta/weight lines prefetched into L2 under the main loop (default 1)
+ * Returns BP_EINVAL for an unknown name. */
+int bp_set_option(bp_handle* h, const char* name, int value);
+
 /* Last error message of the calling thread ("" if none). */
 const char* bp_last_error(void);
 

@@ -1,7 +1,9 @@
+timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
 # First GPU call of the next round: A/B (one box) of the switches prepared but not yet measured at the end of round 1.
 #   BP_L2_PREFETCH=k   producer issues L2-only TMA prefetches k k-blocks ahead of its shared-memory ring (+ under PDL)
 #   BP_DW_STREAM=1     gradient tiles stored with st.global.cs (evict-first)
 #   BP_STAGES=2|3      128-wide pair kernels with a 2- / 3-deep ring (2: two CTAs per SM, fill/drain overlap)
+#   fused update       scripts/gpu_fused_update_check.py: bit-parity of EPI_DW_SGD vs bp_sgd_kernel, then ms/bunch
 # Each line: frames/s, ms per bunch, per-class ms.  Keep what wins by > 1 % twice.  Then the timeline of fwd vs dX.
 bash scripts/gpu_ab.sh "BP_L2_PREFETCH=0" "BP_L2_PREFETCH=4" "BP_L2_PREFETCH=8" "BP_L2_PREFETCH=16" \
                        "BP_DW_STREAM=1" "BP_DW_STREAM=1 BP_L2_PREFETCH=8" "BP_STAGES=2" "BP_STAGES=2 BP_L2_PREFETCH=8" \
