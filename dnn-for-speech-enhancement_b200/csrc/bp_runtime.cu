@@ -446,6 +446,8 @@ struct ChunkBuf {
   bool consumed_valid = false;
 };
 
+constexpr int kPeerFlagGroups = 4;  // counter groups of the peer-memory exchange (Rank::flags)
+
 struct Rank {
   bp_config cfg{};
   int L = 0;               // weight layers
@@ -495,7 +497,10 @@ struct Rank {
   };
   int dp_p2p = 0;
   float* recv = nullptr;                 // world_size slabs of arena_floats: recv + src*arena_floats
-  unsigned long long* flags = nullptr;   // [0..7] gradients of step s landed from src, [8..15] weights landed from src
+  unsigned long long* flags = nullptr;   // kPeerFlagGroups x kMaxPeers counters, group g at flags + g*kMaxPeers:
+                                         // 0 gradients of step s landed from src, 1 weights landed from src;
+                                         // BP_PEER_EARLY: 0/1 = layers >= 2, 2/3 = the same two for layer 1
+  int peer_early = 0;                    // BP_PEER_EARLY=1 (off by default, not yet run on GPUs)
   PeerMem peer[kMaxPeers];
   unsigned long long dp_step = 0;
   PeerLayers peer_layers{};
@@ -653,6 +658,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
   if (const char* e = getenv("BP_AR_SLICES")) r->ar_slices = std::max(1, atoi(e));
   if (const char* e = getenv("BP_COMM_SMS")) r->comm_sms = std::max(0, std::min(64, atoi(e)));
+  if (const char* e = getenv("BP_PEER_EARLY")) r->peer_early = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
   int rc = [&]() -> int {
@@ -1016,8 +1022,8 @@ int rank_p2p_alloc(Rank* r) {
   const size_t slab = sizeof(float) * (size_t)r->arena_floats * r->cfg.world_size;
   CU_TRY(cudaMalloc(&r->recv, slab));
   CU_TRY(cudaMemset(r->recv, 0, slab));
-  CU_TRY(cudaMalloc(&r->flags, sizeof(unsigned long long) * 2 * kMaxPeers));
-  CU_TRY(cudaMemset(r->flags, 0, sizeof(unsigned long long) * 2 * kMaxPeers));
+  CU_TRY(cudaMalloc(&r->flags, sizeof(unsigned long long) * kPeerFlagGroups * kMaxPeers));
+  CU_TRY(cudaMemset(r->flags, 0, sizeof(unsigned long long) * kPeerFlagGroups * kMaxPeers));
   CU_TRY(cudaDeviceSynchronize());
   Rank::PeerMem& me = r->peer[r->cfg.rank];
   me.w = r->w;
@@ -1143,6 +1149,47 @@ int peer_exchange(Rank* r) {
   bp_peer_wait_kernel<<<1, 32, 0, r->compute>>>(r->flags + kMaxPeers, W, step);
   CU_TRY(cudaGetLastError());
   r->launches += 4;
+  return BP_OK;
+}
+
+// BP_PEER_EARLY: the exchange in two parts, each on its own pair of counter groups.  part 0 = arena rows of the layers
+// >= 2 (groups 0/1), issued when their gradient GEMMs are complete and therefore running beside the first layer's;
+// part 1 = the first layer (groups 2/3), followed by the wait for every owner's rows of both parts.  Safe because an
+// owner overwrites a replica's W_l (l >= 2) only after that replica has published its part-0 gradients, which it does
+// in stream order behind its whole dX chain — the last reader of W_l in the bunch.
+int peer_exchange_part(Rank* r, int part, unsigned long long step, long long begin4, long long end4,
+                       int blocks_per_sm) {
+  const bp_config& cf = r->cfg;
+  const int W = cf.world_size, me = cf.rank;
+  const int g_grad = part == 0 ? 0 : 2, g_w = g_grad + 1;
+  PeerFlags fg{}, fw{};
+  PeerArenas pa{};
+  for (int p = 0; p < W; ++p) {
+    fg.slot[p] = r->peer[p].flags + g_grad * kMaxPeers + me;
+    fw.slot[p] = r->peer[p].flags + g_w * kMaxPeers + me;
+    pa.w[p] = (float4*)r->peer[p].w;
+    pa.w_lo[p] = (float4*)r->peer[p].w_lo;
+  }
+  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fg, W, step);
+  const float nf = (float)cf.bunchsize;
+  const float c1 = (1 - cf.momentum) * cf.lrate;
+  const int grid = r->num_sms * blocks_per_sm;
+  const unsigned long long* gf = r->flags + g_grad * kMaxPeers;
+  if (cf.weightcost != 0.0f)
+    bp_peer_sgd_kernel<true, true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
+                                                                 r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                                 cf.momentum, c1, cf.weightcost, gf, step, begin4, end4);
+  else
+    bp_peer_sgd_kernel<false, true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
+                                                                  r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                                  cf.momentum, c1, 0.0f, gf, step, begin4, end4);
+  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fw, W, step);
+  r->launches += 3;
+  if (part == 1) {
+    bp_peer_wait2_kernel<<<1, 32, 0, r->compute>>>(r->flags + kMaxPeers, r->flags + 3 * kMaxPeers, W, step);
+    r->launches++;
+  }
+  CU_TRY(cudaGetLastError());
   return BP_OK;
 }
 
@@ -1302,6 +1349,14 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     return e ? atoi(e) : 6;
   }();
   long long tail_end4 = r->arena_floats / 4;
+  const bool peer_split = r->dp_p2p && r->peer_early && r->L >= 2;
+  unsigned long long peer_step = 0;
+  if (peer_split) {  // exchange of the layers >= 2 beside dW_1 (which the side stream already holds)
+    peer_step = ++r->dp_step;
+    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
+    tail_end4 = r->layer[2].off / 4;
+    BP_TRY(peer_exchange_part(r, 0, peer_step, tail_end4, r->arena_floats / 4, 6));
+  }
   if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p && !fused) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
     if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
@@ -1317,7 +1372,8 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
   }
   mark();                                               // 5: all-reduce waited
-  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
+  if (peer_split) BP_TRY(peer_exchange_part(r, 1, peer_step, 0, tail_end4, 8));
+  else if (r->dp_p2p) BP_TRY(peer_exchange(r));         // owner-side reduce + update + all-gather
   else if (!fused) BP_TRY(launch_sgd(0, tail_end4, 8)); // fused: the dW epilogues have already applied the update
   mark();                                               // 6: sgd done
   r->step++;
@@ -1723,6 +1779,7 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
   for (Rank* r : h->ranks) {
     if (strcmp(name, "fused_update") == 0) r->fused_update = value != 0;
     else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
+    else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
     else return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
   }
   return BP_OK;

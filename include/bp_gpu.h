@@ -97,6 +97,9 @@ int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, 
  *                       (DevFunc.cu:313-318, 270-277) to its own tile instead of storing the gradient for a separate
  *                       update kernel — bit-identical weights, 16 instead of 24 B/parameter (BP_FUSED_UPDATE)
  *   "fused_prefetch" 1: ... with the tile's delta/weight lines prefetched into L2 under the main loop (default 1)
+ *   "peer_early"     1: data-parallel peer-memory exchange in two parts — the layers >= 2 are reduced, updated and
+ *                       all-gathered while the first layer's gradient GEMM still runs (BP_PEER_EARLY); every rank
+ *                       must be given the same value
  * Returns BP_EINVAL for an unknown name. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 
