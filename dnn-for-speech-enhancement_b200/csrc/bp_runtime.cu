@@ -1929,8 +1929,9 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
   bool amn, bmn;
   switch (kind) {
     case 0: case 3: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
-    case 1: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
+    case 1: case 4: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
     case 2: a_rows = K; a_cols = M; b_rows = K; b_cols = N; amn = true; bmn = true; break;
+    case 5: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
     default: return fail(BP_EINVAL, "bp_debug_gemm: kind %d", kind);
   }
   const long long dlda = round_up(a_cols, 32), dldb = round_up(b_cols, 32), dldo = round_up(M, 32),
@@ -1992,13 +1993,17 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     if (const char* e = getenv("BP_DBG_REPS")) reps = std::max(1, atoi(e));
     const int sms = prop.multiProcessorCount;
     if (kind == 0 && !bias) return fail(BP_EINVAL, "kind 0 needs bias");
-    if (kind == 1 && !aux) return fail(BP_EINVAL, "kind 1 needs aux (Y)");
+    if ((kind == 1 || kind == 5) && !aux) return fail(BP_EINVAL, "kind 1 / 5 needs aux (Y)");
     for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is an untimed warm-up when reps > 1
       if (rep == (reps > 1 ? 1 : 0)) CU_TRY(cudaEventRecord(e0, st));
       if (reps == 1 && rep == 1) break;
       if (kind == 0) BP_TRY((launch_gemm<true, false, EPI_FWD_HID>(st, sms, ma, mb, p, &mb64)));
       else if (kind == 3) BP_TRY((launch_gemm<true, false, EPI_PLAIN>(st, sms, ma, mb, p, &mb64)));
       else if (kind == 1) BP_TRY((launch_gemm<false, false, EPI_DX>(st, sms, ma, mb, p, &mb64)));
+      // diagnostics for the dX-vs-forward gap: the dX operand majors with the plain epilogue / the forward majors with
+      // the dX epilogue
+      else if (kind == 4) BP_TRY((launch_gemm<false, false, EPI_PLAIN>(st, sms, ma, mb, p, &mb64)));
+      else if (kind == 5) BP_TRY((launch_gemm<true, false, EPI_DX>(st, sms, ma, mb, p, &mb64)));
       else BP_TRY((launch_gemm<true, true, EPI_PLAIN>(st, sms, ma, mb, p, &mb64)));
     }
     CU_TRY(cudaEventRecord(e1, st));

@@ -188,7 +188,9 @@ int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame
  *  kind 0: fwd  out[n*ldo+m] = act(scale * sum_k W[k*ldw+m] * X[n*ldx+k] + bias[m])     A=W (K x M), B=X (N x K)
  *  kind 1: dX   out[n*ldo+m] = act'(Y[n*ldy+m]) * sum_k W[m*ldw+k] * D[n*ldd+k]         A=W (M x K), B=D (N x K)
  *  kind 2: dW   out[n*ldo+m] = sum_k D[k*ldd+m] * X[k*ldx+n]                            A=D (K x M), B=X (K x N)
- *  kind 3: plain fwd (no bias/activation).   act < 0 means "no activation" for kind 0. */
+ *  kind 3: plain fwd (no bias/activation).   act < 0 means "no activation" for kind 0.
+ *  kind 4: kind 1's operands (A = W, M x K) with the plain epilogue;  kind 5: kind 0's operands (A = W, K x M) with
+ *          kind 1's epilogue (act'(Y) * acc) — diagnostics that separate operand layout from epilogue cost. */
 int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* out,
                   int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
                   float* elapsed_ms);
