@@ -1,3 +1,4 @@
+timeout 200 python scripts/gpu_edge_cases.py 2>&1 | tail -24
 timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
 # First GPU call of the next round: A/B (one box) of the switches prepared but not yet measured at the end of round 1.
 #   BP_L2_PREFETCH=k   producer issues L2-only TMA prefetches k k-blocks ahead of its shared-memory ring (+ under PDL)
