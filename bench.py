@@ -323,6 +323,8 @@ def main():
     px, pt = bp.PinnedArray((n_chunk, sizes[0])), bp.PinnedArray((n_chunk, sizes[-1]))
     synth(n_chunk, sizes[0], sizes[-1], seed=100 + rank, out_x=px.array, out_t=pt.array)
     g.upload_chunk(n_chunk, px.array, pt.array)
+    barrier()   # ranks generate their chunks on shared host cores: line them up before the first collective bunch (the
+                # peer-memory exchange traps after ~10 s of waiting for a rank that has not arrived)
 
     def run_resident(n_steps):
         done = 0

@@ -5,6 +5,7 @@
 //           train_sent_range=a-b cv_sent_range=c-d fea_dim=.. fea_context=.. targ_offset=.. traincache=.. bunchsize=..
 //           layersizes=a,b,.. lrate=.. momentum=.. weightcost=.. dropoutflag=.. visible_omit=.. hid_omit=..
 //           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=.. reader=host|gpu]
+//           [prefetch=0|1  reader=gpu only: chunk i+1 is read while chunk i is uploaded and queued (default 1)]
 //           [epochs=N epoch_first=1 momentum_step=0.04 momentum_max=0.9 seed_step=345  with %d in outwts_file/log_file]
 //
 // epochs=N (> 1) runs the Perl driver's loop (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-249) inside this
@@ -17,11 +18,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <vector>
 
 #include "../../include/bp_gpu.h"
 #include "DecodeWriter.h"
 #include "Interface.h"
+#include "RawPrefetch.h"
 
 static double now_s() {  // the reference uses time(NULL) (1 s steps); the log lines keep their format
   timespec ts;
@@ -66,18 +69,26 @@ static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
   unsigned long long trained_samples = 0;
   RawChunk raw;  // reader=gpu: records + sample table of the current chunk
   const double t_train0 = now_s();
-  for (unsigned int i = 0; i < io->total_chunks; ++i) {
-    const int n = para->reader_gpu ? io->ReadchunkRaw(chunk_index[i], &raw) : io->Readchunk(chunk_index[i]);
-    fprintf(io->fp_log, "Starting chunk %d of %d containing %d samples.\n", i + 1, io->total_chunks, n);
-    fflush(io->fp_log);
-    if (n > 0 && para->reader_gpu) {
-      const bp_raw_chunk c = as_abi(io, raw);
-      if (bp_train_raw(trainer, &c) != BP_OK) die(io, "train failed");
-    } else if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) {
-      die(io, "train failed");
+  {
+    // reader=gpu prefetch=1: the same ReadchunkRaw calls in the same order, one chunk ahead on a reader thread
+    std::unique_ptr<RawPrefetcher> ahead;
+    if (para->reader_gpu && para->prefetch && io->total_chunks > 1) ahead.reset(new RawPrefetcher(io, chunk_index));
+    for (unsigned int i = 0; i < io->total_chunks; ++i) {
+      RawChunk* cur = &raw;
+      const int n = ahead            ? ahead->next(&cur)
+                    : para->reader_gpu ? io->ReadchunkRaw(chunk_index[i], &raw)
+                                       : io->Readchunk(chunk_index[i]);
+      fprintf(io->fp_log, "Starting chunk %d of %d containing %d samples.\n", i + 1, io->total_chunks, n);
+      fflush(io->fp_log);
+      if (n > 0 && para->reader_gpu) {
+        const bp_raw_chunk c = as_abi(io, *cur);
+        if (bp_train_raw(trainer, &c) != BP_OK) die(io, "train failed");
+      } else if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) {
+        die(io, "train failed");
+      }
+      trained_samples += n;
     }
-    trained_samples += n;
-  }
+  }  // joins the reader thread before the Interface is used for the weight dump and the CV pass
 
   printf("begin to write weights\n");
   if (bp_return_weights(trainer, para->weights, para->bias) != BP_OK) die(io, "returnWeights failed");

@@ -229,6 +229,10 @@ void Interface::Initial(int argc, char** argv) {
       para->reader_gpu = (strcmp(val, "gpu") == 0) ? 1 : 0;
       continue;
     }
+    if (key == "prefetch") {  // reader=gpu: read chunk i+1 on a second thread while chunk i is uploaded (default 1)
+      para->prefetch = atoi(val) != 0 ? 1 : 0;
+      continue;
+    }
     if (key == "seed") {
       para->seed = strtoull(val, nullptr, 0);
       continue;

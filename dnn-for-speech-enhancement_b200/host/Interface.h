@@ -60,6 +60,7 @@ struct WorkPara {
   // extensions
   int nat = -1;            // -1 = infer from layersizes[0]
   int reader_gpu = 0;      // reader=gpu: splice / normalise / shuffle on the device (default host, as the reference)
+  int prefetch = 1;        // reader=gpu: the training chunks are read one ahead on a second thread (RawPrefetch.h)
   int activation = 0;      // 0 relu, 1 sigmoid
   unsigned long long seed = 0x5eed5eedULL;
   char decode_FN[MAXLINE] = "";

@@ -2,7 +2,8 @@
 // order and same lrand48 stream as reader_dump) the raw Pfile records and the sample table that
 // Interface::ReadchunkRaw / Readchunk_cvRaw plan.  tests/test_raw_reader.py replays the tables (numpy on CPU, the
 // splice kernel on the GPU) and compares the rows bit for bit with the reference reader's golden chunks.
-//   raw_dump <out.bin> key=value ...        (same argv keys as BPtrain)
+//   raw_dump <out.bin> key=value ...        (same argv keys as BPtrain; prefetch=1, the default, reads the training
+//                                            chunks through the RawPrefetcher thread exactly as BPtrain does)
 // out.bin: int32 fea_dim, ctx, targ_offset, nat, out_dim; float mean[fea_dim], inv_std[fea_dim];
 //          int32 n_train_chunks; per chunk: int32 id, n_records, n_samples; fea words; targ words;
 //          int32 sample_frame[n], sample_seg[n], sample_row[n];   int32 n_cv_chunks; the same.
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "Interface.h"
+#include "RawPrefetch.h"
 
 static void dump(FILE* f, int id, const RawChunk& rc, int dim, int out) {
   fwrite(&id, 4, 1, f);
@@ -44,9 +46,19 @@ int main(int argc, char** argv) {
   for (int i = 0; i < n; ++i) order[i] = i;
   io->GetRandIndex(order.data(), n);
   fwrite(&n, 4, 1, f);
-  for (int i = 0; i < n; ++i) {
-    io->ReadchunkRaw(order[i], &rc);
-    dump(f, order[i], rc, p->fea_dim, out);
+  if (p->prefetch && n > 1) {
+    RawPrefetcher ahead(io, order);
+    RawChunk* cur = nullptr;
+    for (int i = 0; i < n; ++i) {
+      if (ahead.next(&cur) < 0) return 3;
+      dump(f, order[i], *cur, p->fea_dim, out);
+    }
+    if (ahead.next(&cur) != -1) return 3;
+  } else {
+    for (int i = 0; i < n; ++i) {
+      io->ReadchunkRaw(order[i], &rc);
+      dump(f, order[i], rc, p->fea_dim, out);
+    }
   }
   io->get_chunk_info_cv(io->para->cv_sent_range);
   n = io->cv_total_chunks;

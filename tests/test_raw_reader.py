@@ -103,6 +103,26 @@ def test_raw_tables_reproduce_reference_reader(name):
         assert np.array_equal(t.view(np.uint32), gold[f"c{i}_t"].view(np.uint32)), f"chunk {i} targets differ"
 
 
+@pytest.mark.parametrize("traincache", [7, 16, 40])
+def test_prefetch_thread_reads_the_same_chunks_as_the_serial_loop(traincache):
+    """RawPrefetcher (host/RawPrefetch.h, BPtrain reader=gpu prefetch=1) runs the ReadchunkRaw calls one chunk ahead on
+    a second thread: records, tables and chunk order must be byte-identical with the serial loop (prefetch=0), also
+    when there are many more chunks than the two slots."""
+    _build()
+    case = dict(CASES["129"], traincache=traincache)
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, case)
+        dumps = []
+        for pf in (0, 1, 1):
+            out = os.path.join(d, f"raw{len(dumps)}.bin")
+            subprocess.check_call([EXE, out] + reader_args(d, case) + [f"prefetch={pf}"], cwd=d,
+                                  stdout=subprocess.DEVNULL)
+            dumps.append(open(out, "rb").read())
+        n_train = sum(1 for c in parse_raw_dump(os.path.join(d, "raw0.bin"))[1] if c["kind"] == 0)
+    assert n_train >= {7: 5, 16: 4, 40: 2}[traincache]
+    assert dumps[0] == dumps[1] == dumps[2]
+
+
 def _net(bp, case, bunch, **kw):
     ls = layersizes(case)
     rng = np.random.default_rng(1)
