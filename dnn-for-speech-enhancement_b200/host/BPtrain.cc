@@ -5,7 +5,7 @@
 //           train_sent_range=a-b cv_sent_range=c-d fea_dim=.. fea_context=.. targ_offset=.. traincache=.. bunchsize=..
 //           layersizes=a,b,.. lrate=.. momentum=.. weightcost=.. dropoutflag=.. visible_omit=.. hid_omit=..
 //           gpu_used=N init_randem_seed=..   [nat=0|1 activation=relu|sigmoid seed=.. decode_file=.. reader=host|gpu]
-//           [prefetch=0|1  reader=gpu only: chunk i+1 is read while chunk i is uploaded and queued (default 1)]
+//           [prefetch=0|1  chunk i+1 is read by a second thread while chunk i is uploaded and queued (default 1)]
 //           [epochs=N epoch_first=1 momentum_step=0.04 momentum_max=0.9 seed_step=345  with %d in outwts_file/log_file]
 //
 // epochs=N (> 1) runs the Perl driver's loop (finetune_DNN_speech_enhancement_dropout_NAT.pl:131-249) inside this
@@ -24,7 +24,7 @@
 #include "../../include/bp_gpu.h"
 #include "DecodeWriter.h"
 #include "Interface.h"
-#include "RawPrefetch.h"
+#include "ChunkPrefetch.h"
 
 static double now_s() {  // the reference uses time(NULL) (1 s steps); the log lines keep their format
   timespec ts;
@@ -67,28 +67,34 @@ static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
   for (unsigned int i = 0; i < io->total_chunks; ++i) chunk_index[i] = i;
   io->GetRandIndex(chunk_index.data(), io->total_chunks);
   unsigned long long trained_samples = 0;
-  RawChunk raw;  // reader=gpu: records + sample table of the current chunk
+  RawChunk raw[2];  // reader=gpu: records + sample table of the current chunk (and of the one being prefetched)
   const double t_train0 = now_s();
   {
-    // reader=gpu prefetch=1: the same ReadchunkRaw calls in the same order, one chunk ahead on a reader thread
-    std::unique_ptr<RawPrefetcher> ahead;
-    if (para->reader_gpu && para->prefetch && io->total_chunks > 1) ahead.reset(new RawPrefetcher(io, chunk_index));
+    // prefetch=1: the same Readchunk / ReadchunkRaw calls in the same order, one chunk ahead on a reader thread
+    std::unique_ptr<ChunkPrefetcher> ahead;
+    if (para->prefetch && io->total_chunks > 1) {
+      if (!para->reader_gpu) io->ensure_alt_buffers();
+      ahead.reset(new ChunkPrefetcher(chunk_index, [&](int chunk, int slot) {
+        return para->reader_gpu ? io->ReadchunkRaw(chunk, &raw[slot]) : io->Readchunk(chunk, slot);
+      }));
+    }
     for (unsigned int i = 0; i < io->total_chunks; ++i) {
-      RawChunk* cur = &raw;
-      const int n = ahead            ? ahead->next(&cur)
-                    : para->reader_gpu ? io->ReadchunkRaw(chunk_index[i], &raw)
+      int slot = 0;
+      const int n = ahead              ? ahead->next(&slot)
+                    : para->reader_gpu ? io->ReadchunkRaw(chunk_index[i], &raw[0])
                                        : io->Readchunk(chunk_index[i]);
       fprintf(io->fp_log, "Starting chunk %d of %d containing %d samples.\n", i + 1, io->total_chunks, n);
       fflush(io->fp_log);
       if (n > 0 && para->reader_gpu) {
-        const bp_raw_chunk c = as_abi(io, *cur);
+        const bp_raw_chunk c = as_abi(io, raw[slot]);
         if (bp_train_raw(trainer, &c) != BP_OK) die(io, "train failed");
-      } else if (n > 0 && bp_train(trainer, n, para->indata, para->targ) != BP_OK) {
+      } else if (n > 0 && bp_train(trainer, n, io->chunk_in(slot), io->chunk_targ(slot)) != BP_OK) {
         die(io, "train failed");
       }
       trained_samples += n;
     }
   }  // joins the reader thread before the Interface is used for the weight dump and the CV pass
+  io->free_raw(&raw[1]);
 
   printf("begin to write weights\n");
   if (bp_return_weights(trainer, para->weights, para->bias) != BP_OK) die(io, "returnWeights failed");
@@ -121,11 +127,11 @@ static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
     decw.append(dec.data(), n, rel_sent.data(), io->sample_frame_in_sent.data());
   };
   for (unsigned int i = 0; i < io->cv_total_chunks; ++i) {
-    const int n = para->reader_gpu ? io->Readchunk_cvRaw(i, &raw) : io->Readchunk_cv(i);
+    const int n = para->reader_gpu ? io->Readchunk_cvRaw(i, &raw[0]) : io->Readchunk_cv(i);
     printf("cur_chunk_samples=%d\n", n);
     if (n <= 0) continue;
     if (para->reader_gpu) {  // one upload serves the score and the decode output
-      const bp_raw_chunk c = as_abi(io, raw);
+      const bp_raw_chunk c = as_abi(io, raw[0]);
       float sq = 0.0f;
       if (fdec) dec.resize(static_cast<size_t>(n) * para->layersizes[io->numlayers - 1]);
       if (bp_crossvalid_raw(trainer, &c, &sq, fdec ? dec.data() : nullptr) != BP_OK) die(io, "CrossValid failed");
@@ -143,7 +149,7 @@ static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
     }
   }
   decw.close();
-  io->free_raw(&raw);
+  io->free_raw(&raw[0]);
   const float cvacc = squared_err / io->cv_total_samples;
   fprintf(io->fp_log, "CV over. squared error: %f\n", cvacc);
   fflush(io->fp_log);

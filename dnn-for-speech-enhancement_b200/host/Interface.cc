@@ -33,6 +33,23 @@ inline int be_int(const float* p) {
   return static_cast<int>(bswap32(u));
 }
 
+// Static split of [0, n) over the host threads (at most 16, at least `grain` items each); fn(begin, end).
+template <class Fn>
+void parallel_for(int n, int grain, Fn fn) {
+  const int hw = static_cast<int>(std::thread::hardware_concurrency());
+  const int t = std::max(1, std::min({hw > 0 ? hw : 1, 16, n / std::max(1, grain)}));
+  if (t == 1) {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(t - 1);
+  const int per = (n + t - 1) / t;
+  for (int k = 1; k < t; ++k) th.emplace_back([=, &fn] { fn(std::min(n, k * per), std::min(n, (k + 1) * per)); });
+  fn(0, std::min(n, per));
+  for (std::thread& x : th) x.join();
+}
+
 enum ArgKind { kStr, kInt, kFloat };
 struct ArgSpec {
   const char* key;
@@ -96,13 +113,10 @@ Interface::~Interface() {
   if (fp_targ) fclose(fp_targ);
   if (fp_out) fclose(fp_out);
   if (fp_log) fclose(fp_log);
-  auto release = [&](float* p) {
-    if (!p) return;
-    if (host_free) host_free(p);
-    else delete[] p;
-  };
-  release(para->indata);
-  release(para->targ);
+  free_floats(para->indata, pinned_in[0]);
+  free_floats(para->targ, pinned_targ[0]);
+  free_floats(alt_indata, pinned_in[1]);
+  free_floats(alt_targ, pinned_targ[1]);
   for (int i = 1; i < numlayers; ++i) {
     delete[] para->weights[i];
     delete[] para->bias[i];
@@ -347,20 +361,36 @@ void Interface::Initial(int argc, char** argv) {
   if (spliced + (use_nat ? para->fea_dim : 0) != para->layersizes[0])
     fatal("feadim times (+ 129 noise) context must be equal to layersizes[0]\n");
 
-  auto grab = [&](size_t n) -> float* {
-    if (host_alloc) {
-      if (float* p = static_cast<float*>(host_alloc(n * sizeof(float)))) return p;
-    }
-    host_free = nullptr;
-    return new float[n];
-  };
-  para->indata = grab(static_cast<size_t>(para->layersizes[0]) * para->traincache);
-  float* t = nullptr;
-  if (host_free) t = static_cast<float*>(host_alloc(sizeof(float) * para->layersizes[numlayers - 1] * (size_t)para->traincache));
-  para->targ = t ? t : new float[static_cast<size_t>(para->layersizes[numlayers - 1]) * para->traincache];
+  para->indata = alloc_floats(static_cast<size_t>(para->layersizes[0]) * para->traincache, &pinned_in[0]);
+  para->targ = alloc_floats(static_cast<size_t>(para->layersizes[numlayers - 1]) * para->traincache, &pinned_targ[0]);
   chunk_frame_st = new int[MAXCHUNK];
   cv_chunk_frame_st = new int[MAXCHUNK];
   fflush(fp_log);
+}
+
+// Chunk buffers: page-locked through the trainer's allocator when main() installed one (and it succeeds), else heap.
+float* Interface::alloc_floats(size_t n, bool* pinned) {
+  *pinned = false;
+  if (host_alloc && host_free) {
+    if (float* p = static_cast<float*>(host_alloc(n * sizeof(float)))) {
+      *pinned = true;
+      return p;
+    }
+  }
+  return new float[n];
+}
+
+void Interface::free_floats(float* p, bool pinned) {
+  if (!p) return;
+  if (pinned) host_free(p);
+  else delete[] p;
+}
+
+// Second chunk-buffer pair for the prefetching training loop (ChunkPrefetch.h); allocated on first use.
+void Interface::ensure_alt_buffers() {
+  if (alt_indata) return;
+  alt_indata = alloc_floats(static_cast<size_t>(para->layersizes[0]) * para->traincache, &pinned_in[1]);
+  alt_targ = alloc_floats(static_cast<size_t>(para->layersizes[numlayers - 1]) * para->traincache, &pinned_targ[1]);
 }
 
 // Interface::Writeweights — reference Interface.cc:411-465: MAT-v4, little-endian, weights then bias per layer.
@@ -526,7 +556,7 @@ void Interface::note_sample(int cur, const Seg& sg, int first, int j) {
 // byte-swap + (x-mean)*dVar, 11-frame splice, NAT block (mean of the segment's first six frames, /6.0f, summed left to
 // right), target frame j+targ_offset, rows scattered through a Fisher-Yates permutation (train) or in order (CV).
 int Interface::assemble(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples,
-                        int sent_end, bool shuffle) {
+                        int sent_end, bool shuffle, float* in_dst, float* targ_dst) {
   const int dim = para->fea_dim, ctx = para->fea_context, in_w = para->layersizes[0];
   const int out_w = para->layersizes[numlayers - 1];
   const int first = starts[chunk_index];
@@ -539,76 +569,102 @@ int Interface::assemble(int chunk_index, const int* starts, unsigned int n_chunk
   for (int i = 0; i < samples; ++i) order[i] = i;
   if (shuffle) GetRandIndex(order.data(), samples);
 
-  std::vector<float> rec;
-  int sent = 0;
+  // Both record blocks are fetched up front: the target block by a second thread while this one reads the features.
+  std::vector<float>&rec = scratch_rec, &trec = scratch_trec, &fea = scratch_fea;  // kept across chunks: no page faults
+  int sent = 0, tsent = 0;
+  std::thread targ_reader([&] { read_records(fp_targ, out_w, first, n_frames, &trec, &tsent); });
   read_records(fp_data, dim, first, n_frames, &rec, &sent);
-  // normalise in place: two fp32 operations, subtract then multiply (Interface.cc:745-746)
-  std::vector<float> fea(static_cast<size_t>(n_frames) * dim);
-  for (int f = 0; f < n_frames; ++f) {
-    const float* src = rec.data() + static_cast<size_t>(f) * (dim + 2) + 2;
-    float* dst = fea.data() + static_cast<size_t>(f) * dim;
-    for (int j = 0; j < dim; ++j) {
-      float v = be_float(src + j);
-      v -= mean[j];
-      v *= dVar[j];
-      dst[j] = v;
+  // normalise: two fp32 operations, subtract then multiply (Interface.cc:745-746).  Every element is computed exactly
+  // as in the serial loop; only the frames are dealt out to the host threads.
+  if (fea.size() < static_cast<size_t>(n_frames) * dim) fea.resize(static_cast<size_t>(n_frames) * dim);
+  parallel_for(n_frames, 256, [&](int f0, int f1) {
+    for (int f = f0; f < f1; ++f) {
+      const float* src = rec.data() + static_cast<size_t>(f) * (dim + 2) + 2;
+      float* dst = fea.data() + static_cast<size_t>(f) * dim;
+      for (int j = 0; j < dim; ++j) {
+        float v = be_float(src + j);
+        v -= mean[j];
+        v *= dVar[j];
+        dst[j] = v;
+      }
     }
-  }
+  });
 
   const std::vector<Seg> segs = segments(first, n_frames, sent);
 
+  // Plan: sample `cur` = window j of segment sample_segi[cur], in file order (the order the reference's loops visit
+  // them, Interface.cc:755-787); NAT vector per segment (mean of its first six frames, /6.0f, summed left to right;
+  // the reference reads six frames even when the segment is shorter, frames past the block count as 0).
   sample_sent.assign(samples, 0);
   sample_frame_in_sent.assign(samples, 0);
+  std::vector<int> sample_segi(samples), sample_j(samples);
   int cur = 0;
-  for (const Seg& sg : segs) {
-    float nat[4096];
-    std::vector<float> nat_big;
-    float* natp = nat;
-    if (use_nat && sg.len >= ctx) {
-      if (dim > 4096) { nat_big.resize(dim); natp = nat_big.data(); }
-      // the first six frames of the segment; the reference reads them even when the segment is shorter than six
-      for (int k = 0; k < dim; ++k) {
-        float s6 = 0.0f;
-        bool firstterm = true;
-        for (int q = 0; q < 6; ++q) {
-          const int fr = sg.begin + q;
-          const float v = fr < n_frames ? fea[static_cast<size_t>(fr) * dim + k] : 0.0f;
-          s6 = firstterm ? v : s6 + v;
-          firstterm = false;
-        }
-        natp[k] = s6 / 6.0f;
-      }
-    }
+  for (size_t si = 0; si < segs.size(); ++si) {
+    const Seg& sg = segs[si];
     for (int j = 0; j + ctx <= sg.len && cur < samples; ++j, ++cur) {
       note_sample(cur, sg, first, j);
-      float* row = para->indata + static_cast<size_t>(order[cur]) * in_w;
-      std::memcpy(row, fea.data() + static_cast<size_t>(sg.begin + j) * dim, sizeof(float) * dim * ctx);
-      if (use_nat) std::memcpy(row + dim * ctx, natp, sizeof(float) * dim);
+      sample_segi[cur] = static_cast<int>(si);
+      sample_j[cur] = j;
     }
   }
   const int produced = cur;
+  std::vector<float> nat;
+  if (use_nat) {
+    nat.assign(segs.size() * static_cast<size_t>(dim), 0.0f);
+    parallel_for(static_cast<int>(segs.size()), 4, [&](int s0, int s1) {
+      for (int si = s0; si < s1; ++si) {
+        const Seg& sg = segs[si];
+        if (sg.len < ctx) continue;
+        float* natp = nat.data() + static_cast<size_t>(si) * dim;
+        for (int k = 0; k < dim; ++k) {
+          float s6 = 0.0f;
+          for (int q = 0; q < 6; ++q) {
+            const int fr = sg.begin + q;
+            const float v = fr < n_frames ? fea[static_cast<size_t>(fr) * dim + k] : 0.0f;
+            s6 = q == 0 ? v : s6 + v;
+          }
+          natp[k] = s6 / 6.0f;
+        }
+      }
+    });
+  }
+  // Scatter the input rows through the permutation: ~12 KB written per sample, the bulk of the host reader's work.
+  parallel_for(produced, 64, [&](int c0, int c1) {
+    for (int c = c0; c < c1; ++c) {
+      const Seg& sg = segs[sample_segi[c]];
+      float* row = in_dst + static_cast<size_t>(order[c]) * in_w;
+      std::memcpy(row, fea.data() + static_cast<size_t>(sg.begin + sample_j[c]) * dim, sizeof(float) * dim * ctx);
+      if (use_nat)
+        std::memcpy(row + dim * ctx, nat.data() + static_cast<size_t>(sample_segi[c]) * dim, sizeof(float) * dim);
+    }
+  });
 
   // targets: frame j + targ_offset of each segment, not normalised (Interface.cc:815-816, 844-846)
-  int tsent = 0;
-  read_records(fp_targ, out_w, first, n_frames, &rec, &tsent);
-  cur = 0;
-  for (const Seg& sg : segs) {
-    for (int j = 0; j + ctx <= sg.len && cur < samples; ++j, ++cur) {
-      const float* src = rec.data() + static_cast<size_t>(sg.begin + j + para->targ_offset) * (out_w + 2) + 2;
-      float* row = para->targ + static_cast<size_t>(order[cur]) * out_w;
+  targ_reader.join();
+  parallel_for(produced, 256, [&](int c0, int c1) {
+    for (int c = c0; c < c1; ++c) {
+      const Seg& sg = segs[sample_segi[c]];
+      const float* src =
+          trec.data() + static_cast<size_t>(sg.begin + sample_j[c] + para->targ_offset) * (out_w + 2) + 2;
+      float* row = targ_dst + static_cast<size_t>(order[c]) * out_w;
       for (int k = 0; k < out_w; ++k) row[k] = be_float(src + k);
     }
-  }
+  });
   (void)produced;
   return samples;
 }
 
-int Interface::Readchunk(int index) {
-  return assemble(index, chunk_frame_st, total_chunks, total_samples, train_r.en, true);
+int Interface::Readchunk(int index) { return Readchunk(index, 0); }
+
+int Interface::Readchunk(int index, int slot) {
+  if (slot != 0) ensure_alt_buffers();
+  return assemble(index, chunk_frame_st, total_chunks, total_samples, train_r.en, true, chunk_in(slot),
+                  chunk_targ(slot));
 }
 
 int Interface::Readchunk_cv(int index) {
-  return assemble(index, cv_chunk_frame_st, cv_total_chunks, cv_total_samples, cv_r.en, false);
+  return assemble(index, cv_chunk_frame_st, cv_total_chunks, cv_total_samples, cv_r.en, false, para->indata,
+                  para->targ);
 }
 
 // Device-reader variant of `assemble`: same chunk geometry, same shuffle (one GetRandIndex call per

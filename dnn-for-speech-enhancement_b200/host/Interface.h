@@ -60,7 +60,7 @@ struct WorkPara {
   // extensions
   int nat = -1;            // -1 = infer from layersizes[0]
   int reader_gpu = 0;      // reader=gpu: splice / normalise / shuffle on the device (default host, as the reference)
-  int prefetch = 1;        // reader=gpu: the training chunks are read one ahead on a second thread (RawPrefetch.h)
+  int prefetch = 1;        // the training chunks are read one ahead on a second thread (ChunkPrefetch.h)
   int activation = 0;      // 0 relu, 1 sigmoid
   unsigned long long seed = 0x5eed5eedULL;
   char decode_FN[MAXLINE] = "";
@@ -105,7 +105,13 @@ class Interface {
   void get_pfile_info();
   void get_chunk_info(char* range);
   void get_chunk_info_cv(char* range);
-  int Readchunk(int index);
+  int Readchunk(int index);  // into para->indata / para->targ, as the reference
+  // Prefetching training loop (ChunkPrefetch.h): the same chunk into buffer pair `slot` (0 = para->indata/targ,
+  // 1 = a second pair allocated on first use).
+  int Readchunk(int index, int slot);
+  float* chunk_in(int slot) const { return slot == 0 ? para->indata : alt_indata; }
+  float* chunk_targ(int slot) const { return slot == 0 ? para->targ : alt_targ; }
+  void ensure_alt_buffers();
   int Readchunk_cv(int index);
   // reader=gpu: same chunks, same shuffle, but samples are assembled on the device (bp_upload_raw_chunk)
   int ReadchunkRaw(int index, RawChunk* rc);
@@ -161,7 +167,12 @@ class Interface {
   Range parse_range(const char* range, const char* what);
   void plan_chunks(const Range& r, int* starts, unsigned int* n_chunks, unsigned int* n_samples);
   int assemble(int chunk_index, const int* starts, unsigned int n_chunks, unsigned int n_samples, int sent_end,
-               bool shuffle);
+               bool shuffle, float* in_dst, float* targ_dst);
+  float* alloc_floats(size_t n, bool* pinned);
+  void free_floats(float* p, bool pinned);
+  float* alt_indata = nullptr;
+  float* alt_targ = nullptr;
+  bool pinned_in[2] = {false, false}, pinned_targ[2] = {false, false};
   void read_records(FILE* fp, int dim, long first_frame, int n_frames, std::vector<float>* rec, int* first_sent);
   void get_uint(const char* hdr, const char* argname, unsigned int* val);
   void read_tail(FILE* fp, long file_offset, unsigned int sentnum, int* out);
@@ -171,6 +182,7 @@ class Interface {
   FILE* fp_targ = nullptr;
   FILE* fp_out = nullptr;
   std::vector<float> mean, dVar;
+  std::vector<float> scratch_rec, scratch_trec, scratch_fea;  // host assembler's record / normalised-frame buffers
   Range train_r, cv_r;
   bool use_nat = true;
 };

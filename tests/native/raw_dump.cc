@@ -3,7 +3,7 @@
 // Interface::ReadchunkRaw / Readchunk_cvRaw plan.  tests/test_raw_reader.py replays the tables (numpy on CPU, the
 // splice kernel on the GPU) and compares the rows bit for bit with the reference reader's golden chunks.
 //   raw_dump <out.bin> key=value ...        (same argv keys as BPtrain; prefetch=1, the default, reads the training
-//                                            chunks through the RawPrefetcher thread exactly as BPtrain does)
+//                                            chunks through the ChunkPrefetcher thread exactly as BPtrain does)
 // out.bin: int32 fea_dim, ctx, targ_offset, nat, out_dim; float mean[fea_dim], inv_std[fea_dim];
 //          int32 n_train_chunks; per chunk: int32 id, n_records, n_samples; fea words; targ words;
 //          int32 sample_frame[n], sample_seg[n], sample_row[n];   int32 n_cv_chunks; the same.
@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "Interface.h"
-#include "RawPrefetch.h"
+#include "ChunkPrefetch.h"
 
 static void dump(FILE* f, int id, const RawChunk& rc, int dim, int out) {
   fwrite(&id, 4, 1, f);
@@ -47,13 +47,18 @@ int main(int argc, char** argv) {
   io->GetRandIndex(order.data(), n);
   fwrite(&n, 4, 1, f);
   if (p->prefetch && n > 1) {
-    RawPrefetcher ahead(io, order);
-    RawChunk* cur = nullptr;
-    for (int i = 0; i < n; ++i) {
-      if (ahead.next(&cur) < 0) return 3;
-      dump(f, order[i], *cur, p->fea_dim, out);
+    RawChunk slots[2];
+    {
+      ChunkPrefetcher ahead(order, [&](int chunk, int slot) { return io->ReadchunkRaw(chunk, &slots[slot]); });
+      int slot = 0;
+      for (int i = 0; i < n; ++i) {
+        if (ahead.next(&slot) < 0) return 3;
+        dump(f, order[i], slots[slot], p->fea_dim, out);
+      }
+      if (ahead.next(&slot) != -1) return 3;
     }
-    if (ahead.next(&cur) != -1) return 3;
+    io->free_raw(&slots[0]);
+    io->free_raw(&slots[1]);
   } else {
     for (int i = 0; i < n; ++i) {
       io->ReadchunkRaw(order[i], &rc);

@@ -18,7 +18,7 @@ EXE = os.path.join(PKG, "bin", "reader_dump")
 
 
 def _build():
-    if not os.path.exists(EXE):
+    if not os.path.exists(EXE) or not os.path.exists(EXE.replace("reader_dump", "prefetch_dump")):
         subprocess.check_call(["make", "-C", os.path.join(PKG, "csrc"), "-s"])
         subprocess.check_call(["make", "-C", os.path.join(PKG, "host"), "-s"])
 
@@ -38,6 +38,22 @@ def test_reader_bit_exact_vs_reference_golden(name):
         assert kind == int(gold[f"c{i}_kind"]) and cid == int(gold[f"c{i}_id"])
         assert np.array_equal(x.view(np.uint32), gold[f"c{i}_x"].view(np.uint32)), f"chunk {i} inputs differ"
         assert np.array_equal(t.view(np.uint32), gold[f"c{i}_t"].view(np.uint32)), f"chunk {i} targets differ"
+
+
+@pytest.mark.parametrize("traincache", [7, 16, 40, 1000])
+def test_host_reader_prefetch_thread_equals_serial_loop(traincache):
+    """BPtrain prefetch=1 reads the host reader's chunks one ahead on a second thread, alternating between two buffer
+    pairs (host/ChunkPrefetch.h, Interface::Readchunk(index, slot)): every row of every chunk must be byte-identical
+    with the serial loop's, whose rows are pinned against the reference reader above."""
+    _build()
+    case = dict(CASES["129"], traincache=traincache)
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, case)
+        a, b = os.path.join(d, "serial.bin"), os.path.join(d, "prefetch.bin")
+        subprocess.check_call([EXE, a] + reader_args(d, case), cwd=d, stdout=subprocess.DEVNULL)
+        subprocess.check_call([EXE.replace("reader_dump", "prefetch_dump"), b] + reader_args(d, case), cwd=d,
+                              stdout=subprocess.DEVNULL)
+        assert open(a, "rb").read() == open(b, "rb").read()
 
 
 def test_reader_no_nat_257_matches_numpy_restatement():
