@@ -396,6 +396,29 @@ def main():
         dt = max_over_ranks(dt)
         e2e = {"value": n_calls * gb / dt, "unit": "frames/s", "h2d_bytes_per_step": 4 * lb * sizes[0] * world,
                "d2h_bytes_per_step": 4 * lb * sizes[-1] * world, "api": "bp_forward() host in / host out"}
+        # The same decode fed the way BPtrain reader=gpu feeds it: raw big-endian Pfile records from
+        # pinned memory, 11-frame splice + normalisation on the device — 1/11 of the H2D bytes of the spliced rows.
+        try:
+            fea_dim, ctx = 257, 11
+            if sizes[0] == fea_dim * ctx:
+                n_rec = lb + ctx - 1
+                prec = bp.PinnedArray((n_rec, fea_dim + 2))
+                words = np.random.default_rng(7 + rank).standard_normal((n_rec, fea_dim + 2), dtype=np.float32)
+                prec.array[:] = words.view(np.uint32).byteswap().view(np.float32)   # records are big-endian on disk
+                raw = bp.RawChunk(fea_dim, ctx, ctx // 2, 0, prec.array, None, np.zeros(fea_dim, np.float32),
+                                  np.ones(fea_dim, np.float32), np.arange(lb, dtype=np.int32))
+                g.decode_raw(raw)
+                barrier()
+                t0 = time.perf_counter()
+                for c in range(n_calls):
+                    out = g.decode_raw(raw)
+                dt_raw = max_over_ranks(time.perf_counter() - t0)
+                e2e["raw_reader"] = {"value": n_calls * gb / dt_raw, "unit": "frames/s",
+                                     "h2d_bytes_per_step": 4 * n_rec * (fea_dim + 2) * world,
+                                     "d2h_bytes_per_step": 4 * lb * sizes[-1] * world,
+                                     "api": "bp_crossvalid_raw() raw Pfile records in / enhanced frames out"}
+        except Exception as e:   # an extra measurement must not hide the bench line
+            e2e["raw_reader"] = {"error": str(e)}
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:

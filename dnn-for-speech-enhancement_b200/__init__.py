@@ -300,6 +300,15 @@ class BP_GPU:
         _check(load_library().bp_crossvalid_raw(self._h, C.byref(rc), C.byref(sq), _ptr(out)), "bp_crossvalid_raw")
         return float(sq.value), out
 
+    def decode_raw(self, raw: "RawChunk") -> np.ndarray:
+        """Decode straight from raw Pfile records (no targets needed): bp_crossvalid_raw with a null score pointer —
+        the records travel as they lie in the file (1/11 of the spliced rows' bytes), the rows are assembled on the
+        device, the enhanced frames come back."""
+        rc, _keep = self._raw_chunk(raw)
+        out = np.empty((len(raw.sample_frame), self.layersizes[-1]), dtype=np.float32)
+        _check(load_library().bp_crossvalid_raw(self._h, C.byref(rc), None, _ptr(out)), "bp_crossvalid_raw")
+        return out
+
     def download_chunk(self, first_row: int, n_rows: int, want_targ: bool = True):
         x = np.empty((n_rows, self.layersizes[0]), dtype=np.float32)
         t = np.empty((n_rows, self.layersizes[-1]), dtype=np.float32) if want_targ else None
