@@ -777,7 +777,9 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
 }
 
 // ------------------------------------------------------------------------------------------------ chunk upload
-int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
+// wait_host = false: the caller queues the chunk's bunches first and calls rank_wait_uploaded() before it returns to
+// its own caller, so the kernel launches are issued while the DMA runs instead of after it.
+int rank_upload(Rank* r, int n_frames, const float* in, const float* targ, bool wait_host = true) {
   if (n_frames <= 0 || !in) return fail(BP_EINVAL, "upload: n_frames=%d in=%p", n_frames, (const void*)in);
   CU_TRY(cudaSetDevice(r->cfg.device));
   const int nb = r->cur ^ 1;
@@ -801,7 +803,14 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ) {
   r->cur = nb;
   CU_TRY(cudaStreamWaitEvent(r->compute, r->passes == 3 ? c.split_done : c.uploaded, 0));
   // The caller may overwrite its buffers as soon as we return (BP_GPU::train semantics): wait for the DMA only.
-  CU_TRY(cudaEventSynchronize(c.uploaded));
+  if (wait_host) CU_TRY(cudaEventSynchronize(c.uploaded));
+  return BP_OK;
+}
+
+// Host wait for the H2D copies of the current chunk (the one rank_upload / rank_upload_raw filled last).
+int rank_wait_uploaded(Rank* r) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  CU_TRY(cudaEventSynchronize(r->chunk[r->cur].uploaded));
   return BP_OK;
 }
 
@@ -818,7 +827,7 @@ int grow_dev(Rank* r, T** ptr, size_t* cap, size_t need) {
   return BP_OK;
 }
 
-int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows) {
+int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows, bool wait_host = true) {
   CU_TRY(cudaSetDevice(r->cfg.device));
   // all_rows: this rank assembles every sample (cross-validation / decode run on one device, BP_GPU.cu:440-441)
   const int G = all_rows ? 1 : r->cfg.world_size, B = r->cfg.bunchsize, lb = r->local_bunch;
@@ -886,7 +895,7 @@ int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows) {
   c.has_targ = targ_words != 0;
   r->cur = nbuf;
   CU_TRY(cudaStreamWaitEvent(r->compute, c.split_done, 0));
-  CU_TRY(cudaEventSynchronize(c.uploaded));  // the caller may reuse its buffers (BP_GPU::train semantics)
+  if (wait_host) CU_TRY(cudaEventSynchronize(c.uploaded));  // the caller may reuse its buffers (BP_GPU::train semantics)
   return BP_OK;
 }
 
@@ -1688,6 +1697,16 @@ int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
   const int nb = rc->n_samples / B;
   if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
+  if (h->ranks.size() == 1) {  // queue the bunches while the records are still in flight; wait for the DMA last
+    BP_TRY(check_raw_chunk(h, rc));
+    Rank* r = h->ranks[0];
+    BP_TRY(rank_upload_raw(r, rc, false, false));
+    const int rc_train = rank_train_resident(r, 0, nb);
+    const std::string keep = g_err;
+    const int rc_wait = rank_wait_uploaded(r);  // the caller may reuse its buffers only after this
+    if (rc_train != BP_OK) g_err = keep;
+    return rc_train != BP_OK ? rc_train : rc_wait;
+  }
   BP_TRY(bp_upload_raw_chunk(h, rc));
   return bp_train_resident(h, 0, nb);
 }
@@ -1727,6 +1746,14 @@ int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
   if (n_frames % per_call_bunch)
     printf("this bunch has only %d samples and is ignored.\n", n_frames % per_call_bunch);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
+  if (h->ranks.size() == 1) {  // queue the bunches while the chunk is still in flight; wait for the DMA last
+    BP_TRY(rank_upload(r0, n_frames, in, targ, false));
+    const int rc_train = rank_train_resident(r0, 0, nb);
+    const std::string keep = g_err;
+    const int rc_wait = rank_wait_uploaded(r0);  // the caller may overwrite in / targ only after this
+    if (rc_train != BP_OK) g_err = keep;
+    return rc_train != BP_OK ? rc_train : rc_wait;
+  }
   BP_TRY(bp_upload_chunk(h, n_frames, in, targ));
   return bp_train_resident(h, 0, nb);
 }
