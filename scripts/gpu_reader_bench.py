@@ -27,21 +27,21 @@ def main():
         frames = sum(f.shape[0] for f in feas)
         print(f"corpus: {n_sent} sentences, {frames} frames, generated in {time.time() - t0:.1f} s", flush=True)
         cv0 = n_sent - 20
-        for tag in ("host", "gpu", "host", "gpu"):
+        for tag, pf in (("host", 1), ("gpu", 1), ("host", 0), ("gpu", 0), ("host", 1), ("gpu", 1)):
             args = [f"fea_file={d}/fea.pfile", f"norm_file={d}/fea.norm", f"targ_file={d}/targ.pfile",
                     f"outwts_file={d}/{tag}.wts", f"log_file={d}/{tag}.log", "initwts_file=",
                     f"train_sent_range=0-{cv0 - 1}", f"cv_sent_range={cv0}-{n_sent - 1}", "fea_dim=257",
                     "fea_context=11", "targ_offset=5", "traincache=102400", "bunchsize=1024",
                     "layersizes=" + ",".join(map(str, LS)), "gpu_used=1", "init_randem_seed=7", "momentum=0.9",
                     "weightcost=0", "lrate=0.1", "dropoutflag=0", "visible_omit=0", "hid_omit=0", "nat=0",
-                    f"reader={tag}"]
+                    f"reader={tag}", f"prefetch={pf}"]
             t0 = time.time()
             o = subprocess.run([EXE] + args, cwd=d, capture_output=True, text=True, timeout=900)
             wall = time.time() - t0
             log = open(f"{d}/{tag}.log").read()
             thr = re.search(r"Training throughput: (\d+) frames/sec", log)
             cv = re.search(r"CV over\. squared error: (\S+)", log)
-            print(f"reader={tag}: exit {o.returncode}, wall {wall:.2f} s, training pass "
+            print(f"reader={tag} prefetch={pf}: exit {o.returncode}, wall {wall:.2f} s, training pass "
                   f"{thr.group(1) if thr else '?'} frames/s, CV {cv.group(1) if cv else '?'}", flush=True)
         same = open(f"{d}/host.wts", "rb").read() == open(f"{d}/gpu.wts", "rb").read()
         print("weights identical between readers:", same)
