@@ -720,6 +720,34 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaMemsetAsync(r->w, 0, off * 4, r->compute));
     CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
     CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
+    if (const char* e = getenv("BP_L2_PERSIST")) {
+      // Experiment (off by default, not yet run on a GPU): pin the weight arena in L2.  Inside a bunch the forward and
+      // dX products behave as if their operands were cold (ncu: ~25 MB of DRAM reads per hidden-layer product, the
+      // kernel neither DRAM- nor L2-bandwidth bound but ~1.7x slower than with a warm L2) because the update streams
+      // ~5x the arena through L2 between two uses of the weights.  BP_L2_PERSIST=<MB> sets aside that much L2 for
+      // persisting lines (capped by the device limit) and gives every kernel of the compute and side streams an
+      // access-policy window over the weight arena: hits persist, everything else keeps the normal policy.
+      const size_t want_mb = (size_t)std::max(0, atoi(e));
+      cudaDeviceProp prop{};
+      if (want_mb > 0 && cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t carve = std::min(want_mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+        const size_t window = std::min((size_t)off * 4, (size_t)prop.accessPolicyMaxWindowSize);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess && window > 0) {
+          cudaStreamAttrValue v{};
+          v.accessPolicyWindow.base_ptr = r->w;
+          v.accessPolicyWindow.num_bytes = window;
+          v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+          v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+          for (cudaStream_t st : {r->compute, r->side})
+            if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+          if (getenv("BP_VERBOSE"))
+            fprintf(stderr, "libbpgpu: L2 persistence: %zu MB set aside (device max %d MB), window %zu MB, hit ratio %.2f\n",
+                    carve >> 20, prop.persistingL2CacheMaxSize >> 20, window >> 20, v.accessPolicyWindow.hitRatio);
+        }
+        cudaGetLastError();
+      }
+    }
     CU_TRY(cudaMalloc(&r->sqerr_dev, sizeof(double)));
     CU_TRY(cudaMalloc(&r->splitk_ws, sizeof(float) * kMaxSplits * (size_t)cfg->bunchsize * r->layer[r->L].ldN));
 
