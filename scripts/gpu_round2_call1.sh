@@ -1,6 +1,6 @@
 # First GPU call of round 2 (1 GPU, ~12 min of box time).  Round 1 ran out of GPU minutes before the last host-side and
 # gated changes could be run on a B200; this call proves them in the order "what the round-end driver runs" first:
-#   1. GPU test suite (includes tests/test_zz_decode_raw.py, new since the last GPU call)
+#   1. GPU test suite (includes tests/test_zz_late_round1.py, new since the last GPU call)
 #   2. smoke()
 #   3. default bench line (C2)                  -> gpurun_out/r2_bench_C2.json
 #   4. edge cases + fused-update bit parity     -> promote scripts/gpu_edge_cases.py cases into tests/ if green
