@@ -10,6 +10,7 @@
 # Outputs:
 #   oracle/_ref/BPtrain_ref    the reference CLI (HEAD semantics: ReLU, NAT block with the literal 129)
 #   oracle/_ref/ref_reader_dump  tests/native/reader_dump.cc linked against the reference's Interface.o (host only)
+#   oracle/_ref/ref_weights_dump  tests/native/weights_dump.cc linked against the reference's Interface.o (host only)
 #   oracle/_ref/ref_harness    oracle/ref_harness.cc (ours) linked against the reference's BP_GPU.o / DevFunc.o:
 #                              drives class BP_GPU directly on binary blobs (no Pfile plumbing) and times train().
 set -euo pipefail
@@ -33,4 +34,6 @@ $NVCC $ARCH -O2 -w -I"$REF" "$HERE/ref_harness.cc" "$TMP/BP_GPU.o" "$TMP/DevFunc
 # the reference's host-only reader (Interface.cc) behind tests/native/reader_dump.cc: runs without a GPU
 g++ -O2 -w -I/usr/local/cuda/include -I"$REF" "$HERE/../tests/native/reader_dump.cc" "$TMP/Interface.o" \
       -o "$OUT/ref_reader_dump"
+g++ -O2 -w -I/usr/local/cuda/include -I"$REF" "$HERE/../tests/native/weights_dump.cc" "$TMP/Interface.o" \
+      -o "$OUT/ref_weights_dump"
 echo "built: $(ls "$OUT")"
