@@ -40,21 +40,23 @@ def test_reader_equals_live_reference_reader(seed):
     case = random_case(seed)
     with tempfile.TemporaryDirectory() as d:
         make_inputs(d, case)
-        args = reader_args(d, case)
+        args = [a for a in reader_args(d, case) if not a.startswith("log_file=")]
         out = {}
         for name, exe in (("ours", os.path.join(BIN, "reader_dump")), ("prefetch", os.path.join(BIN, "prefetch_dump")),
                           ("raw", os.path.join(BIN, "raw_dump"))):
-            subprocess.run([exe, os.path.join(d, name + ".bin")] + args, cwd=d, stdout=subprocess.DEVNULL, check=True,
-                           timeout=60)
+            subprocess.run([exe, os.path.join(d, name + ".bin")] + args + [f"log_file={d}/{name}.log"], cwd=d,
+                           stdout=subprocess.DEVNULL, check=True, timeout=60)
             out[name] = open(os.path.join(d, name + ".bin"), "rb").read()
         try:
-            subprocess.run([REF, os.path.join(d, "ref.bin")] + args, cwd=d, stdout=subprocess.DEVNULL, check=True,
-                           timeout=6)
+            subprocess.run([REF, os.path.join(d, "ref.bin")] + args + [f"log_file={d}/ref.log"], cwd=d,
+                           stdout=subprocess.DEVNULL, check=True, timeout=6)
         except subprocess.TimeoutExpired:
             assert seed in (3, 47), "the reference reader hangs on a case it used to finish"
             return   # the reference's planner spins; ours terminated above
         ref = open(os.path.join(d, "ref.bin"), "rb").read()
         assert out["ours"] == ref, "serial reader differs from the reference reader"
+        # the log (parameter echo, pfile / chunk / cv-chunk summaries) is the reference's, line for line
+        assert open(f"{d}/ours.log").read().replace("ours.log", "ref.log") == open(f"{d}/ref.log").read()
         assert out["prefetch"] == ref, "prefetching reader differs from the reference reader"
         # device reader: the planner's tables, replayed by the numpy restatement of the splice kernel
         h, raw_chunks = parse_raw_dump(os.path.join(d, "raw.bin"))

@@ -25,10 +25,14 @@ CASE = dict(dim=129, out=129, ctx=11, off=5, nat=1, seed=1, lens=[30, 20, 15], t
             rseed=7, hidden=5)
 
 
+LOGS = {}   # log text of the last run per side, with the side's file names neutralised
+
+
 def _run(exe, d, tag, ls, extra):
     args = [a for a in reader_args(d, CASE) if not a.startswith(("layersizes=", "outwts_file=", "log_file="))]
     args += ["layersizes=" + ",".join(map(str, ls)), f"outwts_file={d}/{tag}.wts", f"log_file={d}/{tag}.log"] + extra
     subprocess.run([exe, f"{d}/{tag}.bin"] + args, cwd=d, stdout=subprocess.DEVNULL, check=True, timeout=60)
+    LOGS[tag] = open(f"{d}/{tag}.log").read().replace(f"{d}/{tag}.", f"{d}/X.")
     return open(f"{d}/{tag}.bin", "rb").read(), open(f"{d}/{tag}.wts", "rb").read()
 
 
@@ -52,6 +56,7 @@ def test_random_init_and_wts_bytes_equal_reference(seed, ls, rng):
     assert len(ref_bin) == 4 * sum((ls[i - 1] + 1) * ls[i] for i in range(1, len(ls)))
     assert our_bin == ref_bin, "initial weights differ from the reference's"
     assert our_wts == ref_wts, ".wts bytes differ from the reference's"
+    assert LOGS["ours"] == LOGS["ref"] and "Saving weights to file..." in LOGS["ours"], "log lines differ"
 
 
 def test_wts_files_load_identically_on_both_sides():
