@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
     lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
+    lib.bp_decode_raw_submit.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp]
+    lib.bp_decode_raw_wait.argtypes = [C.c_void_p]
     lib.bp_crossvalid_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp, _fp]
     lib.bp_download_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp]
     lib.bp_host_alloc.argtypes = [C.c_size_t]
@@ -308,6 +310,18 @@ class BP_GPU:
         out = np.empty((len(raw.sample_frame), self.layersizes[-1]), dtype=np.float32)
         _check(load_library().bp_crossvalid_raw(self._h, C.byref(rc), None, _ptr(out)), "bp_crossvalid_raw")
         return out
+
+    def decode_raw_submit(self, raw: "RawChunk", out: np.ndarray) -> None:
+        """Pipelined decode (bp_decode_raw_submit): queue the chunk and return; `out` (float32, n_samples x
+        layersizes[-1], ideally a PinnedArray's array) holds the enhanced frames after the matching decode_raw_wait().
+        At most two chunks in flight."""
+        if out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or out.size < len(raw.sample_frame) * self.layersizes[-1]:
+            raise ValueError("decode_raw_submit: out must be C-contiguous float32 with n_samples x layersizes[-1] elements")
+        rc, _keep = self._raw_chunk(raw)
+        _check(load_library().bp_decode_raw_submit(self._h, C.byref(rc), _ptr(out)), "bp_decode_raw_submit")
+
+    def decode_raw_wait(self) -> None:
+        _check(load_library().bp_decode_raw_wait(self._h), "bp_decode_raw_wait")
 
     def download_chunk(self, first_row: int, n_rows: int, want_targ: bool = True):
         x = np.empty((n_rows, self.layersizes[0]), dtype=np.float32)

@@ -479,6 +479,16 @@ struct Rank {
   float* out_dev = nullptr;
   long long out_cap_rows = 0;
   double* sqerr_dev = nullptr;
+  // pipelined decode (bp_decode_raw_submit / _wait): two output slots, results copied out on their own stream so that
+  // the D2H of chunk k runs beside the forward pass of chunk k+1
+  struct DecodeSlot {
+    float* out_dev = nullptr;
+    long long cap_rows = 0;
+    cudaEvent_t fwd_done = nullptr, out_done = nullptr;
+  };
+  DecodeSlot dec[2];
+  int dec_head = 0, dec_inflight = 0;
+  cudaStream_t d2h = nullptr;
   // device staging of a raw chunk (bp_upload_raw_chunk): Pfile records, sample table, norm vectors
   uint32_t* raw_fea = nullptr;
   uint32_t* raw_targ = nullptr;
@@ -594,7 +604,12 @@ int rank_destroy(Rank* r) {
     cudaFree(r->loss_dev[i]);
     if (r->loss_done[i]) cudaEventDestroy(r->loss_done[i]);
   }
-  for (auto s : {r->compute, r->copy, r->comm_stream, r->side})
+  for (auto& ds : r->dec) {
+    cudaFree(ds.out_dev);
+    if (ds.fwd_done) cudaEventDestroy(ds.fwd_done);
+    if (ds.out_done) cudaEventDestroy(ds.out_done);
+  }
+  for (auto s : {r->compute, r->copy, r->comm_stream, r->side, r->d2h})
     if (s) cudaStreamDestroy(s);
   delete r;
   return BP_OK;
@@ -1478,6 +1493,52 @@ int rank_forward_resident(Rank* r, int first_frame, int n_frames, float* out_hos
   return BP_OK;
 }
 
+// Pipelined decode of raw chunks: queue "records -> rows (splice kernel) -> forward pass -> D2H into out_host" and
+// return once the records have left the caller's buffers; at most two chunks in flight.  The chunk buffers are
+// double-buffered already (upload of chunk k+1 beside the forward pass of chunk k); what this adds is a second output
+// slot and a D2H stream, so that no stage of chunk k+1 waits for the host to have collected chunk k.
+int rank_decode_submit(Rank* r, const bp_raw_chunk* rc, float* out_host) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  if (r->dec_inflight >= 2)
+    return fail(BP_EINVAL, "bp_decode_raw_submit: two chunks already in flight, call bp_decode_raw_wait first");
+  Rank::DecodeSlot& ds = r->dec[r->dec_head];
+  const int n = rc->n_samples, no = r->Nout();
+  if (!r->d2h) CU_TRY(cudaStreamCreateWithFlags(&r->d2h, cudaStreamNonBlocking));
+  if (!ds.fwd_done) CU_TRY(cudaEventCreateWithFlags(&ds.fwd_done, cudaEventDisableTiming));
+  if (!ds.out_done) CU_TRY(cudaEventCreateWithFlags(&ds.out_done, cudaEventDisableTiming));
+  if (n > ds.cap_rows) {  // the slot is idle: its previous chunk has been waited for
+    if (ds.out_dev) CU_TRY(cudaFree(ds.out_dev));
+    ds.out_dev = nullptr;
+    ds.cap_rows = 0;
+    CU_TRY(cudaMalloc(&ds.out_dev, size_t(n) * no * 4));
+    ds.cap_rows = n;
+  }
+  BP_TRY(rank_upload_raw(r, rc, true));  // returns when the records are on the device; `compute` waits for the rows
+  ChunkBuf& c = r->chunk[r->cur];
+  const int B = r->cfg.bunchsize;
+  for (int i = 0; i < n; i += B)
+    BP_TRY(forward_rows(r, c, i, std::min(B, n - i), false, ds.out_dev + (long long)i * no, no, nullptr));
+  CU_TRY(cudaEventRecord(c.consumed, r->compute));
+  c.consumed_valid = true;
+  CU_TRY(cudaEventRecord(ds.fwd_done, r->compute));
+  CU_TRY(cudaStreamWaitEvent(r->d2h, ds.fwd_done, 0));
+  CU_TRY(cudaMemcpyAsync(out_host, ds.out_dev, size_t(n) * no * 4, cudaMemcpyDeviceToHost, r->d2h));
+  CU_TRY(cudaEventRecord(ds.out_done, r->d2h));
+  r->dec_head ^= 1;
+  r->dec_inflight++;
+  return BP_OK;
+}
+
+// Host wait for the oldest chunk in flight: its enhanced frames are complete in the `out` given at submit time.
+int rank_decode_wait(Rank* r) {
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  if (r->dec_inflight <= 0) return fail(BP_EINVAL, "bp_decode_raw_wait: no chunk in flight");
+  const int oldest = (r->dec_head + 2 - r->dec_inflight) & 1;
+  CU_TRY(cudaEventSynchronize(r->dec[oldest].out_done));
+  r->dec_inflight--;
+  return BP_OK;
+}
+
 int rank_return_weights(Rank* r, float* const* weights, float* const* bias) {
   CU_TRY(cudaSetDevice(r->cfg.device));
   for (int l = 1; l <= r->L; ++l) {
@@ -1716,6 +1777,17 @@ int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* rc, float* sum_sq_err, f
   BP_TRY(rank_forward_resident(r, 0, rc->n_samples, out, sum_sq_err ? &s : nullptr));
   if (sum_sq_err) *sum_sq_err = (float)s;
   return BP_OK;
+}
+
+int bp_decode_raw_submit(bp_handle* h, const bp_raw_chunk* rc, float* out) {
+  BP_TRY(check_raw_chunk(h, rc));
+  if (!out) return fail(BP_EINVAL, "bp_decode_raw_submit: null output buffer");
+  return rank_decode_submit(h->ranks[0], rc, out);  // device 0 only, like bp_crossvalid
+}
+
+int bp_decode_raw_wait(bp_handle* h) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  return rank_decode_wait(h->ranks[0]);
 }
 
 int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {

@@ -149,6 +149,15 @@ int bp_train_raw(bp_handle* h, const bp_raw_chunk* chunk);         /* = upload +
 /* CrossValid (+ optional decode output, n_samples x layersizes[last]) over a raw chunk; all rows on device 0. */
 int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* chunk, float* sum_sq_err /* may be NULL */,
                       float* out /* may be NULL */);
+/* Pipelined decode of a stream of raw chunks (BASELINE config C5; the reference computes the enhanced frames in
+ * cv_bunch_single and drops them, BP_GPU.cu:445-473).  bp_decode_raw_submit queues records -> rows -> forward pass ->
+ * device-to-host copy into `out` (n_samples x layersizes[last]; page-locked memory, bp_host_alloc, makes the copy
+ * asynchronous) and returns as soon as the chunk's records and tables have been consumed (the caller may refill them).
+ * bp_decode_raw_wait blocks until the OLDEST submitted chunk's frames are complete in its `out`.  At most two chunks
+ * are in flight (a third submit returns BP_EINVAL), so the steady-state loop is  submit(k+1); wait()  [-> chunk k] :
+ * upload of k+1, forward of k+1 and the read-back of k overlap.  Device 0 only; no targets needed. */
+int bp_decode_raw_submit(bp_handle* h, const bp_raw_chunk* chunk, float* out);
+int bp_decode_raw_wait(bp_handle* h);
 /* Reads rows of the resident chunk back (tests: bit-exactness of the device reader).  Single-rank handles. */
 int bp_download_chunk(bp_handle* h, int first_row, int n_rows, float* in /* may be NULL */,
                       float* targ /* may be NULL */);

@@ -2,6 +2,7 @@
 `-x` cannot mask the proven tests behind them.
   * decode straight from raw Pfile records without targets (BP_GPU.decode_raw = bp_crossvalid_raw with a null score
     pointer and no target records): bit-identical with bp_forward on the rows the host reader assembles;
+  * the pipelined decode (bp_decode_raw_submit / _wait, two chunks in flight) against the synchronous one;
   * BPtrain's chunk prefetch thread (prefetch=1, the default) trains the very same epoch as the serial loop
     (prefetch=0), for both readers: byte-identical .wts, identical CV score."""
 import importlib
@@ -32,6 +33,32 @@ def test_decode_raw_equals_forward_on_host_assembled_rows():
         assert np.array_equal(out, g.forward(x.shape[0], x))
     with pytest.raises(bp.BpError):   # a score without target records is refused
         g.crossvalid_raw(_raw(bp, h, [c for c in chunks if c["n_samples"] > 0][0], with_targ=False))
+    g.close()
+
+
+def test_pipelined_decode_two_chunks_in_flight():
+    """bp_decode_raw_submit / bp_decode_raw_wait: results of a pipelined stream equal the synchronous decode, a third
+    chunk in flight and a wait without a chunk are refused."""
+    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
+    case = CASES["129b"]
+    h, chunks = run_raw_dump(case)
+    chunks = [c for c in chunks if c["n_samples"] > 0]
+    g, _, _ = _net(bp, case, 16)
+    want = [g.decode_raw(_raw(bp, h, c, with_targ=False)) for c in chunks]
+    stream = [chunks[i % len(chunks)] for i in range(7)]
+    outs = [bp.PinnedArray((c["n_samples"], case["out"])) for c in stream]
+    with pytest.raises(bp.BpError):
+        g.decode_raw_wait()
+    g.decode_raw_submit(_raw(bp, h, stream[0], with_targ=False), outs[0].array)
+    for k in range(1, len(stream)):
+        g.decode_raw_submit(_raw(bp, h, stream[k], with_targ=False), outs[k].array)
+        if k == 1:
+            with pytest.raises(bp.BpError):   # two in flight already
+                g.decode_raw_submit(_raw(bp, h, stream[k], with_targ=False), outs[k].array)
+        g.decode_raw_wait()
+        assert np.array_equal(outs[k - 1].array, want[(k - 1) % len(chunks)])
+    g.decode_raw_wait()
+    assert np.array_equal(outs[-1].array, want[(len(stream) - 1) % len(chunks)])
     g.close()
 
 
