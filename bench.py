@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--chunk-bunches", type=int, default=32, help="bunches resident per chunk (inputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-raw", action="store_true",
+                    help="train workloads, 1 GPU: also time bp_train_raw() fed with raw Pfile records (device reader)")
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"],
                     help="tf32 = single-pass TF32 products (default); 3xtf32 = split precision, ~fp32 accuracy")
     args = ap.parse_args()
@@ -385,6 +387,35 @@ def main():
                "h2d_bytes_per_step": 4 * lb * (sizes[0] + sizes[-1]) * world, "d2h_bytes_per_step": 8 * world,
                "api": f"bp_train() on pinned host chunks of {e2e_cb} bunches + bp_train_losses()",
                "last_loss": float(losses[0]) / (lb * sizes[-1])}
+        if args.e2e_raw and world == 1 and sizes[0] == 257 * 11:
+            # The same chunks fed the way BPtrain reader=gpu feeds them: raw big-endian records (feature + target
+            # Pfiles) from pinned memory, splice / normalise on the device: ~1/6 of the H2D bytes.
+            try:
+                fea_dim, ctx, n_s = 257, 11, e2e_cb * lb
+                n_rec = n_s + ctx - 1
+                rng = np.random.default_rng(11)
+                pf, ptg = bp.PinnedArray((n_rec, fea_dim + 2)), bp.PinnedArray((n_rec, sizes[-1] + 2))
+                for pa, scale in ((pf, 1.0), (ptg, 0.5)):
+                    words = rng.standard_normal(pa.array.shape, dtype=np.float32) * np.float32(scale)
+                    pa.array[:] = words.view(np.uint32).byteswap().view(np.float32)
+                raw = bp.RawChunk(fea_dim, ctx, ctx // 2, 0, pf.array, ptg.array, np.zeros(fea_dim, np.float32),
+                                  np.ones(fea_dim, np.float32), np.arange(n_s, dtype=np.int32))
+                g.train_raw(raw)
+                barrier()
+                t0 = time.perf_counter()
+                for c in range(n_calls):
+                    g.train_raw(raw)
+                    if c > 0:
+                        g.train_losses(age=1, max_n=e2e_cb)
+                g.train_losses(age=0, max_n=e2e_cb)
+                g.sync()
+                dt_raw = time.perf_counter() - t0
+                e2e["raw_reader"] = {"value": n_calls * n_s / dt_raw, "unit": "frames/s",
+                                     "h2d_bytes_per_step": 4 * n_rec * (fea_dim + sizes[-1] + 4) // e2e_cb,
+                                     "d2h_bytes_per_step": 8,
+                                     "api": f"bp_train_raw() on pinned raw-record chunks of {e2e_cb} bunches"}
+            except Exception as e:   # an extra measurement must not hide the bench line
+                e2e["raw_reader"] = {"error": str(e)}
     else:
         n_calls = max(1, K // 4)
         out = None
