@@ -1,0 +1,374 @@
+// libbpgpu.so, launch half: the only translation unit that instantiates the tcgen05 GEMM kernel templates
+// (bp_gemm.cuh, bp_gemm2.cuh).  Tensor-map construction, kernel choice per product, cluster capacity, the split-K
+// finisher and the MMA-rate microbenchmark live here; bp_runtime.cu reaches them through bp_internal.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "bp_gemm.cuh"
+#include "bp_gemm2.cuh"
+#include "bp_internal.h"
+#include "bp_microbench.cuh"
+
+namespace bp {
+
+// ------------------------------------------------------------------------------------------------ driver entry
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static int get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (!g_encode) return fail(BP_ECUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  return BP_OK;
+}
+
+// 3-D view {32 floats, rows (stride ld floats), ld/32 chunks (stride 128 B)} of a row-major fp32 matrix [rows x ld]
+// (see the "Operand fetch" paragraph of bp_gemm.cuh).  OOB rows / chunks are zero-filled.
+//   K-major operand  (reduction dim contiguous): rows = exact M/N extent, chunks = ceil(K/32); box {32, box_rows, 2};
+//                    SWIZZLE_128B.
+//   MN-major operand (M/N dim contiguous):       rows = exact K extent,   chunks = ceil(MN/32); box {32, 64, box_mn/32};
+//                    SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands).
+//   A-slice maps of the multicast clusters (bp_gemm2.cuh): MN-major box_outer = 128/CP; K-major box_outer = 128 or 64
+//   rows with k_chunks = 1 (one 32-wide k-chunk per box instead of the whole 64-deep stage).
+int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
+              int box_outer, bool mn_major, int k_chunks) {
+  BP_TRY(get_encode());
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 31) != 0)
+    return fail(BP_EINVAL, "tensor map: base not 16-byte aligned or ld %% 32 != 0 (ld=%lld)", ld);
+  const long long chunks = (contiguous_extent + 31) / 32;
+  if (chunks * 32 > ld) return fail(BP_EINVAL, "tensor map: extent %lld exceeds ld %lld", contiguous_extent, ld);
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(chunks)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? GEMM_BLOCK_K : box_outer),
+                       static_cast<cuuint32_t>(mn_major ? box_outer / 32 : k_chunks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(BP_ECUDA, "cuTensorMapEncodeTiled failed (%d) extent=%lld rows=%lld ld=%lld box=%d mn=%d", (int)r,
+                contiguous_extent, rows, ld, box_outer, (int)mn_major);
+  return BP_OK;
+}
+
+int make_map(MapPair* mp, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
+             long long ld, int box_outer, bool mn_major, int k_chunks) {
+  BP_TRY(make_map1(&mp->m, base, contiguous_extent, rows, ld, box_outer, mn_major, k_chunks));
+  if (lo_base) BP_TRY(make_map1(&mp->lo, lo_base, contiguous_extent, rows, ld, box_outer, mn_major, k_chunks));
+  else mp->lo = mp->m;
+  return BP_OK;
+}
+
+int make_a_maps(AMaps* am, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
+                long long ld, bool mn_major) {
+  BP_TRY(make_map(&am->full, base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, mn_major));
+  if (mn_major) {
+    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, true));
+    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 4, true));
+  } else {
+    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, false, 1));
+    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, false, 1));
+  }
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <bool kAMN, bool kBMN, int kEpi, int BN>
+static int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
+  auto kern = bp_gemm_kernel<kAMN, kBMN, kEpi, BN>;
+  constexpr size_t smem = gemm_smem_bytes<BN>();
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev;
+  }
+  const int mt = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int nt = (p.N - p.n_begin + BN - 1) / BN;
+  const int tiles = mt * nt;
+  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  if (p.k_splits > 1 && kEpi != EPI_PLAIN) return fail(BP_EINVAL, "gemm: split-K needs the plain epilogue");
+  const int grid = std::min(tiles * std::max(1, p.k_splits), num_sms);
+  static const uint32_t env_flags = [] {
+    const char* e = getenv("BP_GEMM_FLAGS");  // measurement aid, see GemmParams::dbg_flags
+    return e ? (uint32_t)atoi(e) : 0u;
+  }();
+  static const bool use_pdl = [] {
+    const char* e = getenv("BP_PDL");  // programmatic dependent launch between consecutive GEMMs (default on)
+    return e ? atoi(e) != 0 : true;
+  }();
+  static const int l2_prefetch = [] {
+    const char* e = getenv("BP_L2_PREFETCH");
+    return e ? std::max(0, atoi(e)) : 0;
+  }();
+  GemmParams q = p;
+  q.l2_prefetch = l2_prefetch;
+  q.dbg_flags |= env_flags;
+  static const bool use_hints = [] {
+    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (!use_hints) q.hint_a = q.hint_b = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a.m, b.m, a.lo, b.lo, q));
+  return BP_OK;
+}
+
+// CTA-pair (cta_group::2) variant: 256 x PAIR_N pair tiles, CP pairs per cluster sharing their A rows by TMA multicast
+// (CP = 1: plain pairs).  `a` is the A map the kernel loads with: the whole-block map for CP = 1, the slice map else.
+// Clusters that can be co-resident (GPC granularity) per (PAIR_N, CP), filled by the first launch of each shape.
+static int g_max_clusters[2][3] = {{0, 0, 0}, {0, 0, 0}};
+inline int& max_clusters_slot(int pair_n, int cp) { return g_max_clusters[pair_n == 256][cp == 1 ? 0 : cp == 2 ? 1 : 2]; }
+
+// Occupancy depends on the cluster size and the shared-memory size only, so one instantiation per (PAIR_N, CP) answers
+// for all of them.  Called once per device before the first kernel choice (rank_create / bp_debug_gemm).
+template <int PAIR_N, int CP>
+static void query_cluster_capacity(int num_sms) {
+  auto kern = bp_gemm2_kernel<true, false, EPI_FWD_HID, PAIR_N, CP>;
+  constexpr int kCluster = 2 * CP;
+  int cap = num_sms / kCluster;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm2_smem_bytes<PAIR_N>()) ==
+      cudaSuccess) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(num_sms / kCluster * kCluster);
+    qc.blockDim = dim3(GEMM_THREADS);
+    qc.dynamicSmemBytes = gemm2_smem_bytes<PAIR_N>();
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = kCluster;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) cap = std::min(n, cap);
+  }
+  cudaGetLastError();
+  max_clusters_slot(PAIR_N, CP) = cap;
+}
+void init_cluster_capacity(int num_sms) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (g_max_clusters[0][0] > 0) return;
+  query_cluster_capacity<128, 2>(num_sms);
+  query_cluster_capacity<128, 4>(num_sms);
+  query_cluster_capacity<256, 1>(num_sms);
+  query_cluster_capacity<256, 2>(num_sms);
+  query_cluster_capacity<256, 4>(num_sms);
+  query_cluster_capacity<128, 1>(num_sms);
+  if (getenv("BP_VERBOSE"))
+    fprintf(stderr, "libbpgpu: co-resident clusters  128-wide pairs x1/x2/x4: %d %d %d   256-wide: %d %d %d\n",
+            g_max_clusters[0][0], g_max_clusters[0][1], g_max_clusters[0][2], g_max_clusters[1][0],
+            g_max_clusters[1][1], g_max_clusters[1][2]);
+}
+
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP, bool kTrace = false, int kStagesOv = 0>
+static int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP, kTrace, kStagesOv>;
+  constexpr size_t smem = gemm2_smem_bytes<PAIR_N, kStagesOv>();
+  constexpr int kCluster = 2 * CP;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev;
+  }
+  init_cluster_capacity(num_sms);
+  const int max_clusters = max_clusters_slot(PAIR_N, CP);
+  const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  const int nt = (p.N - p.n_begin + CP * PAIR_N - 1) / (CP * PAIR_N);
+  const int tiles = mt * nt;
+  if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  static const bool use_pdl = [] {
+    const char* e = getenv("BP_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  static const bool use_hints = [] {
+    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
+    return e ? atoi(e) != 0 : true;
+  }();
+  static const int l2_prefetch = [] {
+    const char* e = getenv("BP_L2_PREFETCH");  // k-blocks of L2-only prefetch ahead of the ring (default off; untested A/B)
+    return e ? std::max(0, atoi(e)) : 0;
+  }();
+  GemmParams q = p;
+  q.l2_prefetch = l2_prefetch;
+  if (!use_hints || CP > 1) q.hint_a = 0;  // the multicast A-slice load carries no hint
+  if (!use_hints) q.hint_b = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(std::min(tiles, std::min(max_clusters, num_sms / kCluster)) * kCluster);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 2 : 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, a.m, b.m, a.lo, b.lo, q));
+  return BP_OK;
+}
+
+// Kernel choice per product: {pair_n, cp}; pair_n = 0 -> 128 x 128 tiles on lone CTAs.
+//   BP_PAIRS: 0 = lone CTAs only, 1 = automatic (default), 2 = 256-wide pairs always, 3 = 128-wide pairs whenever the
+//             narrow B map exists.
+//   BP_MC:    pairs per multicast cluster when a pair kernel is chosen: 1 = none (default), 2, 4 (experimental, see
+//             measured no gain on K-major A, MN-major A slices not yet correct).
+// Automatic: 256 x 256 pair tiles if they fill >= 60 % of the SM pairs, else 256 x 128 pair tiles under the same
+// condition, else 128 x 128 tiles on lone CTAs.  Measured in isolation on the B200 (scripts/gpu_mc_probe.py, r1d):
+// 2048x1024x2048 fwd 18.4 us on 128-wide pairs vs 25.9 us on 256-wide ones (64 CTAs); 2048x2049x1024 dW 17.6 us on
+// 256-wide pairs vs 19.5 us on 128-wide ones — the rule picks the faster one in every product of C2/C3/C5.
+struct KernelChoice {
+  int pair_n;
+  int cp;
+};
+inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
+  static const int mode = [] {
+    const char* e = getenv("BP_PAIRS");
+    return e ? atoi(e) : 1;
+  }();
+  static const int cp = [] {
+    const char* e = getenv("BP_MC");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4) ? v : 1;
+  }();
+  if (mode == 0) return {0, 1};
+  if (mode == 2) return {256, cp};
+  if (mode == 3) return {have_b64 ? 128 : 0, cp};
+  const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  const int n = p.N - p.n_begin;
+  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return {256, cp};
+  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return {128, cp};
+  return {0, 1};
+}
+
+
+// b = B operand map with 128-wide boxes (lone CTAs and 256-wide pairs); b64 = the same operand with 64-wide boxes
+// (128-wide pairs: each CTA stages 64 B columns), or null.
+template <bool kAMN, bool kBMN, int kEpi>
+static int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
+                       const MapPair* b64 = nullptr) {
+  const KernelChoice k = pick_kernel(p, num_sms, b64 != nullptr);
+  if constexpr (kEpi == EPI_DW_SGD) {  // fused update: plain pairs / lone CTAs only (no multicast, trace or stage variants)
+    if (k.pair_n == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+    if (k.pair_n == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
+    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
+  } else {
+    if (k.pair_n == 256) {
+      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
+      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
+      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1, true>(st, num_sms, a.full, b, p);
+      return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
+    }
+    if (k.pair_n == 128) {
+      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
+      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
+      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
+      static const int stages = [] {
+        const char* e = getenv("BP_STAGES");  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
+        return e ? atoi(e) : 0;
+      }();
+      if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
+      if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
+      return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
+    }
+    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
+                   const MapPair* b64) {
+  switch (prod) {
+    case PROD_FWD_HID: return launch_gemm<true, false, EPI_FWD_HID>(st, num_sms, a, b, p, b64);
+    case PROD_FWD_OUT: return launch_gemm<true, false, EPI_FWD_OUT>(st, num_sms, a, b, p, b64);
+    case PROD_FWD_PLAIN: return launch_gemm<true, false, EPI_PLAIN>(st, num_sms, a, b, p, b64);
+    case PROD_FWD_SPLITK: return launch_gemm_bn<true, false, EPI_PLAIN, kBlockN>(st, num_sms, a.full, b, p);
+    case PROD_FWD_DXEPI: return launch_gemm<true, false, EPI_DX>(st, num_sms, a, b, p, b64);
+    case PROD_DX: return launch_gemm<false, false, EPI_DX>(st, num_sms, a, b, p, b64);
+    case PROD_DX_PLAIN: return launch_gemm<false, false, EPI_PLAIN>(st, num_sms, a, b, p, b64);
+    case PROD_DW: return launch_gemm<true, true, EPI_PLAIN>(st, num_sms, a, b, p, b64);
+    case PROD_DW_SGD: return launch_gemm<true, true, EPI_DW_SGD>(st, num_sms, a, b, p, b64);
+  }
+  return fail(BP_EINVAL, "launch_product: unknown product %d", (int)prod);
+}
+
+int launch_out_finish(cudaStream_t st, const float* ws, long long ldw, const GemmParams& p, long long cells) {
+  bp_out_finish_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ws, ldw, p);
+  CU_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+}  // namespace bp
+
+extern "C" {
+using namespace bp;
+
+// Bring-up aid: cycles per 128 x bn x 8 TF32 MMA (issue, issue+drain) on one SM; combo 0 = A MN/B K, 1 = K/K, 2 = MN/MN,
+// 3 = K/MN.  mode bit 0: fence before each group of 8, bit 1: commit after each group.
+int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total) {
+  long long* d = nullptr;
+  long long h[2] = {0, 0};
+  int rc = [&]() -> int {
+    CU_TRY(cudaMalloc(&d, 16));
+    const size_t smem = (128 + 256) * 64 * 4 + 1024;
+#define BP_RATE(AM, BM, BN_)                                                                         \
+  {                                                                                                  \
+    auto k = bp_mma_rate_kernel<AM, BM, BN_>;                                                        \
+    CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    k<<<1, 64, smem>>>(iters, mode, d);                                                              \
+  }
+    if (bn == 128) {
+      if (combo == 0) BP_RATE(true, false, 128) else if (combo == 1) BP_RATE(false, false, 128)
+      else if (combo == 2) BP_RATE(true, true, 128) else BP_RATE(false, true, 128)
+    } else if (bn == 256) {
+      if (combo == 0) BP_RATE(true, false, 256) else if (combo == 1) BP_RATE(false, false, 256)
+      else if (combo == 2) BP_RATE(true, true, 256) else BP_RATE(false, true, 256)
+    } else if (bn == 64) {
+      if (combo == 0) BP_RATE(true, false, 64) else if (combo == 1) BP_RATE(false, false, 64)
+      else if (combo == 2) BP_RATE(true, true, 64) else BP_RATE(false, true, 64)
+    } else {
+      return fail(BP_EINVAL, "bn must be 64, 128 or 256");
+    }
+#undef BP_RATE
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+    return BP_OK;
+  }();
+  cudaFree(d);
+  if (cyc_issue) *cyc_issue = (double)h[0] / (8.0 * iters);
+  if (cyc_total) *cyc_total = (double)h[1] / (8.0 * iters);
+  return rc;
+}
+
+}  // extern "C"

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda.h>
+#include "bp_gemm_params.h"
 
 namespace bp {
 
@@ -123,9 +124,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 
 // Same with an L2 eviction-priority hint (createpolicy-encoded: kEvictLast keeps re-read operands such as the weights
 // resident, kEvictFirst marks streaming data).
-constexpr unsigned long long kEvictNormal = 0x1000000000000000ull;
-constexpr unsigned long long kEvictFirst = 0x12F0000000000000ull;
-constexpr unsigned long long kEvictLast = 0x14F0000000000000ull;
+// (kEvictNormal / kEvictFirst / kEvictLast: bp_gemm_params.h, shared with the host side)
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                  int c2, unsigned long long policy) {
   asm volatile(
