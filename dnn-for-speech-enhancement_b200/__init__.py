@@ -89,6 +89,8 @@ def load_library() -> C.CDLL:
     lib.bp_train_resident.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bp_forward_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.POINTER(C.c_double)]
     lib.bp_sync.argtypes = [C.c_void_p]
+    lib.bp_get_timeline.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.bp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
@@ -368,6 +370,19 @@ class BP_GPU:
 
     def set_profiling(self, on: bool) -> None:
         _check(load_library().bp_set_profiling(self._h, 1 if on else 0), "bp_set_profiling")
+
+    def set_timeline(self, on: bool) -> None:
+        """Launch timeline of the next <= 16 training bunches (bp_set_profiling(h, 2)); off = plain profiling off."""
+        _check(load_library().bp_set_profiling(self._h, 2 if on else 0), "bp_set_profiling")
+
+    def timeline(self):
+        """[(label, ms since the bunch's start mark)] per launch, averaged over the recorded bunches, + their count."""
+        lab = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n, nb = C.c_int(0), C.c_int(0)
+        _check(load_library().bp_get_timeline(self._h, lab, 4096, ms, 64, C.byref(n), C.byref(nb)), "bp_get_timeline")
+        names = lab.value.decode().split("\n")[: n.value]
+        return [(names[i], float(ms[i])) for i in range(n.value)], nb.value
 
     def profile(self):
         ms = (C.c_float * 6)()

@@ -206,6 +206,17 @@ struct Rank {
   static constexpr int kProfCap = 64;        // profiled bunches kept (ring)
   std::vector<cudaEvent_t> pev;              // 7 events per profiled bunch, no host sync while recording
   uint64_t prof_cnt = 0;
+  // Launch timeline (bp_set_profiling(h, 2)): one event behind EVERY launch of a bunch, on the stream it was launched
+  // on, for the first kTlBunches profiled bunches; bp_get_timeline reports each launch's completion time since the
+  // bunch's start mark.  The records sit between the kernels, so programmatic dependent launch does not overlap
+  // across them: this is the dependency chain's latency, launch by launch, with warm-in-place caches (what neither the
+  // per-class events nor ncu's serialised, cache-flushed replays show).
+  static constexpr int kTlCap = 40, kTlBunches = 16;
+  int timeline = 0;
+  std::vector<cudaEvent_t> tev;              // kTlBunches x kTlCap, created on first use
+  const char* tl_label[kTlCap] = {};
+  int tl_idx = 0, tl_marks = 0;
+  uint64_t tl_bunches = 0;
   // per-bunch sum of squared output error of the two most recent train calls (ring), so that a caller can read
   // call i-1's losses while call i computes (no compute-stream sync on the reading path)
   double* loss_dev[2] = {nullptr, nullptr};
@@ -284,6 +295,8 @@ int rank_destroy(Rank* r) {
   for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
   for (auto e : r->pev)
+    if (e) cudaEventDestroy(e);
+  for (auto e : r->tev)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     cudaFree(r->loss_dev[i]);
@@ -643,6 +656,27 @@ inline int out_layer_splits(const GemmParams& p, int num_sms) {
   return (num_kb + per - 1) / per;  // every slice non-empty
 }
 
+// Launch timeline mark: an event behind the launch just issued on `st` (see Rank::timeline).
+inline void tl_mark(Rank* r, cudaStream_t st, const char* label) {
+  if (!r->timeline || r->tl_bunches >= (uint64_t)Rank::kTlBunches || r->tl_idx >= Rank::kTlCap) return;
+  if (r->tev.empty()) {
+    r->tev.assign((size_t)Rank::kTlBunches * Rank::kTlCap, nullptr);
+    for (auto& e : r->tev)
+      if (cudaEventCreate(&e) != cudaSuccess) {
+        e = nullptr;
+        cudaGetLastError();
+      }
+  }
+  cudaEvent_t e = r->tev[(size_t)r->tl_bunches * Rank::kTlCap + r->tl_idx];
+  if (!e) return;
+  cudaEventRecord(e, st);
+  r->tl_label[r->tl_idx++] = label;
+}
+static const char* const kFwdLabel[BP_MAXLAYER] = {"", "fwd1", "fwd2", "fwd3", "fwd4", "fwd5", "fwd6", "fwd7", "fwd8", "fwd9"};
+static const char* const kDxLabel[BP_MAXLAYER] = {"", "dx1", "dx2", "dx3", "dx4", "dx5", "dx6", "dx7", "dx8", "dx9"};
+static const char* const kDwLabel[BP_MAXLAYER] = {"", "dw1 (side)", "dw2 (side)", "dw3 (side)", "dw4 (side)", "dw5 (side)",
+                                                  "dw6 (side)", "dw7 (side)", "dw8 (side)", "dw9 (side)"};
+
 // ------------------------------------------------------------------------------------------------ forward
 // Forward over rows [f0, f0+n) of the resident chunk.  train=true: masks + D_L; train=false: keep-scaling (CV).
 int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, long long ldo2, double* sqerr) {
@@ -659,6 +693,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
                                                           r->step, frame0);
     CU_TRY(cudaGetLastError());
     r->launches++;
+    if (train) tl_mark(r, r->compute, "input dropout");
     if (r->passes == 3) {  // the same mask on the low part
       bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(c.x_lo + (long long)f0 * r->ldx, r->ldx, n, r->K0(),
                                                             cf.visible_omit, seed_lo, seed_hi, r->step, frame0);
@@ -699,6 +734,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
       BP_TRY((launch_product(PROD_FWD_HID, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
+      if (train) tl_mark(r, r->compute, kFwdLabel[l]);
     } else {
       if (train) {
         p.out = ls.d;
@@ -730,12 +766,15 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
         g.ldo = ls.ldN;
         BP_TRY(launch_product(PROD_FWD_SPLITK, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, g));
         r->launches++;
+        if (train) tl_mark(r, r->compute, "out split-K");
         p.k_splits = splits;
         p.split_stride = g.split_stride;
         const long long cells = (long long)n * ls.ldN;
         BP_TRY(launch_out_finish(r->compute, r->splitk_ws, ls.ldN, p, cells));
+        if (train) tl_mark(r, r->compute, "out finish");
       } else {
         BP_TRY((launch_product(PROD_FWD_OUT, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
+        if (train) tl_mark(r, r->compute, "out");
       }
     }
     r->launches++;
@@ -937,6 +976,8 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   int pe = 7 * (int)(r->prof_cnt % Rank::kProfCap);
   auto mark = [&]() { if (prof) cudaEventRecord(r->pev[pe++], r->compute); };
   mark();                                               // 0
+  r->tl_idx = 0;
+  tl_mark(r, r->compute, "start");
   BP_TRY(forward_rows(r, c, f0, n, true, nullptr, 0, loss_slot));
   mark();                                               // 1: fwd done
   float* xb = c.x + (long long)f0 * r->ldx;
@@ -992,6 +1033,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
       p.upd_prefetch = r->fused_prefetch;
       BP_TRY((launch_product(PROD_DW_SGD, r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
       r->launches++;
+      tl_mark(r, r->side, kDwLabel[l]);
       return BP_OK;
     }
     const int total = p.N;
@@ -1003,6 +1045,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
       p.N = std::min(total, b0 + per);
       BP_TRY((launch_product(PROD_DW, r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
       r->launches++;
+      tl_mark(r, r->side, kDwLabel[l]);
       if (r->nccl_comm && !r->dp_p2p) {
         float* gs = r->g + ls.off + (long long)b0 * ls.ldN;
         const size_t cnt = (p.N == total) ? (size_t)(ls.size - (long long)b0 * ls.ldN)
@@ -1036,6 +1079,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.hint_a = kEvictLast;  // A = the weights
     BP_TRY((launch_product(PROD_DX, r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
     r->launches++;
+    tl_mark(r, r->compute, kDxLabel[l - 1]);
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
     return BP_OK;
   };
@@ -1098,10 +1142,12 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
     tail_end4 = r->layer[2].off / 4;
     BP_TRY(launch_sgd(tail_end4, r->arena_floats / 4, sgd_early_blocks));
+    tl_mark(r, r->compute, "update, layers >= 2");
   }
   mark();                                               // 3: early update of layers >= 2 done
   CU_TRY(cudaEventRecord(r->ev_side, r->side));
   CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_side, 0));
+  tl_mark(r, r->compute, "join (all dW done)");
   mark();                                               // 4: all dW done
   if (r->nccl_comm && !r->dp_p2p) {
     CU_TRY(cudaEventRecord(r->ev_comm, r->comm_stream));
@@ -1111,10 +1157,15 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   if (peer_split) BP_TRY(peer_exchange_part(r, 1, peer_step, 0, tail_end4, 8));
   else if (r->dp_p2p) BP_TRY(peer_exchange(r));         // owner-side reduce + update + all-gather
   else if (!fused) BP_TRY(launch_sgd(0, tail_end4, 8)); // fused: the dW epilogues have already applied the update
+  tl_mark(r, r->compute, "update / exchange, end of bunch");
   mark();                                               // 6: sgd done
   r->step++;
   r->bunches++;
   if (prof) r->prof_cnt++;
+  if (r->timeline && r->tl_bunches < (uint64_t)Rank::kTlBunches) {
+    r->tl_marks = r->tl_idx;
+    r->tl_bunches++;
+  }
   return BP_OK;
 }
 
@@ -1650,9 +1701,44 @@ int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bun
 int bp_set_profiling(bp_handle* h, int on) {
   if (!h) return fail(BP_EINVAL, "null handle");
   for (Rank* r : h->ranks) {
-    r->profiling = on != 0;
+    r->profiling = on == 1;
     r->prof_cnt = 0;
+    r->timeline = on == 2;
+    r->tl_bunches = 0;
+    r->tl_marks = 0;
   }
+  return BP_OK;
+}
+
+int bp_get_timeline(bp_handle* h, char* labels, int labels_len, float* ms, int max_marks, int* n_marks,
+                    int* bunches) {
+  if (!h || !labels || labels_len <= 0 || !ms || !n_marks) return fail(BP_EINVAL, "bp_get_timeline: null argument");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  CU_TRY(cudaStreamSynchronize(r->side));
+  const int nb = (int)r->tl_bunches, nm = std::min(r->tl_marks, max_marks);
+  labels[0] = 0;
+  *n_marks = 0;
+  if (bunches) *bunches = nb;
+  if (nb == 0 || nm == 0) return BP_OK;
+  std::string all;
+  for (int k = 0; k < nm; ++k) {
+    double sum = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      float t = 0.0f;
+      cudaEvent_t e0 = r->tev[(size_t)b * Rank::kTlCap], ek = r->tev[(size_t)b * Rank::kTlCap + k];
+      if (!e0 || !ek) return fail(BP_ECUDA, "bp_get_timeline: events missing");
+      CU_TRY(cudaEventElapsedTime(&t, e0, ek));
+      sum += t;
+    }
+    ms[k] = (float)(sum / nb);
+    all += r->tl_label[k] ? r->tl_label[k] : "?";
+    all += '\n';
+  }
+  if ((int)all.size() + 1 > labels_len) return fail(BP_EINVAL, "bp_get_timeline: label buffer too small");
+  memcpy(labels, all.c_str(), all.size() + 1);
+  *n_marks = nm;
   return BP_OK;
 }
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled) {

@@ -179,6 +179,13 @@ int bp_get_counters(bp_handle* h, uint64_t* kernel_launches, uint64_t* train_bun
  * ms[5] = early SGD update of layers >= 2, which overlaps the first layer's dW GEMM.  Sums over the last <= 64 profiled bunches; records events only, no host sync per bunch. */
 int bp_set_profiling(bp_handle* h, int on);
 int bp_get_profile(bp_handle* h, float ms[6], uint64_t* bunches_profiled);
+/* Launch timeline (bp_set_profiling(h, 2); measurement aid): an event behind EVERY launch of a training bunch, on the
+ * stream it was issued on, for the next <= 16 bunches.  bp_get_timeline returns, per launch in issue order, its
+ * label (newline-separated in `labels`) and its completion time in ms since the bunch's start mark, averaged over the
+ * recorded bunches — the latency of the dependency chain launch by launch, caches as the pipeline leaves them.  The
+ * records sit between the kernels, so programmatic dependent launch cannot overlap across them (~3 % pessimistic). */
+int bp_get_timeline(bp_handle* h, char* labels, int labels_len, float* ms, int max_marks, int* n_marks,
+                    int* bunches /* may be NULL */);
 
 /* Training-loss monitor (our extension): sum over this handle's rows and output dims of (out - targ)^2 for each bunch
  * of the most recent (age 0) or the previous (age 1) bp_train / bp_train_resident call, accumulated in the

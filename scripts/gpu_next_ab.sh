@@ -13,3 +13,4 @@ bash scripts/gpu_ab.sh "BP_L2_PREFETCH=0" "BP_L2_PREFETCH=4" "BP_L2_PREFETCH=8" 
 for s in 0 2; do echo "== isolated, BP_STAGES=$s"; BP_STAGES=$s timeout 60 python scripts/gpu_mc_probe.py quick 2>&1 | tail -7; done
 timeout 120 python scripts/gpu_pair_trace.py 2>&1 | head -150
 echo "== dX gap: operand layout vs epilogue"; timeout 120 python scripts/gpu_mc_probe.py dxgap 2>&1 | tail -14
+echo "== launch timeline of a bunch (default, then with the L2 switches)"; for e in "BP_X=0" "BP_L2_PREFETCH=8" "BP_L2_PERSIST=64" "BP_FUSED_UPDATE=1"; do echo "-- $e"; env $e timeout 120 python scripts/gpu_timeline.py C2 2>&1 | tail -22; done
