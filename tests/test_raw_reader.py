@@ -105,7 +105,7 @@ def test_raw_tables_reproduce_reference_reader(name):
 
 @pytest.mark.parametrize("traincache", [7, 16, 40])
 def test_prefetch_thread_reads_the_same_chunks_as_the_serial_loop(traincache):
-    """RawPrefetcher (host/RawPrefetch.h, BPtrain reader=gpu prefetch=1) runs the ReadchunkRaw calls one chunk ahead on
+    """ChunkPrefetcher (host/ChunkPrefetch.h, BPtrain reader=gpu prefetch=1) runs the ReadchunkRaw calls one chunk ahead on
     a second thread: records, tables and chunk order must be byte-identical with the serial loop (prefetch=0), also
     when there are many more chunks than the two slots."""
     _build()
