@@ -84,10 +84,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
           if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
       }
     }
-  } else if constexpr (kEpi == EPI_FWD_HID) {
+  } else if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_HID_MASK) {
     if (m_ok) {
       float* o = p.out + size_t(nc) * p.ldo + m;
       const bool drop = p.drop_p > 0.0f;
+      uint32_t bits = 0;  // EPI_FWD_HID_MASK: bit j = (y_j > 0) of the values as stored
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
         float u4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
@@ -102,9 +103,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
           if (whole || nc + j < p.N) {
             *o = y;
             if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(y);
+            if constexpr (kEpi == EPI_FWD_HID_MASK) bits |= (y > 0.0f ? 1u : 0u) << j;
           }
         }
       }
+      if constexpr (kEpi == EPI_FWD_HID_MASK) p.relu_mask[size_t(nc >> 5) * p.ldmask + m] = bits;
     }
   } else if constexpr (kEpi == EPI_FWD_OUT) {
     if (m_ok) {
@@ -261,6 +264,48 @@ __device__ __forceinline__ void gemm_sgd_epilogue(const GemmParams& p, SgdPrefet
     tmem_ld32(taddr + uint32_t((c + 1) * 32), v);
     tmem_ld_wait();
     gemm_sgd_store(p, v, pre.d[1], pre.x[1], m, m_ok, nc + 32);
+  }
+}
+
+// EPI_DX_MASK: the ReLU-derivative predicate comes from the forward epilogue's bit mask (one word per lane and
+// 32-column chunk) instead of Y itself.  All of a tile's words are fetched before the accumulator is waited for — a
+// handful of registers where DxPrefetch needs 64 for two chunks — and the result is bit-identical with EPI_DX at
+// act == 0 (y > 0 ? acc : 0, DevFunc.cu:81-97 + 244-250).
+template <int BLOCK_N>
+struct DxMaskPrefetch {
+  uint32_t w[BLOCK_N / 32];
+  __device__ __forceinline__ void start(const GemmParams& p, int m, bool m_ok, int n0) {
+#pragma unroll
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int nc = n0 + c * 32;
+      w[c] = (m_ok && nc < p.N) ? __ldg(p.relu_mask + size_t(nc >> 5) * p.ldmask + m) : 0u;
+    }
+  }
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ void gemm_dxmask_epilogue(const GemmParams& p, const DxMaskPrefetch<BLOCK_N>& pre,
+                                                     uint32_t taddr, int m, bool m_ok, int n0) {
+#pragma unroll
+  for (int c = 0; c < BLOCK_N / 32; ++c) {  // unrolled: pre.w[c] stays in registers
+    const int nc = n0 + c * 32;
+    if (nc < p.N) {                         // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(taddr + uint32_t(c * 32), v);
+      tmem_ld_wait();
+      if (m_ok) {
+        const bool whole = nc + 32 <= p.N;
+        const uint32_t bits = pre.w[c];
+        float* o = p.out + size_t(nc) * p.ldo + m;
+#pragma unroll
+        for (int j = 0; j < 32; ++j, o += p.ldo)
+          if (whole || nc + j < p.N) {
+            const float dv = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.0f;
+            *o = dv;
+            if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
+          }
+      }
+    }
   }
 }
 
@@ -474,19 +519,23 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         upd.load(p, 0, m, m_ok, n0);
         gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
       }
+      DxMaskPrefetch<BLOCK_N> mpre;
+      if constexpr (kEpi == EPI_DX_MASK) mpre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
       if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
-      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
+      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT || kEpi == EPI_FWD_HID_MASK) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
       } else if constexpr (kEpi == EPI_DW_SGD) {
         gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
+      } else if constexpr (kEpi == EPI_DX_MASK) {
+        gemm_dxmask_epilogue<BLOCK_N>(p, mpre, taddr, m, m_ok, n0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {

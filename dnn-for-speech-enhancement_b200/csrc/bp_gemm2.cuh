@@ -265,6 +265,8 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         upd.load(p, 0, m, m_ok, n0);
         gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
       }
+      DxMaskPrefetch<BLOCK_N> mpre;  // EPI_DX_MASK: the tile's ReLU-mask words (see gemm_dxmask_epilogue)
+      if constexpr (kEpi == EPI_DX_MASK) mpre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
       if constexpr (kTrace) {
@@ -273,13 +275,15 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
-      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
+      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT || kEpi == EPI_FWD_HID_MASK) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
       } else if constexpr (kEpi == EPI_DW_SGD) {
         gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
+      } else if constexpr (kEpi == EPI_DX_MASK) {
+        gemm_dxmask_epilogue<BLOCK_N>(p, mpre, taddr, m, m_ok, n0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {

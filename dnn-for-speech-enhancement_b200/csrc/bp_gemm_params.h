@@ -18,6 +18,10 @@ enum Epi : int {
   EPI_DX = 3,         // out = act'(aux) * acc                    (back-prop through the non-linearity)
   EPI_DW_SGD = 4,     // acc = gradient tile, consumed in place: momentum-SGD update of the same tile of the weight and
                       // delta arenas (kernUpdatedelta + kernAccSum, DevFunc.cu:313-318, 270-277); no gradient is stored
+  // ReLU nets (BP_RELU_MASK=1, off by default): kernDsigmoid's ReLU' is the predicate y > 0 (DevFunc.cu:81-97), so the
+  // forward epilogue can leave one BIT per activation and the dX epilogue read 1/32 of what re-reading Y costs it.
+  EPI_FWD_HID_MASK = 5,  // EPI_FWD_HID + relu_mask word (32 frames x 1 unit) per accumulator chunk
+  EPI_DX_MASK = 6,       // out = bit ? acc : 0  — EPI_DX for act == 0 with the mask instead of aux (bit-identical)
 };
 
 struct GemmParams {
@@ -70,6 +74,10 @@ struct GemmParams {
   float upd_momentum, upd_c1, upd_wc;  // c1 = (1-momentum)*lr
   int upd_bias_col;       // product column that is the bias row of the block (weight cost does not apply, BP_GPU.cu:648)
   int upd_prefetch;       // 1: epilogue warps pull their tile's delta/w lines into L2 while the main loop runs
+  // EPI_FWD_HID_MASK / EPI_DX_MASK: bit j of relu_mask[(n/32)*ldmask + m] = (Y[n - n%32 + j][m] > 0), Y as stored
+  // (after the activation and the dropout mask); one coalesced 128-byte row of words per warp and 32-column chunk.
+  uint32_t* relu_mask;
+  long long ldmask;
 };
 
 constexpr int GEMM_BLOCK_M = 128;

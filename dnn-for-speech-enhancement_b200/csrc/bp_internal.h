@@ -65,6 +65,8 @@ enum Product : int {
   PROD_DX_PLAIN,    //   "                                 EPI_PLAIN    probe: dX operands, plain epilogue
   PROD_DW,          // A = D^T MN-major, B = Y^T MN-major, EPI_PLAIN    weight (+bias) gradient
   PROD_DW_SGD,      //   "                                 EPI_DW_SGD   ... with the update applied in the epilogue
+  PROD_FWD_HID_MASK,  // PROD_FWD_HID that also leaves the ReLU bit mask (EPI_FWD_HID_MASK)
+  PROD_DX_MASK,       // PROD_DX reading that mask instead of Y (EPI_DX_MASK)
 };
 // Picks the kernel (lone CTAs / 128- / 256-wide CTA pairs, see pick_kernel in bp_launch.cu) and launches it on `st`.
 // b = B map with 128-wide boxes, b64 = the same operand with 64-wide boxes (for 128-wide pairs) or null.

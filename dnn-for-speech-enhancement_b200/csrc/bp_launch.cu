@@ -278,7 +278,8 @@ template <bool kAMN, bool kBMN, int kEpi>
 static int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
                        const MapPair* b64 = nullptr) {
   const KernelChoice k = pick_kernel(p, num_sms, b64 != nullptr);
-  if constexpr (kEpi == EPI_DW_SGD) {  // fused update: plain pairs / lone CTAs only (no multicast, trace or stage variants)
+  if constexpr (kEpi == EPI_DW_SGD || kEpi == EPI_FWD_HID_MASK || kEpi == EPI_DX_MASK) {
+    // gated variants (fused update, ReLU bit mask): plain pairs / lone CTAs only (no multicast, trace or stage variants)
     if (k.pair_n == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
     if (k.pair_n == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
     return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
@@ -318,6 +319,8 @@ int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, c
     case PROD_DX_PLAIN: return launch_gemm<false, false, EPI_PLAIN>(st, num_sms, a, b, p, b64);
     case PROD_DW: return launch_gemm<true, true, EPI_PLAIN>(st, num_sms, a, b, p, b64);
     case PROD_DW_SGD: return launch_gemm<true, true, EPI_DW_SGD>(st, num_sms, a, b, p, b64);
+    case PROD_FWD_HID_MASK: return launch_gemm<true, false, EPI_FWD_HID_MASK>(st, num_sms, a, b, p, b64);
+    case PROD_DX_MASK: return launch_gemm<false, false, EPI_DX_MASK>(st, num_sms, a, b, p, b64);
   }
   return fail(BP_EINVAL, "launch_product: unknown product %d", (int)prod);
 }

@@ -107,6 +107,8 @@ struct LayerState {
   float* d = nullptr;      // dE/dX_l: rows x ldd
   float* d_lo = nullptr;
   long long ldd = 0;
+  uint32_t* mask = nullptr;  // ReLU bit mask of Y_l (hidden layers): ceil(rows/32) x ldmask words, see bp_gemm_params.h
+  long long ldmask = 0;
   // tensor maps that do not depend on the chunk
   AMaps w_fwd;         // W^T as MN-major A: {N, K}
   AMaps w_dx;          // W as K-major A:    {N, K}
@@ -146,6 +148,9 @@ struct Rank {
                                 // (EPI_DW_SGD) instead of storing the gradient for bp_sgd_kernel.  BP_FUSED_UPDATE=1 /
                                 // bp_set_option("fused_update"); default off until measured on the B200
   int fused_prefetch = 1;       // ... with the tile's delta/w lines pulled into L2 under the main loop
+  int relu_mask = 0;            // ReLU nets: the forward epilogues leave a bit mask of Y > 0 and the dX epilogues read it
+                                // instead of Y (1/32 of the bytes, no 32-deep load chains).  BP_RELU_MASK=1 /
+                                // bp_set_option("relu_mask"); bit-identical results; off until measured on the B200
   int comm_sms = 0;             // data-parallel: SMs the persistent GEMMs leave free so that NCCL's kernels can run
                                 // next to them instead of behind them (BP_COMM_SMS; 16/32 measured no better: the
                                 // exposed all-reduce time is that of the last, largest layers' gradients)
@@ -278,6 +283,7 @@ int rank_destroy(Rank* r) {
     cudaFree(r->layer[l].d);
     cudaFree(r->layer[l].y_lo);
     cudaFree(r->layer[l].d_lo);
+    cudaFree(r->layer[l].mask);
   }
   cudaFree(r->w);
   cudaFree(r->w_lo);
@@ -374,6 +380,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   if (const char* e = getenv("BP_PEER_EARLY")) r->peer_early = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("BP_RELU_MASK")) r->relu_mask = atoi(e) != 0;
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -479,6 +486,9 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
         ls.ldy = round_up(ls.N + 1, 32);
         CU_TRY(cudaMalloc(&ls.y, rows * ls.ldy * 4));
         CU_TRY(cudaMemsetAsync(ls.y, 0, rows * ls.ldy * 4, r->compute));
+        ls.ldmask = round_up(ls.N, 32);
+        CU_TRY(cudaMalloc(&ls.mask, ((rows + 31) / 32) * ls.ldmask * 4));
+        CU_TRY(cudaMemsetAsync(ls.mask, 0, ((rows + 31) / 32) * ls.ldmask * 4, r->compute));
         if (r->passes == 3) {  // the ones column's low part is 0: 1.0f truncates exactly
           CU_TRY(cudaMalloc(&ls.y_lo, rows * ls.ldy * 4));
           CU_TRY(cudaMemsetAsync(ls.y_lo, 0, rows * ls.ldy * 4, r->compute));
@@ -733,7 +743,13 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
       p.out_lo = ls.y_lo;
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
-      BP_TRY((launch_product(PROD_FWD_HID, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
+      const bool with_mask = train && r->relu_mask && cf.activation == 0;
+      if (with_mask) {
+        p.relu_mask = ls.mask;
+        p.ldmask = ls.ldmask;
+      }
+      BP_TRY((launch_product(with_mask ? PROD_FWD_HID_MASK : PROD_FWD_HID, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p,
+                             bmap64)));
       if (train) tl_mark(r, r->compute, kFwdLabel[l]);
     } else {
       if (train) {
@@ -1077,7 +1093,13 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.act = cf.activation;
     p.passes = r->passes;
     p.hint_a = kEvictLast;  // A = the weights
-    BP_TRY((launch_product(PROD_DX, r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
+    const bool with_mask = r->relu_mask && cf.activation == 0;  // the forward pass of this bunch left lp.mask
+    if (with_mask) {
+      p.relu_mask = lp.mask;
+      p.ldmask = lp.ldmask;
+    }
+    BP_TRY((launch_product(with_mask ? PROD_DX_MASK : PROD_DX, r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p,
+                           &ls.d_dx64)));
     r->launches++;
     tl_mark(r, r->compute, kDxLabel[l - 1]);
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
@@ -1642,6 +1664,7 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
     if (strcmp(name, "fused_update") == 0) r->fused_update = value != 0;
     else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
     else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
+    else if (strcmp(name, "relu_mask") == 0) r->relu_mask = value != 0;    // between bunches only (bp_train* has returned)
     else return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
   }
   return BP_OK;

@@ -100,6 +100,9 @@ int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, 
  *   "peer_early"     1: data-parallel peer-memory exchange in two parts — the layers >= 2 are reduced, updated and
  *                       all-gathered while the first layer's gradient GEMM still runs (BP_PEER_EARLY); every rank
  *                       must be given the same value
+ *   "relu_mask"      1: ReLU nets — the hidden layers' forward epilogues also leave a bit mask of Y > 0 and the
+ *                       back-propagation epilogues read that mask instead of Y (kernDsigmoid's ReLU' is the predicate
+ *                       y > 0, DevFunc.cu:81-97): 1/32 of the bytes, bit-identical results (BP_RELU_MASK)
  * Returns BP_EINVAL for an unknown name. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 

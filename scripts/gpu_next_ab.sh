@@ -9,7 +9,7 @@ timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
 # Each line: frames/s, ms per bunch, per-class ms.  Keep what wins by > 1 % twice.  Then the timeline of fwd vs dX.
 bash scripts/gpu_ab.sh "BP_L2_PREFETCH=0" "BP_L2_PREFETCH=4" "BP_L2_PREFETCH=8" "BP_L2_PREFETCH=16" \
                        "BP_DW_STREAM=1" "BP_DW_STREAM=1 BP_L2_PREFETCH=8" "BP_STAGES=2" "BP_STAGES=2 BP_L2_PREFETCH=8" \
-                       "BP_STAGES=3" "BP_L2_PERSIST=64" "BP_L2_PERSIST=96" "BP_L2_PERSIST=64 BP_FUSED_UPDATE=1" "BP_L2_PREFETCH=0"
+                       "BP_STAGES=3" "BP_L2_PERSIST=64" "BP_L2_PERSIST=96" "BP_L2_PERSIST=64 BP_FUSED_UPDATE=1" "BP_RELU_MASK=1" "BP_RELU_MASK=1 BP_FUSED_UPDATE=1" "BP_L2_PREFETCH=0"
 for s in 0 2; do echo "== isolated, BP_STAGES=$s"; BP_STAGES=$s timeout 60 python scripts/gpu_mc_probe.py quick 2>&1 | tail -7; done
 timeout 120 python scripts/gpu_pair_trace.py 2>&1 | head -150
 echo "== dX gap: operand layout vs epilogue"; timeout 120 python scripts/gpu_mc_probe.py dxgap 2>&1 | tail -14

@@ -17,6 +17,8 @@ timeout 200 python bench.py --e2e-raw > gpurun_out/r2_bench_C2.json 2> gpurun_ou
 echo "== 4. edge cases, fused update"
 timeout 200 python scripts/gpu_edge_cases.py 2>&1 | tail -24
 timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
+echo "== 4b. ReLU bit mask: bit parity + timing"
+timeout 300 python scripts/gpu_relu_mask_check.py 2>&1 | tail -24
 echo "== 5. reader bench (host / gpu reader, prefetch on / off)"
 timeout 400 python scripts/gpu_reader_bench.py 1500 2>&1 | tail -12
 echo "== 6. C5"
