@@ -1848,8 +1848,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
   long long a_rows, a_cols, b_rows, b_cols;
   bool amn, bmn;
   switch (kind) {
-    case 0: case 3: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
-    case 1: case 4: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
+    case 0: case 3: case 7: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
+    case 1: case 4: case 6: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
     case 2: a_rows = K; a_cols = M; b_rows = K; b_cols = N; amn = true; bmn = true; break;
     case 5: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
     default: return fail(BP_EINVAL, "bp_debug_gemm: kind %d", kind);
@@ -1858,6 +1858,8 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
                   dldaux = round_up(M, 32);
   float *dA = nullptr, *dB = nullptr, *dO = nullptr, *dBias = nullptr, *dAux = nullptr, *dAlo = nullptr,
         *dBlo = nullptr;
+  uint32_t* dMask = nullptr;  // kinds 6 / 7: ReLU bit mask, ceil(N/32) x dldo words
+  const long long mask_words = (long long)((N + 31) / 32) * dldo;
   cudaStream_t st;
   cudaEvent_t e0, e1;
   int rc = [&]() -> int {
@@ -1912,8 +1914,22 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     int reps = 1;
     if (const char* e = getenv("BP_DBG_REPS")) reps = std::max(1, atoi(e));
     const int sms = prop.multiProcessorCount;
-    if (kind == 0 && !bias) return fail(BP_EINVAL, "kind 0 needs bias");
-    if ((kind == 1 || kind == 5) && !aux) return fail(BP_EINVAL, "kind 1 / 5 needs aux (Y)");
+    if ((kind == 0 || kind == 7) && !bias) return fail(BP_EINVAL, "kind 0 / 7 needs bias");
+    if ((kind == 1 || kind == 5 || kind == 6) && !aux) return fail(BP_EINVAL, "kind 1 / 5 / 6 needs aux (Y)");
+    if (kind == 6 || kind == 7) {
+      CU_TRY(cudaMalloc(&dMask, mask_words * 4));
+      CU_TRY(cudaMemset(dMask, 0, mask_words * 4));
+      p.relu_mask = dMask;
+      p.ldmask = dldo;
+      p.act = 0;  // the mask is the ReLU derivative
+      if (kind == 6) {  // what the forward epilogue would have left for this Y
+        std::vector<uint32_t> hm((size_t)mask_words, 0u);
+        for (int n = 0; n < N; ++n)
+          for (int m = 0; m < M; ++m)
+            if (aux[(size_t)n * ldaux + m] > 0.0f) hm[(size_t)(n >> 5) * dldo + m] |= 1u << (n & 31);
+        CU_TRY(cudaMemcpy(dMask, hm.data(), mask_words * 4, cudaMemcpyHostToDevice));
+      }
+    }
     for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is an untimed warm-up when reps > 1
       if (rep == (reps > 1 ? 1 : 0)) CU_TRY(cudaEventRecord(e0, st));
       if (reps == 1 && rep == 1) break;
@@ -1924,6 +1940,9 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       // the dX epilogue
       else if (kind == 4) BP_TRY((launch_product(PROD_DX_PLAIN, st, sms, ma, mb, p, &mb64)));
       else if (kind == 5) BP_TRY((launch_product(PROD_FWD_DXEPI, st, sms, ma, mb, p, &mb64)));
+      // ReLU bit mask: the dX product reading the mask instead of Y / the forward product leaving the mask
+      else if (kind == 6) BP_TRY((launch_product(PROD_DX_MASK, st, sms, ma, mb, p, &mb64)));
+      else if (kind == 7) BP_TRY((launch_product(PROD_FWD_HID_MASK, st, sms, ma, mb, p, &mb64)));
       else BP_TRY((launch_product(PROD_DW, st, sms, ma, mb, p, &mb64)));
     }
     CU_TRY(cudaEventRecord(e1, st));
@@ -1933,6 +1952,22 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       *elapsed_ms /= (float)reps;
     }
     CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
+    if (kind == 7) {  // self-check: every bit of the mask the epilogue left equals (stored y > 0)
+      std::vector<uint32_t> hm((size_t)mask_words);
+      CU_TRY(cudaMemcpy(hm.data(), dMask, mask_words * 4, cudaMemcpyDeviceToHost));
+      for (int n = 0; n < N; ++n)
+        for (int m = 0; m < M; ++m) {
+          const bool bit = (hm[(size_t)(n >> 5) * dldo + m] >> (n & 31)) & 1u;
+          if (bit != (out[(size_t)n * ldo + m] > 0.0f))
+            return fail(BP_ECUDA, "kind 7: mask bit of (unit %d, frame %d) is %d but y = %g", m, n, (int)bit,
+                        out[(size_t)n * ldo + m]);
+        }
+      for (long long i = 0; i < mask_words; ++i) {  // bits of frames >= N stay clear
+        const int c = (int)(i / dldo);
+        const int valid = std::min(32, N - c * 32);
+        if (valid < 32 && (hm[(size_t)i] >> valid) != 0u) return fail(BP_ECUDA, "kind 7: mask bits set beyond frame %d", N);
+      }
+    }
     if (dtrace) {  // bring-up aid: print CTA 0's timeline of the last launch (cycles relative to kernel start)
       std::vector<long long> t(2048);
       CU_TRY(cudaMemcpy(t.data(), dtrace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -1950,6 +1985,7 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     return BP_OK;
   }();
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux); cudaFree(dAlo); cudaFree(dBlo);
+  cudaFree(dMask);
   return rc;
 }
 

@@ -209,7 +209,10 @@ int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame
  *  kind 2: dW   out[n*ldo+m] = sum_k D[k*ldd+m] * X[k*ldx+n]                            A=D (K x M), B=X (K x N)
  *  kind 3: plain fwd (no bias/activation).   act < 0 means "no activation" for kind 0.
  *  kind 4: kind 1's operands (A = W, M x K) with the plain epilogue;  kind 5: kind 0's operands (A = W, K x M) with
- *          kind 1's epilogue (act'(Y) * acc) — diagnostics that separate operand layout from epilogue cost. */
+ *          kind 1's epilogue (act'(Y) * acc) — diagnostics that separate operand layout from epilogue cost.
+ *  kind 6: kind 1 for ReLU with the bit mask of Y > 0 (built here from aux) instead of Y — must equal kind 1's output
+ *          bit for bit;  kind 7: kind 0 for ReLU that also leaves the mask; the call fails if any mask bit differs
+ *          from (out > 0) or a bit beyond frame N is set. */
 int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* out,
                   int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
                   float* elapsed_ms);
