@@ -97,3 +97,27 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
     log = open(f"{d}/o.log").read()
     assert "GPU trainer creation failed" in log and "no CPU fallback" in log
     assert os.path.getsize(f"{d}/o.wts") == 0                  # nothing was trained, nothing was written
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import, load, link or exec it (comments aside)."""
+    import re
+    pkg = os.path.join(ROOT, "dnn-for-speech-enhancement_b200")
+    pat = re.compile(r"libbporacle|oracle_py|bp_oracle|oracle/|import\s+oracle|from\s+oracle")
+    hits = []
+    for d, _dirs, files in os.walk(pkg):
+        if os.sep + "lib" in d or os.sep + "bin" in d or "__pycache__" in d:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cc", ".h", ".cu", ".cuh")) or f == "Makefile":
+                for i, line in enumerate(open(os.path.join(d, f), errors="ignore"), 1):
+                    if pat.search(line):
+                        hits.append(f"{f}:{i}: {line.strip()}")
+    assert not hits, hits
+    out = subprocess.run(["ldd", bp_lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def bp_lib_path():
+    import importlib
+    return importlib.import_module("dnn-for-speech-enhancement_b200").LIB_PATH
