@@ -5,7 +5,7 @@ A "step" is one bunch (minibatch) of spliced LPS frames through forward + back-p
 BASELINE.json: 2827 -> 2048x3 (ReLU) -> 257, bunch 1024 per GPU (weak scaling: global bunch = 1024 * N), synthetic
 frames, Glorot-initialised weights (Gen_rand_net scheme), lrate 1 (reference script), momentum 0.9.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C1|C2|C3|C4|C5]
   N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...` (one rank/GPU).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs in HBM before the timed region, CUDA
@@ -28,12 +28,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (layersizes, local bunch, dropoutflag, visible_omit, hid_omit, train?)
+    # name: (layersizes, local bunch, dropoutflag, visible_omit, hid_omit, train?)   [C1: sigmoid, see ACTIVATION]
+    "C1": ([257, 512, 257], 128, 0, 0.0, 0.0, False),   # BASELINE configs[0]: the CPU plumbing case, forward only
     "C2": ([2827, 2048, 2048, 2048, 257], 1024, 0, 0.0, 0.0, True),
     "C3": ([3084, 2048, 2048, 2048, 257], 2048, 1, 0.2, 0.2, True),
     "C4": ([2827, 2048, 2048, 2048, 2048, 2048, 257], 512, 0, 0.0, 0.0, True),
     "C5": ([2827, 2048, 2048, 2048, 257], 8192, 0, 0.0, 0.0, False),
 }
+
+
+ACTIVATION = {"C1": 1}   # 1 = sigmoid (the reference's commented variant, DevFunc.cu:52,62); everything else ReLU
 
 
 def flops_per_frame(sizes, train):
@@ -134,14 +138,14 @@ class CpuPort:
     bunch of `frames` frames (train: forward + back-prop + update; decode: forward).  TEST INFRASTRUCTURE used as the
     reported baseline only (cpu_baseline / --impl reference) — never on the product path."""
 
-    def __init__(self, sizes, frames, train, dropout=(0, 0.0, 0.0), pool=4):
+    def __init__(self, sizes, frames, train, dropout=(0, 0.0, 0.0), pool=4, activation=0):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_py as O
         w, b = glorot(sizes)
         self.frames, self.train, self.pool, self.i = frames, train, pool, 0
         self.x, self.t = synth(frames * pool, sizes[0], sizes[-1], seed=1)
         self.net = O.Net(sizes, frames, lrate=1.0, momentum=0.9, dropoutflag=dropout[0], visible_omit=dropout[1],
-                         hid_omit=dropout[2], weights=w, bias=b)
+                         hid_omit=dropout[2], activation=activation, weights=w, bias=b)
 
     def step(self):
         o = (self.i % self.pool) * self.frames
@@ -239,12 +243,13 @@ def main():
         print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU)", file=sys.stderr)
         return 2
     sizes, lb, dflag, vo, ho, train = WORKLOADS[args.workload]
+    act = ACTIVATION.get(args.workload, 0)
     K, W = args.steps, max(args.warmup, 3)
     gb = lb * world
     metric = "frames_per_sec"
     cfg = {"workload": f"{args.workload}: {'-'.join(map(str, sizes))} {'train (fwd+bwd+SGD)' if train else 'forward decode'}",
            "bunch_per_gpu": lb, "global_bunch": gb, "parallelism": f"dp{world}",
-           "dropout": [dflag, vo, ho], "l2_policy": "inputs larger than L2 (resident chunk cycles)",
+           "dropout": [dflag, vo, ho], "activation": "sigmoid" if act else "relu", "l2_policy": "inputs larger than L2 (resident chunk cycles)",
            "math": ("3xTF32 split-precision tensor-core products (fp32 storage, fp32 accumulate, ~fp32 accuracy)"
                     if args.math == "3xtf32" else "tf32 tensor-core products (fp32 storage, fp32 accumulate)")}
 
@@ -257,12 +262,12 @@ def main():
         budget_s = 150.0
         frames = lb
         cfg = dict(cfg, math="literal fp32 on the host cores (one fused multiply-add per term, ascending k)")
-        port = CpuPort(sizes, frames, train, (dflag, vo, ho))
+        port = CpuPort(sizes, frames, train, (dflag, vo, ho), activation=act)
         _, t1 = port.run(steps=1)          # first call: thread start-up, page faults
         _, t1 = port.run(steps=1)
         if (K + W) * t1 > budget_s and frames > 64:
             frames = max(64, int(frames * budget_s / ((K + W) * t1)) // 64 * 64)
-            port = CpuPort(sizes, frames, train, (dflag, vo, ho))
+            port = CpuPort(sizes, frames, train, (dflag, vo, ho), activation=act)
             port.run(steps=1)
         port.run(steps=max(0, W - 2))
         n, dt = port.run(steps=K)
@@ -295,7 +300,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w, b = glorot(sizes)
     g = bp.BP_GPU(1, len(sizes), sizes, gb, 1.0, 0.9, 0.0, w, b, dflag, vo, ho, seed=12345, device=local_rank,
-                  world_size=world, rank=rank,
+                  world_size=world, rank=rank, activation=act,
                   math_mode=bp.BP_MATH_3XTF32 if args.math == "3xtf32" else bp.BP_MATH_TF32)
     if world > 1:
         import torch
@@ -527,7 +532,7 @@ def main():
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2"}
     if not args.no_cpu_baseline and world == 1:
         try:
-            port = CpuPort(sizes, lb, train, (dflag, vo, ho))
+            port = CpuPort(sizes, lb, train, (dflag, vo, ho), activation=act)
             port.run(steps=1)                                  # thread start-up, page faults
             n, dt = port.run(min_seconds=10.0, max_steps=64)   # ~10 s of CPU work on all host cores
             line["cpu_baseline"] = {"value": n * lb / dt, "unit": "frames/s", "cores": host_cores(), "kind": "port",
