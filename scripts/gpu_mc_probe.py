@@ -34,14 +34,15 @@ def main():
         # which half of dX costs the extra ~6.5 us per launch: its operand majors (kind 4 = K-major A, plain epilogue)
         # or its epilogue (kind 5 = forward's MN-major A with the dX epilogue)?
         cases = [(k, n, M, N, K) for (M, N, K) in ((300, 700, 515), (2048, 1024, 257), (2048, 1024, 2048))
-                 for (k, n) in ((3, "fwd        "), (1, "dX         "), (4, "dX-A, plain"), (5, "fwd-A, dXep"))]
+                 for (k, n) in ((3, "fwd        "), (1, "dX         "), (4, "dX-A, plain"), (5, "fwd-A, dXep"),
+                                (6, "dX, bitmask"))]
     tag = f"PAIRS={os.environ.get('BP_PAIRS', '-')} MC={os.environ.get('BP_MC', '-')}"
     ok_all = True
     for kind, name, M, N, K in cases:
         if kind in (3, 5):
             A = rng.standard_normal((K, M), dtype=np.float32); B = rng.standard_normal((N, K), dtype=np.float32)
             ref = tr(B) @ tr(A)
-        elif kind in (1, 4):
+        elif kind in (1, 4, 6):
             A = rng.standard_normal((M, K), dtype=np.float32); B = rng.standard_normal((N, K), dtype=np.float32)
             ref = tr(B) @ tr(A).T
         else:
@@ -51,7 +52,7 @@ def main():
         aux = np.ones((N, M), dtype=np.float32)
         ms = C.c_float(0)
         rc = lib.bp_debug_gemm(kind, M, N, K, A.ctypes.data_as(fp), A.shape[1], B.ctypes.data_as(fp), B.shape[1],
-                               out.ctypes.data_as(fp), M, None, aux.ctypes.data_as(fp) if kind in (1, 5) else None, M,
+                               out.ctypes.data_as(fp), M, None, aux.ctypes.data_as(fp) if kind in (1, 5, 6) else None, M,
                                1.0, 0, 0, C.byref(ms))
         if rc != 0:
             print(f"[{tag}] {name} {M}x{N}x{K}: rc={rc} {lib.bp_last_error().decode()}", flush=True)
