@@ -150,3 +150,27 @@ def test_relu_mask_training_is_bit_identical(case):
     for l in range(1, len(sizes)):
         assert np.array_equal(res[0][0][l], res[1][0][l]) and np.array_equal(res[0][1][l], res[1][1][l]), f"layer {l}"
         assert not np.array_equal(res[0][0][l], w[l])   # it did train
+
+
+EDGE_CASES = [("bunch 37, ragged tail", [75, 96, 33], 37, 3 * 37 + 5, dict(lrate=0.7, momentum=0.9)),
+              ("bunch 1", [40, 24, 8], 1, 5, dict(lrate=0.1, momentum=0.5)),
+              ("one weight layer", [129, 65], 32, 96, dict(momentum=0.9)),
+              ("nine weight layers", [64, 72, 40, 96, 33, 80, 48, 56, 64, 20], 32, 64, dict(lrate=0.5)),
+              ("one output unit", [90, 70, 1], 32, 64, dict(momentum=0.9)),
+              ("chunk shorter than a bunch", [75, 96, 33], 64, 20, dict()),
+              ("weight cost, odd sizes", [257, 131, 67, 3], 40, 120, dict(lrate=0.5, momentum=0.9, weightcost=1e-3)),
+              ("sigmoid, odd sizes", [61, 45, 29], 24, 72, dict(activation=1, momentum=0.9))]
+
+
+@unproven
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_edge_shapes_against_the_oracle(case, fused):
+    """The shapes of scripts/gpu_edge_cases.py (odd and unit bunches, 1 and 9 weight layers, a 1-unit output, a chunk
+    shorter than a bunch = no-op like BP_GPU.cu:297-318, forward of 1 frame, CV of a ragged tail) against the
+    tf32-conditioned oracle, with the separate and the fused update."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import gpu_edge_cases as E
+    name, sizes, bunch, n_frames, kw = case
+    assert E.case(name, sizes, bunch, n_frames, fused, **kw)
