@@ -392,7 +392,7 @@ def main():
                "h2d_bytes_per_step": 4 * lb * (sizes[0] + sizes[-1]) * world, "d2h_bytes_per_step": 8 * world,
                "api": f"bp_train() on pinned host chunks of {e2e_cb} bunches + bp_train_losses()",
                "last_loss": float(losses[0]) / (lb * sizes[-1])}
-        if args.e2e_raw and world == 1 and sizes[0] == 257 * 11:
+        if args.e2e_raw and world == 1 and sizes[0] in (257 * 11, 257 * 12):   # 12 = with the NAT block (C3)
             # The same chunks fed the way BPtrain reader=gpu feeds them: raw big-endian records (feature + target
             # Pfiles) from pinned memory, splice / normalise on the device: ~1/6 of the H2D bytes.
             try:
@@ -403,8 +403,11 @@ def main():
                 for pa, scale in ((pf, 1.0), (ptg, 0.5)):
                     words = rng.standard_normal(pa.array.shape, dtype=np.float32) * np.float32(scale)
                     pa.array[:] = words.view(np.uint32).byteswap().view(np.float32)
-                raw = bp.RawChunk(fea_dim, ctx, ctx // 2, 0, pf.array, ptg.array, np.zeros(fea_dim, np.float32),
-                                  np.ones(fea_dim, np.float32), np.arange(n_s, dtype=np.int32))
+                nat = 1 if sizes[0] == fea_dim * (ctx + 1) else 0
+                frames = np.arange(n_s, dtype=np.int32)
+                raw = bp.RawChunk(fea_dim, ctx, ctx // 2, nat, pf.array, ptg.array, np.zeros(fea_dim, np.float32),
+                                  np.ones(fea_dim, np.float32), frames,
+                                  (frames // 300) * 300 if nat else None)   # "sentences" of 300 frames for the NAT mean
                 g.train_raw(raw)
                 barrier()
                 t0 = time.perf_counter()
