@@ -68,3 +68,44 @@ def test_reader_equals_live_reference_reader(seed):
                 xs, ts = splice_numpy(h, c)
                 assert np.array_equal(xs.view(np.uint32), x.view(np.uint32))
                 assert np.array_equal(ts.view(np.uint32), t.view(np.uint32))
+
+
+ERROR_CASES = {
+    "bad_range": ("train_sent_range", "5-2"), "range_beyond": ("train_sent_range", "0-99"),
+    "no_dash": ("cv_sent_range", "7"), "width_mismatch": ("layersizes", "1000,4,129"),
+    "missing_fea": ("fea_file", "/nonexistent.pfile"), "missing_norm": ("norm_file", "/nonexistent.norm"),
+    "missing_init": ("initwts_file", "/nonexistent.wts"), "missing_targ": ("targ_file", "/nonexistent.pfile"),
+}
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_reader_dump not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(ERROR_CASES))
+def test_error_paths_equal_live_reference(name):
+    """The reference's error convention is "message to stdout and/or the log, then exit(0)" (SURVEY.md §5): for every
+    bad input here the exit status, stdout and the log text must be the reference's, character for character."""
+    from reader_case import CASES
+    case = CASES["129"]
+    key, val = ERROR_CASES[name]
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, case)
+        got = {}
+        for tag, exe in (("ref", REF), ("ours", os.path.join(BIN, "reader_dump"))):
+            args = [a for a in reader_args(d, case) if not a.startswith(("log_file=", key + "="))]
+            args += [f"log_file={d}/{tag}.log", f"{key}={val}"]
+            p = subprocess.run([exe, f"{d}/{tag}.bin"] + args, cwd=d, capture_output=True, text=True, timeout=20)
+            log = open(f"{d}/{tag}.log").read() if os.path.exists(f"{d}/{tag}.log") else None
+            got[tag] = (p.returncode, p.stdout.replace(tag + ".", "X."), None if log is None else log.replace(tag + ".", "X."))
+    assert got["ours"] == got["ref"]
+    assert got["ours"][0] == 0   # "log + exit(0)"
+
+
+def test_malformed_argument_exits_cleanly():
+    """An argument without '=': the reference writes to its not-yet-opened log and crashes (SIGSEGV); ours reports the
+    format error and exits 0 like every other error path."""
+    from reader_case import CASES
+    case = CASES["129"]
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, case)
+        p = subprocess.run([os.path.join(BIN, "reader_dump"), f"{d}/o.bin"] + reader_args(d, case) + ["oops"], cwd=d,
+                           capture_output=True, text=True, timeout=20)
+    assert p.returncode == 0 and "Format Error" in p.stdout + p.stderr
