@@ -3,7 +3,7 @@ lengths 1..69, so sentences shorter than the context, chunks cut mid-sentence, e
 offsets, narrow and wide targets) go through oracle/_ref/ref_reader_dump (unmodified /root/reference/Interface.cc behind
 tests/native/reader_dump.cc, built by oracle/build_ref.sh) and through ours — serial loop, prefetch thread, and the
 device reader's tables replayed in numpy — and every byte of every chunk must agree.  340 such cases were run when
-this was written (331 identical; in the other 9 the reference never returns — its chunk planner spins when a chunk is
+this was written, plus 200 with other context widths (all identical where the reference terminates; in 16 it never returns — its chunk planner spins when a chunk is
 exactly full at a boundary, Interface.cc:607-614 — and ours terminates).  A seeded subset runs here.  Skipped where the
 reference binary is absent."""
 import os
@@ -26,13 +26,21 @@ def random_case(seed):
     ns = int(rng.integers(3, 14))
     lens = [int(rng.integers(1, 70)) for _ in range(ns)]
     split = int(rng.integers(1, ns - 1))
+    # seeds >= 200: other context widths too.  Only >= 6: with a shorter context a sentence of fewer than six frames
+    # yields samples, and the reference's NAT mean then reads past its record buffer (stale memory; 13 of 150 such
+    # cases differed from ours in exactly those NAT elements and nowhere else) — ours counts those frames as 0.
+    ctx = 11 if seed < 200 else int(rng.choice([6, 7, 15, 21]))
+    if seed >= 200:
+        return dict(dim=129, out=int(rng.choice([129, 5])), ctx=ctx, off=int(rng.integers(0, ctx)), nat=1, seed=seed,
+                    lens=lens, traincache=int(rng.choice([9, 25, 64, 1000])), train=f"0-{split - 1}",
+                    cv=f"{split}-{ns - 1}", rseed=int(rng.integers(0, 1000)), hidden=3)
     return dict(dim=129, out=int(rng.choice([129, 7, 40])), ctx=11, off=int(rng.integers(0, 11)), nat=1, seed=seed,
                 lens=lens, traincache=int(rng.choice([5, 13, 40, 100, 1000])), train=f"0-{split - 1}",
                 cv=f"{split}-{ns - 1}", rseed=int(rng.integers(0, 1000)), hidden=3)
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_reader_dump not built (needs /root/reference)")
-@pytest.mark.parametrize("seed", list(range(100, 124)) + [3, 47])   # 3 and 47: the reference hangs
+@pytest.mark.parametrize("seed", list(range(100, 124)) + list(range(200, 212)) + [3, 47])   # 3, 47: the reference hangs
 def test_reader_equals_live_reference_reader(seed):
     for exe in ("reader_dump", "prefetch_dump", "raw_dump"):
         if not os.path.exists(os.path.join(BIN, exe)):
