@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--chunk-bunches", type=int, default=32, help="bunches resident per chunk (inputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", action="store_true",
+                    help="train workloads: add the dominant product's in-place launch duration (bp_get_timeline)")
     ap.add_argument("--e2e-raw", action="store_true",
                     help="train workloads, 1 GPU: also time bp_train_raw() fed with raw Pfile records (device reader)")
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"],
@@ -370,6 +372,24 @@ def main():
         prof, nprof = g.profile()
         g.set_profiling(False)
 
+    # ---- optional: launch timeline (an event behind every launch, 16 bunches): the dominant product in place
+    tl = None
+    if train and args.timeline and len(sizes) > 3:
+        try:
+            g.set_timeline(True)
+            run_resident(16)
+            marks, nb_tl = g.timeline()
+            g.set_timeline(False)
+            done_at = dict(marks)
+            if nb_tl > 0 and "fwd1" in done_at and "fwd2" in done_at:
+                us = (done_at["fwd2"] - done_at["fwd1"]) * 1e3
+                tl = {"product": f"forward affine {sizes[2]} units x {lb} frames x {sizes[1]} fan-in, in place "
+                                 "(completion of fwd2 minus completion of fwd1; no PDL overlap across the marks)",
+                      "us_per_launch": us, "tflops": 2.0 * sizes[2] * lb * sizes[1] / (us * 1e-6) / 1e12,
+                      "bunches": nb_tl, "launch_done_at_us": {k: round(v * 1e3, 2) for k, v in marks}}
+        except Exception as e:   # a measurement aid must not hide the bench line
+            tl = {"error": str(e)}
+
     # ---- e2e: bp_train() from pinned host buffers, one chunk of `e2e_cb` bunches per call, loss read back per step
     e2e_cb = 8
     e2e = None
@@ -506,6 +526,10 @@ def main():
                             "traffic": traffic.get("gemm_dram_bytes_per_bunch") if args.workload == "C2" else None,
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2 (kind::tf32 issues at half the bf16 rate)",
                             "per_class_ms": {k: v / nprof for k, v in prof.items()}}
+        if tl is not None:
+            if "tflops" in tl:
+                tl["frac"] = tl["tflops"] / tf32_peak
+            line["roofline"]["dominant_kernel_in_place"] = tl
         if world == 1 and len(sizes) > 3:
             try:
                 iso = isolated_dominant_gemm(bp, sizes, lb)
