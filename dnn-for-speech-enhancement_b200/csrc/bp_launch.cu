@@ -336,6 +336,31 @@ int launch_out_finish(cudaStream_t st, const float* ws, long long ldw, const Gem
 extern "C" {
 using namespace bp;
 
+// Host-only: which kernel launch_product would pick for an M x N x K product and what its launch looks like — the
+// selection rule of pick_kernel made inspectable without a GPU (tests/test_launch_plan.py pins the plans of the
+// BASELINE configs).  max_pairs = co-resident CTA pairs to assume (<= 0: num_sms / 2).
+int bp_debug_plan(int M, int N, int K, int have_b64, int num_sms, int max_pairs, int* pair_n, int* tiles, int* ctas,
+                  int* k_blocks) {
+  if (M <= 0 || N <= 0 || K <= 0 || num_sms <= 0 || !pair_n || !tiles || !ctas || !k_blocks)
+    return fail(BP_EINVAL, "bp_debug_plan: bad argument");
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  const KernelChoice k = pick_kernel(p, num_sms, have_b64 != 0);
+  *pair_n = k.pair_n;
+  *k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  if (k.pair_n == 0) {
+    *tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + kBlockN - 1) / kBlockN);
+    *ctas = std::min(*tiles, num_sms);
+  } else {
+    const int pairs = max_pairs > 0 ? std::min(max_pairs, num_sms / 2) : num_sms / 2;
+    *tiles = ((M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * ((N + k.pair_n - 1) / k.pair_n);
+    *ctas = 2 * std::min(*tiles, pairs);
+  }
+  return BP_OK;
+}
+
 // Bring-up aid: cycles per 128 x bn x 8 TF32 MMA (issue, issue+drain) on one SM; combo 0 = A MN/B K, 1 = K/K, 2 = MN/MN,
 // 3 = K/MN.  mode bit 0: fence before each group of 8, bit 1: commit after each group.
 int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total) {

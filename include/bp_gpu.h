@@ -203,6 +203,12 @@ int bp_comm_init(bp_handle* h, const char id128[128]);
  * exposed so tests can replay masks against the oracle.  Returns 1 = dropped, 0 = kept. */
 int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame, uint32_t unit, float p);
 
+/* Host-only (no GPU needed): the kernel the library would pick for an M x N x K product on a device with num_sms SMs —
+ * *pair_n = 0 (128 x 128 tiles on lone CTAs), 128 or 256 (256 x pair_n tiles on CTA pairs) — the number of output
+ * tiles, the CTAs launched (persistent, <= one per SM) and the 64-deep k-blocks per tile.  have_b64: the B operand
+ * also has a 64-row-box tensor map (hidden-layer forward and dX products); max_pairs <= 0 assumes num_sms / 2. */
+int bp_debug_plan(int M, int N, int K, int have_b64, int num_sms, int max_pairs, int* pair_n, int* tiles, int* ctas,
+                  int* k_blocks);
 /* Stand-alone launch of one fused GEMM (host operands, testing only).
  *  kind 0: fwd  out[n*ldo+m] = act(scale * sum_k W[k*ldw+m] * X[n*ldx+k] + bias[m])     A=W (K x M), B=X (N x K)
  *  kind 1: dX   out[n*ldo+m] = act'(Y[n*ldy+m]) * sum_k W[m*ldw+k] * D[n*ldd+k]         A=W (M x K), B=D (N x K)
