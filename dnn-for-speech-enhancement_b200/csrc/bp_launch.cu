@@ -268,6 +268,14 @@ inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64)
   const int n = p.N - p.n_begin;
   if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return {256, cp};
   if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return {128, cp};
+  // BP_SMALL_PAIRS=1 (off by default, not yet run on a GPU): when the unit count is a multiple of 256 a 128-wide pair
+  // tile is exactly two lone-CTA tiles — the same number of CTAs at the higher shared-memory roof (67 % against 50 %)
+  // — so small products (C4's 512 frames per GPU, the reference script's bunch 128) need not fall back to lone CTAs.
+  static const int small_pairs = [] {
+    const char* e = getenv("BP_SMALL_PAIRS");
+    return e ? atoi(e) : 0;
+  }();
+  if (small_pairs && have_b64 && p.M % (2 * GEMM_BLOCK_M) == 0 && n >= 128) return {128, cp};
   return {0, 1};
 }
 

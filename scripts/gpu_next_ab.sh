@@ -14,3 +14,4 @@ for s in 0 2; do echo "== isolated, BP_STAGES=$s"; BP_STAGES=$s timeout 60 pytho
 timeout 120 python scripts/gpu_pair_trace.py 2>&1 | head -150
 echo "== dX gap: operand layout vs epilogue"; timeout 120 python scripts/gpu_mc_probe.py dxgap 2>&1 | tail -14
 echo "== launch timeline of a bunch (default, then with the L2 switches)"; for e in "BP_X=0" "BP_L2_PREFETCH=8" "BP_L2_PERSIST=64" "BP_FUSED_UPDATE=1"; do echo "-- $e"; env $e timeout 120 python scripts/gpu_timeline.py C2 2>&1 | tail -22; done
+echo "== C4 (512 frames per GPU, 6 weight layers): lone CTAs vs 128-wide pairs for small products"; for e in "BP_X=0" "BP_SMALL_PAIRS=1" "BP_X=0" "BP_SMALL_PAIRS=1"; do echo "-- $e"; env $e timeout 120 python bench.py --workload C4 --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],4), {k:round(v,4) for k,v in d['roofline']['per_class_ms'].items()})"; done
