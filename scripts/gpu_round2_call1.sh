@@ -6,7 +6,7 @@
 #   4. edge cases + fused-update bit parity     -> promote scripts/gpu_edge_cases.py cases into tests/ if green
 #   5. reader throughput end to end from Pfiles (host reader on all cores, chunk prefetch, upload wait deferred)
 #   6. C5 line with the raw-records e2e
-# usage: gpurun --timeout 900 -- 'bash scripts/gpu_round2_call1.sh 2>&1 | tee gpurun_out/r2_call1.log'
+# usage: gpurun --timeout 1200 -- 'bash scripts/gpu_round2_call1.sh 2>&1 | tee gpurun_out/r2_call1.log'
 mkdir -p gpurun_out
 echo "== 1. pytest -m gpu (as the driver runs it), then the gated tests of never-run code paths"
 timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
