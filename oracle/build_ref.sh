@@ -11,6 +11,7 @@
 #   oracle/_ref/BPtrain_ref    the reference CLI (HEAD semantics: ReLU, NAT block with the literal 129)
 #   oracle/_ref/ref_reader_dump  tests/native/reader_dump.cc linked against the reference's Interface.o (host only)
 #   oracle/_ref/ref_weights_dump  tests/native/weights_dump.cc linked against the reference's Interface.o (host only)
+#   oracle/_ref/BPtrain_shim  the reference's BPtrain.cc + Interface.cc + host/BP_GPU_shim.cc + OUR libbpgpu.so
 #   oracle/_ref/ref_harness    oracle/ref_harness.cc (ours) linked against the reference's BP_GPU.o / DevFunc.o:
 #                              drives class BP_GPU directly on binary blobs (no Pfile plumbing) and times train().
 set -euo pipefail
@@ -36,4 +37,15 @@ g++ -O2 -w -I/usr/local/cuda/include -I"$REF" "$HERE/../tests/native/reader_dump
       -o "$OUT/ref_reader_dump"
 g++ -O2 -w -I/usr/local/cuda/include -I"$REF" "$HERE/../tests/native/weights_dump.cc" "$TMP/Interface.o" \
       -o "$OUT/ref_weights_dump"
+# the reference's unmodified main() and Interface with OUR trainer behind its class BP_GPU: the
+# binding dnn-for-speech-enhancement_b200/host/BP_GPU_shim.cc compiled against the reference's BP_GPU.h, linked with
+# libbpgpu.so instead of BP_GPU.o / DevFunc.o / cuBLAS / cuRAND.  Proves the C-ABI covers the reference's call sites.
+LIB="$HERE/../dnn-for-speech-enhancement_b200/lib"
+if [ -f "$LIB/libbpgpu.so" ]; then
+  g++ -O2 -w -I/usr/local/cuda/include -I"$REF" -c "$REF/BPtrain.cc" -o "$TMP/BPtrain_host.o"
+  g++ -O2 -w -I/usr/local/cuda/include -I"$REF" -I"$HERE/../include" \
+      -c "$HERE/../dnn-for-speech-enhancement_b200/host/BP_GPU_shim.cc" -o "$TMP/BP_GPU_shim.o"
+  g++ -o "$OUT/BPtrain_shim" "$TMP/BPtrain_host.o" "$TMP/Interface.o" "$TMP/BP_GPU_shim.o" \
+      -L"$LIB" -lbpgpu -Wl,-rpath,'$ORIGIN/../../dnn-for-speech-enhancement_b200/lib'
+fi
 echo "built: $(ls "$OUT")"

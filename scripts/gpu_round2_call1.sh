@@ -10,7 +10,7 @@
 mkdir -p gpurun_out
 echo "== 1. pytest -m gpu (as the driver runs it), then the gated tests of never-run code paths"
 timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
-BP_TEST_UNPROVEN=1 timeout 300 python -m pytest tests/test_zz_late_round1.py -q -m gpu 2>&1 | tail -8
+BP_TEST_UNPROVEN=1 timeout 400 python -m pytest tests/test_zz_late_round1.py tests/test_shim.py -q -m gpu 2>&1 | tail -8
 echo "== 2. smoke"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== 3. default bench"
