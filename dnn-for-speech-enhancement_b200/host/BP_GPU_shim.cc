@@ -2,7 +2,7 @@
 // reference's class BP_GPU (declared in the reference's own, unmodified BP_GPU.h:40-88) on top of libbpgpu's C-ABI
 // (include/bp_gpu.h).  Compiled against the reference's header and linked with the reference's unmodified BPtrain.cc
 // and Interface.cc in place of BP_GPU.cu / DevFunc.cu, it yields the reference's binary with the B200 trainer behind it
-// (oracle/build_ref.sh builds exactly that as oracle/_ref/BPtrain_shim; tests/test_shim.py).
+// (the test infrastructure's reference build recipe produces exactly that binary; tests/test_shim.py).
 //
 // Nothing of the reference is copied here: this file only defines the member functions the reference declares.
 #include <cstdio>
