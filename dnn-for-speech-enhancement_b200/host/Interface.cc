@@ -33,11 +33,11 @@ inline int be_int(const float* p) {
   return static_cast<int>(bswap32(u));
 }
 
-// Static split of [0, n) over the host threads (at most 16, at least `grain` items each); fn(begin, end).
+// Static split of [0, n) over the host threads (at most 32, at least `grain` items each); fn(begin, end).
 template <class Fn>
 void parallel_for(int n, int grain, Fn fn) {
   const int hw = static_cast<int>(std::thread::hardware_concurrency());
-  const int t = std::max(1, std::min({hw > 0 ? hw : 1, 16, n / std::max(1, grain)}));
+  const int t = std::max(1, std::min({hw > 0 ? hw : 1, 32, n / std::max(1, grain)}));
   if (t == 1) {
     fn(0, n);
     return;
