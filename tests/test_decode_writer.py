@@ -54,3 +54,30 @@ def test_raw_output_and_denormalisation():
         den = np.fromfile(_run(d, "raw", os.path.join(d, "out.norm"), dim, n_sent), dtype="<f4").reshape(-1, dim)
     assert np.array_equal(plain, rows)
     assert np.array_equal(den, (rows / inv_std + mean).astype(np.float32))
+
+
+def test_reference_parser_reads_the_decode_pfile():
+    """The Pfile the decode writer produces goes through the REFERENCE's own Pfile parser and reader (unmodified
+    Interface.cc behind oracle/_ref/ref_reader_dump): same frame / sentence counts — the empty sentence included — and
+    the rows it hands out are the rows our reader hands out, byte for byte."""
+    import pytest
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_reader_dump")
+    ours = os.path.join(PKG, "bin", "reader_dump")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/ref_reader_dump not built (needs /root/reference)")
+    dim, n_sent = 129, 8
+    with tempfile.TemporaryDirectory() as d:
+        pf = _run(d, "pfile", None, dim, n_sent)
+        T.write_norm(os.path.join(d, "n.norm"), np.zeros(dim, np.float32), np.ones(dim, np.float32))
+        args = [f"fea_file={pf}", f"norm_file={d}/n.norm", f"targ_file={pf}", f"outwts_file={d}/o.wts", "initwts_file=",
+                "train_sent_range=0-5", "cv_sent_range=6-7", f"fea_dim={dim}", "fea_context=1", "targ_offset=0",
+                "traincache=1000", "bunchsize=8", f"layersizes={2 * dim},3,{dim}", "gpu_used=1", "init_randem_seed=1",
+                "momentum=0.5", "weightcost=0", "lrate=1", "dropoutflag=0", "visible_omit=0", "hid_omit=0"]
+        out = {}
+        for tag, exe in (("ref", ref), ("ours", ours)):
+            subprocess.run([exe, f"{d}/{tag}.bin"] + args + [f"log_file={d}/{tag}.log"], check=True, timeout=60,
+                           stdout=subprocess.DEVNULL)
+            out[tag] = (open(f"{d}/{tag}.bin", "rb").read(), [l for l in open(f"{d}/{tag}.log") if l.startswith("Get")])
+    frames = sum(3 + s for s in range(n_sent) if s != 1)
+    assert f"Get pfile info over: Training data has {frames} frames, {n_sent} sentences.\n" in out["ref"][1]
+    assert out["ours"] == out["ref"]
