@@ -65,13 +65,13 @@ def test_reference_parser_reads_the_decode_pfile():
     ours = os.path.join(PKG, "bin", "reader_dump")
     if not os.path.exists(ref):
         pytest.skip("oracle/_ref/ref_reader_dump not built (needs /root/reference)")
-    dim, n_sent = 129, 8
+    dim, n_sent = 129, 24   # sentences of 3 .. 26 frames: with an 11-frame context some yield samples, some none
     with tempfile.TemporaryDirectory() as d:
         pf = _run(d, "pfile", None, dim, n_sent)
         T.write_norm(os.path.join(d, "n.norm"), np.zeros(dim, np.float32), np.ones(dim, np.float32))
         args = [f"fea_file={pf}", f"norm_file={d}/n.norm", f"targ_file={pf}", f"outwts_file={d}/o.wts", "initwts_file=",
-                "train_sent_range=0-5", "cv_sent_range=6-7", f"fea_dim={dim}", "fea_context=1", "targ_offset=0",
-                "traincache=1000", "bunchsize=8", f"layersizes={2 * dim},3,{dim}", "gpu_used=1", "init_randem_seed=1",
+                "train_sent_range=0-19", "cv_sent_range=20-23", f"fea_dim={dim}", "fea_context=11", "targ_offset=5",
+                "traincache=1000", "bunchsize=8", f"layersizes={12 * dim},3,{dim}", "gpu_used=1", "init_randem_seed=1",
                 "momentum=0.5", "weightcost=0", "lrate=1", "dropoutflag=0", "visible_omit=0", "hid_omit=0"]
         out = {}
         for tag, exe in (("ref", ref), ("ours", ours)):
