@@ -11,6 +11,7 @@
 #   oracle/_ref/BPtrain_ref    the reference CLI (HEAD semantics: ReLU, NAT block with the literal 129)
 #   oracle/_ref/ref_reader_dump  tests/native/reader_dump.cc linked against the reference's Interface.o (host only)
 #   oracle/_ref/ref_weights_dump  tests/native/weights_dump.cc linked against the reference's Interface.o (host only)
+#   oracle/_ref/ref_harness_shim  oracle/ref_harness.cc + host/BP_GPU_shim.cc + OUR libbpgpu.so (same driver, our trainer)
 #   oracle/_ref/BPtrain_shim  the reference's BPtrain.cc + Interface.cc + host/BP_GPU_shim.cc + OUR libbpgpu.so
 #   oracle/_ref/ref_harness    oracle/ref_harness.cc (ours) linked against the reference's BP_GPU.o / DevFunc.o:
 #                              drives class BP_GPU directly on binary blobs (no Pfile plumbing) and times train().
@@ -47,5 +48,11 @@ if [ -f "$LIB/libbpgpu.so" ]; then
       -c "$HERE/../dnn-for-speech-enhancement_b200/host/BP_GPU_shim.cc" -o "$TMP/BP_GPU_shim.o"
   g++ -o "$OUT/BPtrain_shim" "$TMP/BPtrain_host.o" "$TMP/Interface.o" "$TMP/BP_GPU_shim.o" \
       -L"$LIB" -lbpgpu -Wl,-rpath,'$ORIGIN/../../dnn-for-speech-enhancement_b200/lib'
+  # ... and the blob harness over the same binding: class BP_GPU driven exactly like ref_harness drives the reference's,
+  # so that scripts/gpu_ref_gpu_timing.py times both implementations through one and the same C++ interface
+  g++ -O2 -w -I/usr/local/cuda/include -I"$REF" -c "$HERE/ref_harness.cc" -o "$TMP/ref_harness_host.o"
+  g++ -o "$OUT/ref_harness_shim" "$TMP/ref_harness_host.o" "$TMP/BP_GPU_shim.o" -L"$LIB" -lbpgpu \
+      -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$ORIGIN/../../dnn-for-speech-enhancement_b200/lib' \
+      -Wl,-rpath,/usr/local/cuda/lib64
 fi
 echo "built: $(ls "$OUT")"

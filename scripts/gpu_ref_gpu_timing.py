@@ -33,9 +33,21 @@ def main():
         r = subprocess.run([H, fin, fout], capture_output=True, text=True, timeout=900, cwd=d)
         print(r.stdout.strip(), r.stderr.strip()[-300:])
         raw = np.fromfile(fout, dtype="<f4")
-    ms = float(raw[-1])
-    print(f"REF-GPU (reference CUDA path, cuBLAS FP32, B200): {n} frames in {ms:.2f} ms -> {n / (ms * 1e-3):.0f} frames/s "
-          f"({ms / nb * 1e3:.1f} us per bunch of {bunch}, H2D of the chunk included)")
+        ms = float(raw[-1])
+        print(f"REF-GPU (reference CUDA path, cuBLAS FP32, B200): {n} frames in {ms:.2f} ms -> {n / (ms * 1e-3):.0f} "
+              f"frames/s ({ms / nb * 1e3:.1f} us per bunch of {bunch}, H2D of the chunk included)")
+        # the same driver, the same class interface, the same pageable host buffers — our trainer behind the binding
+        # of INTEGRATION.md B (oracle/_ref/ref_harness_shim)
+        hs = H + "_shim"
+        if os.path.exists(hs):
+            r = subprocess.run([hs, fin, fout], capture_output=True, text=True, timeout=900, cwd=d)
+            print(r.stdout.strip(), r.stderr.strip()[-300:])
+            ours = np.fromfile(fout, dtype="<f4")
+            ms2 = float(ours[-1])
+            rel = float(np.linalg.norm(ours[:-2].astype(np.float64) - raw[:-2]) / np.linalg.norm(raw[:-2]))
+            print(f"OURS through class BP_GPU (BP_GPU_shim.cc, TF32): {n} frames in {ms2:.2f} ms -> "
+                  f"{n / (ms2 * 1e-3):.0f} frames/s ({ms2 / nb * 1e3:.1f} us per bunch, pageable H2D included): "
+                  f"{ms / ms2:.1f}x; weights after training differ by {rel:.2e} (relative Frobenius norm)")
 
 
 if __name__ == "__main__":

@@ -22,5 +22,7 @@ echo "== 4b. ReLU bit mask: bit parity + timing"
 timeout 300 python scripts/gpu_relu_mask_check.py 2>&1 | tail -24
 echo "== 5. reader bench (host / gpu reader, prefetch on / off)"
 timeout 400 python scripts/gpu_reader_bench.py 1500 2>&1 | tail -12
+echo "== 5b. the reference's class BP_GPU, both implementations behind it (reference CUDA path vs ours through the shim)"
+timeout 300 python scripts/gpu_ref_gpu_timing.py 16 2>&1 | tail -5
 echo "== 6. C5"
 timeout 200 python bench.py --workload C5 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r2_bench_C5.json 2> gpurun_out/r2_bench_C5.err; cut -c1-2500 gpurun_out/r2_bench_C5.json; tail -3 gpurun_out/r2_bench_C5.err
