@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_decode_raw_submit.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp]
     lib.bp_decode_raw_wait.argtypes = [C.c_void_p]
+    lib.bp_forward_submit.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
+    lib.bp_forward_wait.argtypes = [C.c_void_p]
     lib.bp_crossvalid_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp, _fp]
     lib.bp_download_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp]
     lib.bp_host_alloc.argtypes = [C.c_size_t]
@@ -324,6 +326,17 @@ class BP_GPU:
 
     def decode_raw_wait(self) -> None:
         _check(load_library().bp_decode_raw_wait(self._h), "bp_decode_raw_wait")
+
+    def forward_submit(self, n_frames: int, indata: np.ndarray, out: np.ndarray) -> None:
+        """Pipelined bp_forward (bp_forward_submit): spliced rows in, `out` complete after the matching forward_wait();
+        at most two chunks in flight.  Both arrays float32 C-contiguous (PinnedArray for asynchronous copies)."""
+        if indata.dtype != np.float32 or out.dtype != np.float32 or not indata.flags["C_CONTIGUOUS"] \
+                or not out.flags["C_CONTIGUOUS"] or out.size < n_frames * self.layersizes[-1]:
+            raise ValueError("forward_submit: float32 C-contiguous arrays, out >= n_frames x layersizes[-1]")
+        _check(load_library().bp_forward_submit(self._h, int(n_frames), _ptr(indata), _ptr(out)), "bp_forward_submit")
+
+    def forward_wait(self) -> None:
+        _check(load_library().bp_forward_wait(self._h), "bp_forward_wait")
 
     def download_chunk(self, first_row: int, n_rows: int, want_targ: bool = True):
         x = np.empty((n_rows, self.layersizes[0]), dtype=np.float32)

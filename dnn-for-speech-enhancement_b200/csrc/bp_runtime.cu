@@ -1254,12 +1254,14 @@ int rank_forward_resident(Rank* r, int first_frame, int n_frames, float* out_hos
 // return once the records have left the caller's buffers; at most two chunks in flight.  The chunk buffers are
 // double-buffered already (upload of chunk k+1 beside the forward pass of chunk k); what this adds is a second output
 // slot and a D2H stream, so that no stage of chunk k+1 waits for the host to have collected chunk k.
-int rank_decode_submit(Rank* r, const bp_raw_chunk* rc, float* out_host) {
+// rc != null: raw records (splice on the device); rc == null: n_rows spliced, normalised rows at `rows` (bp_forward's
+// input), for callers that keep the reference's host reader.
+int rank_decode_submit(Rank* r, const bp_raw_chunk* rc, int n_rows, const float* rows, float* out_host) {
   CU_TRY(cudaSetDevice(r->cfg.device));
   if (r->dec_inflight >= 2)
-    return fail(BP_EINVAL, "bp_decode_raw_submit: two chunks already in flight, call bp_decode_raw_wait first");
+    return fail(BP_EINVAL, "decode submit: two chunks already in flight, call the matching wait first");
   Rank::DecodeSlot& ds = r->dec[r->dec_head];
-  const int n = rc->n_samples, no = r->Nout();
+  const int n = rc ? rc->n_samples : n_rows, no = r->Nout();
   if (!r->d2h) CU_TRY(cudaStreamCreateWithFlags(&r->d2h, cudaStreamNonBlocking));
   if (!ds.fwd_done) CU_TRY(cudaEventCreateWithFlags(&ds.fwd_done, cudaEventDisableTiming));
   if (!ds.out_done) CU_TRY(cudaEventCreateWithFlags(&ds.out_done, cudaEventDisableTiming));
@@ -1270,7 +1272,9 @@ int rank_decode_submit(Rank* r, const bp_raw_chunk* rc, float* out_host) {
     CU_TRY(cudaMalloc(&ds.out_dev, size_t(n) * no * 4));
     ds.cap_rows = n;
   }
-  BP_TRY(rank_upload_raw(r, rc, true));  // returns when the records are on the device; `compute` waits for the rows
+  // both return when the caller's buffers have been consumed; `compute` waits for the rows
+  if (rc) BP_TRY(rank_upload_raw(r, rc, true));
+  else BP_TRY(rank_upload(r, n, rows, nullptr));
   ChunkBuf& c = r->chunk[r->cur];
   const int B = r->cfg.bunchsize;
   for (int i = 0; i < n; i += B)
@@ -1289,7 +1293,7 @@ int rank_decode_submit(Rank* r, const bp_raw_chunk* rc, float* out_host) {
 // Host wait for the oldest chunk in flight: its enhanced frames are complete in the `out` given at submit time.
 int rank_decode_wait(Rank* r) {
   CU_TRY(cudaSetDevice(r->cfg.device));
-  if (r->dec_inflight <= 0) return fail(BP_EINVAL, "bp_decode_raw_wait: no chunk in flight");
+  if (r->dec_inflight <= 0) return fail(BP_EINVAL, "decode wait: no chunk in flight");
   const int oldest = (r->dec_head + 2 - r->dec_inflight) & 1;
   CU_TRY(cudaEventSynchronize(r->dec[oldest].out_done));
   r->dec_inflight--;
@@ -1539,8 +1543,15 @@ int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* rc, float* sum_sq_err, f
 int bp_decode_raw_submit(bp_handle* h, const bp_raw_chunk* rc, float* out) {
   BP_TRY(check_raw_chunk(h, rc));
   if (!out) return fail(BP_EINVAL, "bp_decode_raw_submit: null output buffer");
-  return rank_decode_submit(h->ranks[0], rc, out);  // device 0 only, like bp_crossvalid
+  return rank_decode_submit(h->ranks[0], rc, 0, nullptr, out);  // device 0 only, like bp_crossvalid
 }
+
+int bp_forward_submit(bp_handle* h, int n_frames, const float* in, float* out) {
+  if (!h || !in || !out || n_frames <= 0) return fail(BP_EINVAL, "bp_forward_submit: bad argument");
+  return rank_decode_submit(h->ranks[0], nullptr, n_frames, in, out);
+}
+
+int bp_forward_wait(bp_handle* h) { return bp_decode_raw_wait(h); }
 
 int bp_decode_raw_wait(bp_handle* h) {
   if (!h) return fail(BP_EINVAL, "null handle");

@@ -161,6 +161,11 @@ int bp_crossvalid_raw(bp_handle* h, const bp_raw_chunk* chunk, float* sum_sq_err
  * upload of k+1, forward of k+1 and the read-back of k overlap.  Device 0 only; no targets needed. */
 int bp_decode_raw_submit(bp_handle* h, const bp_raw_chunk* chunk, float* out);
 int bp_decode_raw_wait(bp_handle* h);
+/* The same pipeline for callers that keep the reference's host reader: `in` = n_frames spliced, normalised rows (what
+ * bp_forward / BP_GPU::CrossValid take, BP_GPU.cu:408-479).  Shares the two in-flight slots with the raw variant;
+ * bp_forward_submit returns when `in` may be refilled, bp_forward_wait when the oldest chunk's `out` is complete. */
+int bp_forward_submit(bp_handle* h, int n_frames, const float* in, float* out);
+int bp_forward_wait(bp_handle* h);
 /* Reads rows of the resident chunk back (tests: bit-exactness of the device reader).  Single-rank handles. */
 int bp_download_chunk(bp_handle* h, int first_row, int n_rows, float* in /* may be NULL */,
                       float* targ /* may be NULL */);

@@ -43,6 +43,29 @@ def test_decode_raw_equals_forward_on_host_assembled_rows():
 
 
 @unproven
+def test_pipelined_forward_of_spliced_rows():
+    """bp_forward_submit / bp_forward_wait (the pipeline for callers that keep the host reader) == bp_forward."""
+    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
+    case = CASES["129b"]
+    h, chunks = run_raw_dump(case)
+    chunks = [c for c in chunks if c["n_samples"] > 0]
+    g, _, _ = _net(bp, case, 16)
+    xs = [np.ascontiguousarray(splice_numpy(h, c)[0]) for c in chunks]
+    want = [g.forward(x.shape[0], x) for x in xs]
+    outs = [bp.PinnedArray((x.shape[0], case["out"])) for x in xs]
+    g.forward_submit(xs[0].shape[0], xs[0], outs[0].array)
+    for k in range(1, len(xs)):
+        g.forward_submit(xs[k].shape[0], xs[k], outs[k].array)
+        g.forward_wait()
+        assert np.array_equal(outs[k - 1].array, want[k - 1])
+    g.forward_wait()
+    assert np.array_equal(outs[-1].array, want[-1])
+    with pytest.raises(bp.BpError):
+        g.forward_wait()
+    g.close()
+
+
+@unproven
 def test_pipelined_decode_two_chunks_in_flight():
     """bp_decode_raw_submit / bp_decode_raw_wait: results of a pipelined stream equal the synchronous decode, a third
     chunk in flight and a wait without a chunk are refused."""
