@@ -541,7 +541,7 @@ def main():
         gemm_ms = (prof["fwd"] + prof["dx"] + prof["sgd_upper"] + prof["dw"]) / nprof
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
         ach = fl / (gemm_ms * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm_kernel (fwd + dX + dW launches of one bunch)",
+        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm2_kernel / bp_gemm_kernel (the 11 fwd + dX + dW products of one bunch + split-K finisher)",
                             "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                             "traffic": traffic.get("gemm_dram_bytes_per_bunch") if args.workload == "C2" else None,
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2 (kind::tf32 issues at half the bf16 rate)",
@@ -574,7 +574,7 @@ def main():
     else:
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
         ach = fl / (ms / K * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm_kernel (forward chain)", "achieved": ach,
+        line["roofline"] = {"bound": "tensor", "kernel": "bp_gemm2_kernel / bp_gemm_kernel (forward chain)", "achieved": ach,
                             "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
                             "peak_source": f"{peak_src}: bf16_tflops_sustained/2"}
     if not args.no_cpu_baseline and world == 1:
