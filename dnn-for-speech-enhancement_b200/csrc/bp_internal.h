@@ -76,4 +76,25 @@ int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, c
 int launch_out_finish(cudaStream_t st, const float* ws, long long ldw, const GemmParams& p, long long cells);
 void init_cluster_capacity(int num_sms);
 
+// Process-wide scheduling / kernel-choice switches.  Each starts from its environment variable (scripts/SWITCHES.md),
+// read once at first use, and can be changed between launches through bp_set_option(h, name, value) — so that
+// alternatives are A/B-timed inside ONE process on one resident chunk (scripts/gpu_ab_inproc.py) instead of one process
+// per setting.  None of them changes a result bit.
+enum Tunable : int {
+  TUN_PDL,          // "pdl"          BP_PDL          1   programmatic dependent launch between consecutive GEMMs
+  TUN_TMA_HINT,     // "tma_hint"     BP_TMA_HINT     1   L2 eviction-priority hints on operand loads
+  TUN_L2_PREFETCH,  // "l2_prefetch"  BP_L2_PREFETCH  0   k-blocks of L2-only TMA prefetch ahead of the smem ring
+  TUN_STAGES,       // "stages"       BP_STAGES       0   2 | 3: ring depth of the 128-wide pair kernels (0 = default 4)
+  TUN_PAIRS,        // "pairs"        BP_PAIRS        1   0 lone CTAs, 1 automatic, 2 always 256-wide, 3 128-wide pairs
+  TUN_MC,           // "mc"           BP_MC           1   pairs per multicast cluster (1, 2, 4)
+  TUN_SMALL_PAIRS,  // "small_pairs"  BP_SMALL_PAIRS  0   128-wide pairs for small products with M % 256 == 0
+  TUN_DW_STREAM,    // "dw_stream"    BP_DW_STREAM    0   evict-first stores of the gradient tiles
+  TUN_SGD_STREAM,   // "sgd_stream"   BP_SGD_STREAM   1   streaming access to the momentum deltas in the update
+  TUN_SGD_EARLY,    // "sgd_early"    BP_SGD_EARLY    6   blocks per SM of the early update of layers >= 2 (0 = off)
+  TUN_SPLITK,       // "splitk"       BP_SPLITK      -1   output-layer K slices: -1 automatic, 0 never, N force
+  TUN_COUNT
+};
+int tunable(Tunable t);
+int set_tunable(const char* name, int value);  // BP_OK, or BP_EINVAL (without touching g_err) for an unknown name
+
 }  // namespace bp

@@ -5,8 +5,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "bp_gemm.cuh"
@@ -15,6 +17,45 @@
 #include "bp_microbench.cuh"
 
 namespace bp {
+
+// ------------------------------------------------------------------------------------------------ tunables
+namespace {
+struct TunableDef {
+  const char* name;
+  const char* env;
+  int dflt;
+};
+const TunableDef kTunables[TUN_COUNT] = {
+    {"pdl", "BP_PDL", 1},           {"tma_hint", "BP_TMA_HINT", 1},       {"l2_prefetch", "BP_L2_PREFETCH", 0},
+    {"stages", "BP_STAGES", 0},     {"pairs", "BP_PAIRS", 1},             {"mc", "BP_MC", 1},
+    {"small_pairs", "BP_SMALL_PAIRS", 0}, {"dw_stream", "BP_DW_STREAM", 0}, {"sgd_stream", "BP_SGD_STREAM", 1},
+    {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}};
+std::atomic<int> g_tunable[TUN_COUNT];
+std::once_flag g_tunable_once;
+void init_tunables() {
+  std::call_once(g_tunable_once, [] {
+    for (int i = 0; i < TUN_COUNT; ++i) {
+      const char* e = getenv(kTunables[i].env);
+      g_tunable[i].store(e ? atoi(e) : kTunables[i].dflt, std::memory_order_relaxed);
+    }
+  });
+}
+}  // namespace
+
+int tunable(Tunable t) {
+  init_tunables();
+  return g_tunable[t].load(std::memory_order_relaxed);
+}
+
+int set_tunable(const char* name, int value) {
+  init_tunables();
+  for (int i = 0; i < TUN_COUNT; ++i)
+    if (strcmp(name, kTunables[i].name) == 0) {
+      g_tunable[i].store(value, std::memory_order_relaxed);
+      return BP_OK;
+    }
+  return BP_EINVAL;
+}
 
 // ------------------------------------------------------------------------------------------------ driver entry
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -108,21 +149,11 @@ static int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const 
     const char* e = getenv("BP_GEMM_FLAGS");  // measurement aid, see GemmParams::dbg_flags
     return e ? (uint32_t)atoi(e) : 0u;
   }();
-  static const bool use_pdl = [] {
-    const char* e = getenv("BP_PDL");  // programmatic dependent launch between consecutive GEMMs (default on)
-    return e ? atoi(e) != 0 : true;
-  }();
-  static const int l2_prefetch = [] {
-    const char* e = getenv("BP_L2_PREFETCH");
-    return e ? std::max(0, atoi(e)) : 0;
-  }();
+  const bool use_pdl = tunable(TUN_PDL) != 0;  // programmatic dependent launch between consecutive GEMMs (default on)
   GemmParams q = p;
-  q.l2_prefetch = l2_prefetch;
+  q.l2_prefetch = std::max(0, tunable(TUN_L2_PREFETCH));
   q.dbg_flags |= env_flags;
-  static const bool use_hints = [] {
-    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
-    return e ? atoi(e) != 0 : true;
-  }();
+  const bool use_hints = tunable(TUN_TMA_HINT) != 0;  // L2 eviction-priority hints on operand loads (default on)
   if (!use_hints) q.hint_a = q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -204,20 +235,10 @@ static int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const Ma
   const int nt = (p.N - p.n_begin + CP * PAIR_N - 1) / (CP * PAIR_N);
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  static const bool use_pdl = [] {
-    const char* e = getenv("BP_PDL");
-    return e ? atoi(e) != 0 : true;
-  }();
-  static const bool use_hints = [] {
-    const char* e = getenv("BP_TMA_HINT");  // L2 eviction-priority hints on operand loads (default on)
-    return e ? atoi(e) != 0 : true;
-  }();
-  static const int l2_prefetch = [] {
-    const char* e = getenv("BP_L2_PREFETCH");  // k-blocks of L2-only prefetch ahead of the ring (default off; untested A/B)
-    return e ? std::max(0, atoi(e)) : 0;
-  }();
+  const bool use_pdl = tunable(TUN_PDL) != 0;
+  const bool use_hints = tunable(TUN_TMA_HINT) != 0;  // L2 eviction-priority hints on operand loads (default on)
   GemmParams q = p;
-  q.l2_prefetch = l2_prefetch;
+  q.l2_prefetch = std::max(0, tunable(TUN_L2_PREFETCH));  // k-blocks of L2-only prefetch ahead of the ring (default off)
   if (!use_hints || CP > 1) q.hint_a = 0;  // the multicast A-slice load carries no hint
   if (!use_hints) q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
@@ -252,15 +273,9 @@ struct KernelChoice {
   int cp;
 };
 inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
-  static const int mode = [] {
-    const char* e = getenv("BP_PAIRS");
-    return e ? atoi(e) : 1;
-  }();
-  static const int cp = [] {
-    const char* e = getenv("BP_MC");
-    const int v = e ? atoi(e) : 1;
-    return (v == 2 || v == 4) ? v : 1;
-  }();
+  const int mode = tunable(TUN_PAIRS);
+  const int mc = tunable(TUN_MC);
+  const int cp = (mc == 2 || mc == 4) ? mc : 1;
   if (mode == 0) return {0, 1};
   if (mode == 2) return {256, cp};
   if (mode == 3) return {have_b64 ? 128 : 0, cp};
@@ -271,10 +286,7 @@ inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64)
   // BP_SMALL_PAIRS=1 (off by default, not yet run on a GPU): when the unit count is a multiple of 256 a 128-wide pair
   // tile is exactly two lone-CTA tiles — the same number of CTAs at the higher shared-memory roof (67 % against 50 %)
   // — so small products (C4's 512 frames per GPU, the reference script's bunch 128) need not fall back to lone CTAs.
-  static const int small_pairs = [] {
-    const char* e = getenv("BP_SMALL_PAIRS");
-    return e ? atoi(e) : 0;
-  }();
+  const int small_pairs = tunable(TUN_SMALL_PAIRS);
   if (small_pairs && have_b64 && p.M % (2 * GEMM_BLOCK_M) == 0 && n >= 128) return {128, cp};
   return {0, 1};
 }
@@ -302,10 +314,7 @@ static int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPa
       if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
       if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
       if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
-      static const int stages = [] {
-        const char* e = getenv("BP_STAGES");  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
-        return e ? atoi(e) : 0;
-      }();
+      const int stages = tunable(TUN_STAGES);  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
       if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
       if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
       return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);

@@ -337,6 +337,43 @@ int upload_params(Rank* r, float* const* weights, float* const* bias) {
   return BP_OK;
 }
 
+// Experiment (off by default, not yet run on a GPU): pin the weight arena in L2.  Inside a bunch the forward and dX
+// products behave as if their operands were cold (ncu: ~25 MB of DRAM reads per hidden-layer product, the kernel neither
+// DRAM- nor L2-bandwidth bound but ~1.7x slower than with a warm L2) because the update streams ~5x the arena through
+// L2 between two uses of the weights.  BP_L2_PERSIST=<MB> / bp_set_option("l2_persist", MB) sets aside that much L2 for
+// persisting lines (capped by the device limit) and gives every kernel of the compute and side streams an
+// access-policy window over the weight arena: hits persist, everything else keeps the normal policy.  mb <= 0 removes
+// the window and resets the persisting lines.  Best effort: failures leave the default policy in place.
+void rank_set_l2_persist(Rank* r, int mb) {
+  if (!r->w || !r->compute || !r->side) return;
+  cudaSetDevice(r->cfg.device);
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = r->w;
+  v.accessPolicyWindow.num_bytes = 0;
+  v.accessPolicyWindow.hitRatio = 0.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  cudaDeviceProp prop{};
+  size_t carve = 0, window = 0;
+  if (mb > 0 && cudaGetDeviceProperties(&prop, r->cfg.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+    carve = std::min((size_t)mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+    window = std::min((size_t)r->arena_floats * 4, (size_t)prop.accessPolicyMaxWindowSize);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess && window > 0) {
+      v.accessPolicyWindow.num_bytes = window;
+      v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    }
+  }
+  for (cudaStream_t st : {r->compute, r->side})
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+  if (mb <= 0) cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+  if (getenv("BP_VERBOSE"))
+    fprintf(stderr, "libbpgpu: L2 persistence: %zu MB set aside (device max %d MB), window %zu MB, hit ratio %.2f\n",
+            carve >> 20, prop.persistingL2CacheMaxSize >> 20, v.accessPolicyWindow.num_bytes >> 20,
+            v.accessPolicyWindow.hitRatio);
+}
+
 int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* const* bias) {
   if (!cfg || !weights || !bias) return fail(BP_EINVAL, "bp_create: null argument");
   if (cfg->numlayers < 2 || cfg->numlayers > BP_MAXLAYER)
@@ -440,34 +477,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaMemsetAsync(r->w, 0, off * 4, r->compute));
     CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
     CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
-    if (const char* e = getenv("BP_L2_PERSIST")) {
-      // Experiment (off by default, not yet run on a GPU): pin the weight arena in L2.  Inside a bunch the forward and
-      // dX products behave as if their operands were cold (ncu: ~25 MB of DRAM reads per hidden-layer product, the
-      // kernel neither DRAM- nor L2-bandwidth bound but ~1.7x slower than with a warm L2) because the update streams
-      // ~5x the arena through L2 between two uses of the weights.  BP_L2_PERSIST=<MB> sets aside that much L2 for
-      // persisting lines (capped by the device limit) and gives every kernel of the compute and side streams an
-      // access-policy window over the weight arena: hits persist, everything else keeps the normal policy.
-      const size_t want_mb = (size_t)std::max(0, atoi(e));
-      cudaDeviceProp prop{};
-      if (want_mb > 0 && cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-        const size_t carve = std::min(want_mb << 20, (size_t)prop.persistingL2CacheMaxSize);
-        const size_t window = std::min((size_t)off * 4, (size_t)prop.accessPolicyMaxWindowSize);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess && window > 0) {
-          cudaStreamAttrValue v{};
-          v.accessPolicyWindow.base_ptr = r->w;
-          v.accessPolicyWindow.num_bytes = window;
-          v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
-          v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-          v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-          for (cudaStream_t st : {r->compute, r->side})
-            if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-          if (getenv("BP_VERBOSE"))
-            fprintf(stderr, "libbpgpu: L2 persistence: %zu MB set aside (device max %d MB), window %zu MB, hit ratio %.2f\n",
-                    carve >> 20, prop.persistingL2CacheMaxSize >> 20, window >> 20, v.accessPolicyWindow.hitRatio);
-        }
-        cudaGetLastError();
-      }
-    }
+    if (const char* e = getenv("BP_L2_PERSIST")) rank_set_l2_persist(r, atoi(e));
     CU_TRY(cudaMalloc(&r->sqerr_dev, sizeof(double)));
     CU_TRY(cudaMalloc(&r->splitk_ws, sizeof(float) * kMaxSplits * (size_t)cfg->bunchsize * r->layer[r->L].ldN));
 
@@ -653,10 +663,7 @@ int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows, bool wait_ho
 // Number of K slices for the output-layer product (1 = no split).  BP_SPLITK: 0 = never, N>1 = force N, unset = auto:
 // as many slices as idle SMs allow, each at least 4 k-blocks deep, at most kMaxSplits.
 inline int out_layer_splits(const GemmParams& p, int num_sms) {
-  static const int mode = [] {
-    const char* e = getenv("BP_SPLITK");
-    return e ? atoi(e) : -1;
-  }();
+  const int mode = tunable(TUN_SPLITK);
   if (mode == 0) return 1;
   const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + kBlockN - 1) / kBlockN);
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
@@ -1014,11 +1021,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.out = r->g + ls.off;
     p.ldo = ls.ldN;
     p.passes = r->passes;
-    static const int dw_stream = [] {
-      const char* e = getenv("BP_DW_STREAM");
-      return e ? atoi(e) : 0;
-    }();
-    p.stream_out = dw_stream;
+    p.stream_out = tunable(TUN_DW_STREAM);
     MapPair xmap;
     const MapPair* bmap = &ls.yprev_dw;
     if (l == 1) {
@@ -1125,10 +1128,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   mark();                                               // 2: dX chain issued/done on `compute`
   const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
   const float c1 = (1 - cf.momentum) * cf.lrate;
-  static const int sgd_stream = [] {
-    const char* e = getenv("BP_SGD_STREAM");
-    return e ? atoi(e) : 1;
-  }();
+  const int sgd_stream = tunable(TUN_SGD_STREAM);
   auto launch_sgd = [&](long long begin4, long long end4, int blocks_per_sm) -> int {
     const int grid = r->num_sms * blocks_per_sm;
     if (cf.weightcost != 0.0f)
@@ -1146,10 +1146,7 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   // The update is HBM-bound, the first layer's gradient GEMM (the largest, and the last to become computable) is
   // tensor-bound and reads neither weights nor deltas: once the dX chain is done the layers >= 2 are updated while dW_1
   // still runs on the side stream.  The early launch leaves thread slots free so the GEMM's CTAs become resident.
-  static const int sgd_early_blocks = [] {
-    const char* e = getenv("BP_SGD_EARLY");  // 0 = one update launch after all gradients (as the reference orders it)
-    return e ? atoi(e) : 6;
-  }();
+  const int sgd_early_blocks = tunable(TUN_SGD_EARLY);  // 0 = one update launch after all gradients (reference order)
   long long tail_end4 = r->arena_floats / 4;
   const bool peer_split = r->dp_p2p && r->peer_early && r->L >= 2;
   unsigned long long peer_step = 0;
@@ -1676,7 +1673,9 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
     else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
     else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
     else if (strcmp(name, "relu_mask") == 0) r->relu_mask = value != 0;    // between bunches only (bp_train* has returned)
-    else return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
+    else if (strcmp(name, "l2_persist") == 0) rank_set_l2_persist(r, value);   // value = MB, <= 0 removes the window
+    else if (set_tunable(name, value) != BP_OK)                            // process-wide switches (bp_internal.h)
+      return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
   }
   return BP_OK;
 }

@@ -103,6 +103,10 @@ int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, 
  *   "relu_mask"      1: ReLU nets — the hidden layers' forward epilogues also leave a bit mask of Y > 0 and the
  *                       back-propagation epilogues read that mask instead of Y (kernDsigmoid's ReLU' is the predicate
  *                       y > 0, DevFunc.cu:81-97): 1/32 of the bytes, bit-identical results (BP_RELU_MASK)
+ *   "l2_persist"     MB of persisting L2 with an access-policy window over the weight arena (<= 0 removes it)
+ *   process-wide scheduling switches (each starts from its environment variable, scripts/SWITCHES.md): "pdl",
+ *   "tma_hint", "l2_prefetch", "stages", "pairs", "mc", "small_pairs", "dw_stream", "sgd_stream", "sgd_early", "splitk"
+ *   — changeable between calls so that alternatives are A/B-timed inside one process (scripts/gpu_ab_inproc.py)
  * Returns BP_EINVAL for an unknown name. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 
