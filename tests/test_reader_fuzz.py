@@ -117,3 +117,31 @@ def test_malformed_argument_exits_cleanly():
         p = subprocess.run([os.path.join(BIN, "reader_dump"), f"{d}/o.bin"] + reader_args(d, case) + ["oops"], cwd=d,
                            capture_output=True, text=True, timeout=20)
     assert p.returncode == 0 and "Format Error" in p.stdout + p.stderr
+
+
+MALFORMED = {
+    "truncated_data": lambda b: b[:32768 + 5000],
+    "no_header_magic": lambda b: b"-xfile_header" + b[13:],
+    "wrong_num_features": lambda b: b.replace(b"-num_features 129", b"-num_features 128"),
+    "no_sent_table": lambda b: b.replace(b"-sent_table_data", b"-sent_table_dxta"),
+    "empty_file": lambda b: b"",
+}
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_reader_dump not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(MALFORMED))
+def test_malformed_pfiles_are_handled_like_the_live_reference(name):
+    """Damaged feature Pfiles (Interface.cc:468-555, 1057-1093): exit status, stdout and log text equal the
+    reference's, character for character."""
+    from reader_case import CASES
+    case = CASES["129"]
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, case)
+        good = open(f"{d}/fea.pfile", "rb").read()
+        open(f"{d}/fea.pfile", "wb").write(MALFORMED[name](good))
+        got = {}
+        for tag, exe in (("ref", REF), ("ours", os.path.join(BIN, "reader_dump"))):
+            args = [a for a in reader_args(d, case) if not a.startswith("log_file=")] + [f"log_file={d}/{tag}.log"]
+            p = subprocess.run([exe, f"{d}/{tag}.bin"] + args, cwd=d, capture_output=True, text=True, timeout=20)
+            got[tag] = (p.returncode, p.stdout, open(f"{d}/{tag}.log").read().replace(tag + ".", "X."))
+    assert got["ours"] == got["ref"]
