@@ -79,3 +79,29 @@ def test_wts_files_load_identically_on_both_sides():
         w2, b2 = T.read_wts(f"{d}/ref.wts", ls)                  # our Python reader on the reference's file
         for i in range(1, len(ls)):
             assert np.array_equal(w2[i], w[i]) and np.array_equal(b2[i], b[i])
+
+
+def test_truncated_weight_and_norm_files_are_refused():
+    """Two places where we are deliberately stricter than the reference (both still "message + exit(0)"): a truncated
+    initwts_file is reported as such (the reference reads on into garbage and complains about bias node counts), and a
+    norm file that ends early is an error (the reference carries on with whatever its buffers held)."""
+    _build()
+    T = importlib.import_module("dnn-for-speech-enhancement_b200.tools.pfile")
+    ls = [1548, 5, 129]
+    rng = np.random.default_rng(0)
+    w = [None] + [rng.standard_normal((ls[i - 1], ls[i])).astype(np.float32) for i in (1, 2)]
+    b = [None] + [rng.standard_normal(ls[i]).astype(np.float32) for i in (1, 2)]
+    with tempfile.TemporaryDirectory() as d:
+        make_inputs(d, CASE)
+        T.write_wts(f"{d}/good.wts", w, b)
+        good = open(f"{d}/good.wts", "rb").read()
+        open(f"{d}/short.wts", "wb").write(good[: len(good) // 2])
+        norm = open(f"{d}/fea.norm").read().split("\\n")
+        open(f"{d}/short.norm", "w").write("\\n".join(norm[:100]))
+        for extra, msg in (([f"initwts_file={d}/short.wts"], "init weights file truncated"),
+                           ([f"norm_file={d}/short.norm"], "norm file too short")):
+            args = [a for a in reader_args(d, CASE) if not a.startswith(("layersizes=", "outwts_file=", "log_file="))]
+            args += ["layersizes=" + ",".join(map(str, ls)), f"outwts_file={d}/o.wts", f"log_file={d}/o.log"] + extra
+            p = subprocess.run([OURS, f"{d}/o.bin"] + args, cwd=d, capture_output=True, text=True, timeout=60)
+            assert p.returncode == 0 and msg in open(f"{d}/o.log").read()
+            assert os.path.getsize(f"{d}/o.bin") == 0      # stopped before any weights were produced
