@@ -96,8 +96,8 @@ def test_truncated_weight_and_norm_files_are_refused():
         T.write_wts(f"{d}/good.wts", w, b)
         good = open(f"{d}/good.wts", "rb").read()
         open(f"{d}/short.wts", "wb").write(good[: len(good) // 2])
-        norm = open(f"{d}/fea.norm").read().split("\\n")
-        open(f"{d}/short.norm", "w").write("\\n".join(norm[:100]))
+        norm = open(f"{d}/fea.norm").read().split("\n")
+        open(f"{d}/short.norm", "w").write("\n".join(norm[:100]))
         for extra, msg in (([f"initwts_file={d}/short.wts"], "init weights file truncated"),
                            ([f"norm_file={d}/short.norm"], "norm file too short")):
             args = [a for a in reader_args(d, CASE) if not a.startswith(("layersizes=", "outwts_file=", "log_file="))]
