@@ -299,7 +299,10 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others (and the box) waiting for the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     w, b = glorot(sizes)
     g = bp.BP_GPU(1, len(sizes), sizes, gb, 1.0, 0.9, 0.0, w, b, dflag, vo, ho, seed=12345, device=local_rank,
                   world_size=world, rank=rank, activation=act,
