@@ -92,6 +92,8 @@ enum Tunable : int {
   TUN_SGD_STREAM,   // "sgd_stream"   BP_SGD_STREAM   1   streaming access to the momentum deltas in the update
   TUN_SGD_EARLY,    // "sgd_early"    BP_SGD_EARLY    6   blocks per SM of the early update of layers >= 2 (0 = off)
   TUN_SPLITK,       // "splitk"       BP_SPLITK      -1   output-layer K slices: -1 automatic, 0 never, N force
+  TUN_UPLOAD_WAIT_FIRST,  // "upload_wait_first" BP_UPLOAD_WAIT_FIRST 0  1: bp_train* wait for the H2D before queueing
+                          //                     the bunches (the order used up to round 1d) instead of after
   TUN_COUNT
 };
 int tunable(Tunable t);

@@ -29,7 +29,7 @@ const TunableDef kTunables[TUN_COUNT] = {
     {"pdl", "BP_PDL", 1},           {"tma_hint", "BP_TMA_HINT", 1},       {"l2_prefetch", "BP_L2_PREFETCH", 0},
     {"stages", "BP_STAGES", 0},     {"pairs", "BP_PAIRS", 1},             {"mc", "BP_MC", 1},
     {"small_pairs", "BP_SMALL_PAIRS", 0}, {"dw_stream", "BP_DW_STREAM", 0}, {"sgd_stream", "BP_SGD_STREAM", 1},
-    {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}};
+    {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}, {"upload_wait_first", "BP_UPLOAD_WAIT_FIRST", 0}};
 std::atomic<int> g_tunable[TUN_COUNT];
 std::once_flag g_tunable_once;
 void init_tunables() {

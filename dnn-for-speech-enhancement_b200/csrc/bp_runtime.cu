@@ -1562,7 +1562,8 @@ int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
   const int nb = rc->n_samples / B;
   if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
-  if (h->ranks.size() == 1) {  // queue the bunches while the records are still in flight; wait for the DMA last
+  if (h->ranks.size() == 1 && !tunable(TUN_UPLOAD_WAIT_FIRST)) {
+    // queue the bunches while the records are still in flight; wait for the DMA last
     BP_TRY(check_raw_chunk(h, rc));
     Rank* r = h->ranks[0];
     BP_TRY(rank_upload_raw(r, rc, false, false));
@@ -1611,7 +1612,8 @@ int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
   if (n_frames % per_call_bunch)
     printf("this bunch has only %d samples and is ignored.\n", n_frames % per_call_bunch);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
-  if (h->ranks.size() == 1) {  // queue the bunches while the chunk is still in flight; wait for the DMA last
+  if (h->ranks.size() == 1 && !tunable(TUN_UPLOAD_WAIT_FIRST)) {
+    // queue the bunches while the chunk is still in flight; wait for the DMA last
     BP_TRY(rank_upload(r0, n_frames, in, targ, false));
     const int rc_train = rank_train_resident(r0, 0, nb);
     const std::string keep = g_err;
