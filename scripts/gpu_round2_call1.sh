@@ -15,6 +15,8 @@ echo "== 2. smoke"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== 3. default bench"
 timeout 200 python bench.py --e2e-raw --timeline > gpurun_out/r2_bench_C2.json 2> gpurun_out/r2_bench_C2.err; cut -c1-3500 gpurun_out/r2_bench_C2.json; tail -3 gpurun_out/r2_bench_C2.err
+echo "== 3b. e2e with the old / new ordering of upload wait and bunch queueing in bp_train (twice each)"
+bash scripts/gpu_ab.sh "BP_UPLOAD_WAIT_FIRST=1" "BP_UPLOAD_WAIT_FIRST=0" "BP_UPLOAD_WAIT_FIRST=1" "BP_UPLOAD_WAIT_FIRST=0"
 echo "== 4. edge cases, fused update"
 timeout 200 python scripts/gpu_edge_cases.py 2>&1 | tail -24
 timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
