@@ -3,7 +3,7 @@
 #   1. GPU test suite (includes tests/test_zz_late_round1.py, new since the last GPU call)
 #   2. smoke()
 #   3. default bench line (C2)                  -> gpurun_out/r2_bench_C2.json
-#   4. edge cases + fused-update bit parity     -> promote scripts/gpu_edge_cases.py cases into tests/ if green
+#   4. fused-update and ReLU-mask bit parity + timing (edge shapes: gated tests of step 1)
 #   5. reader throughput end to end from Pfiles (host reader on all cores, chunk prefetch, upload wait deferred)
 #   6. C5 line with the raw-records e2e
 # usage: gpurun --timeout 1200 -- 'bash scripts/gpu_round2_call1.sh 2>&1 | tee gpurun_out/r2_call1.log'
@@ -17,8 +17,7 @@ echo "== 3. default bench"
 timeout 200 python bench.py --e2e-raw --timeline > gpurun_out/r2_bench_C2.json 2> gpurun_out/r2_bench_C2.err; cut -c1-3500 gpurun_out/r2_bench_C2.json; tail -3 gpurun_out/r2_bench_C2.err
 echo "== 3b. e2e with the old / new ordering of upload wait and bunch queueing in bp_train (twice each)"
 bash scripts/gpu_ab.sh "BP_UPLOAD_WAIT_FIRST=1" "BP_UPLOAD_WAIT_FIRST=0" "BP_UPLOAD_WAIT_FIRST=1" "BP_UPLOAD_WAIT_FIRST=0"
-echo "== 4. edge cases, fused update"
-timeout 200 python scripts/gpu_edge_cases.py 2>&1 | tail -24
+echo "== 4. fused update: bit parity + timing (the edge shapes ran as gated tests in step 1)"
 timeout 300 python scripts/gpu_fused_update_check.py 2>&1 | tail -20
 echo "== 4b. ReLU bit mask: bit parity + timing"
 timeout 300 python scripts/gpu_relu_mask_check.py 2>&1 | tail -24
