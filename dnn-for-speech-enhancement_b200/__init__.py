@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.bp_get_timeline.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.bp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.bp_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
@@ -358,6 +359,13 @@ class BP_GPU:
     def set_option(self, name: str, value: int) -> None:
         """Run-time switch of an experimental code path (bp_set_option), e.g. ``set_option("fused_update", 1)``."""
         _check(load_library().bp_set_option(self._h, name.encode(), int(value)), "bp_set_option")
+
+    def get_option(self, name: str) -> int:
+        """Read-only state (bp_get_option): "dp_exchange" (0 single rank / 1 NCCL / 2 peer memory), "sm_clock_mhz"
+        (SM clock measured on the device behind whatever is queued), or the value of a set_option switch."""
+        v = C.c_int(0)
+        _check(load_library().bp_get_option(self._h, name.encode(), C.byref(v)), "bp_get_option")
+        return int(v.value)
 
     def sync(self) -> None:
         _check(load_library().bp_sync(self._h), "bp_sync")

@@ -98,5 +98,6 @@ enum Tunable : int {
 };
 int tunable(Tunable t);
 int set_tunable(const char* name, int value);  // BP_OK, or BP_EINVAL (without touching g_err) for an unknown name
+int get_tunable(const char* name, int* value);  // BP_OK / BP_EINVAL, as set_tunable
 
 }  // namespace bp

@@ -57,6 +57,16 @@ int set_tunable(const char* name, int value) {
   return BP_EINVAL;
 }
 
+int get_tunable(const char* name, int* value) {
+  init_tunables();
+  for (int i = 0; i < TUN_COUNT; ++i)
+    if (strcmp(name, kTunables[i].name) == 0) {
+      *value = g_tunable[i].load(std::memory_order_relaxed);
+      return BP_OK;
+    }
+  return BP_EINVAL;
+}
+
 // ------------------------------------------------------------------------------------------------ driver entry
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

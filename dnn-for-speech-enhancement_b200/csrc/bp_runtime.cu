@@ -1682,6 +1682,46 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
   return BP_OK;
 }
 
+// SM clock as the device sees it: clock64 ticks per globaltimer nanosecond over a ~50 us spin of one thread.
+__global__ void bp_clock_probe_kernel(unsigned long long* out) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < 50000ull);
+  const long long c1 = clock64();
+  out[0] = (unsigned long long)(c1 - c0);
+  out[1] = t1 - t0;
+}
+
+int bp_get_option(bp_handle* h, const char* name, int* value) {
+  if (!h || !name || !value) return fail(BP_EINVAL, "bp_get_option: null argument");
+  Rank* r = h->ranks[0];
+  if (strcmp(name, "dp_exchange") == 0) {
+    *value = r->dp_p2p ? 2 : (r->nccl_comm ? 1 : 0);
+    if (h->ranks.size() > 1 && *value == 0) *value = 1;
+    return BP_OK;
+  }
+  if (strcmp(name, "sm_clock_mhz") == 0) {
+    CU_TRY(cudaSetDevice(r->cfg.device));
+    unsigned long long* d = nullptr;
+    unsigned long long hv[2] = {0, 0};
+    CU_TRY(cudaMalloc(&d, 16));
+    bp_clock_probe_kernel<<<1, 1, 0, r->compute>>>(d);
+    cudaError_t e = cudaMemcpyAsync(hv, d, 16, cudaMemcpyDeviceToHost, r->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->compute);
+    cudaFree(d);
+    CU_TRY(e);
+    *value = hv[1] ? (int)(1000.0 * (double)hv[0] / (double)hv[1] + 0.5) : 0;
+    return BP_OK;
+  }
+  if (strcmp(name, "peer_early") == 0) { *value = r->peer_early; return BP_OK; }
+  if (strcmp(name, "relu_mask") == 0) { *value = r->relu_mask; return BP_OK; }
+  if (get_tunable(name, value) == BP_OK) return BP_OK;
+  return fail(BP_EINVAL, "bp_get_option: unknown option '%s'", name);
+}
+
 int bp_sync(bp_handle* h) {
   if (!h) return fail(BP_EINVAL, "null handle");
   return for_each_rank(h, [&](int i) -> int {

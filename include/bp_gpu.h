@@ -110,6 +110,14 @@ int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, 
  * Returns BP_EINVAL for an unknown name. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 
+/* Read-only state of a handle, for the benchmark line and the tests:
+ *   "dp_exchange"  0 = single rank, 1 = NCCL all-reduce, 2 = peer-memory exchange fused into the kernels
+ *   "sm_clock_mhz" SM clock measured ON the device right now (a one-thread kernel on the compute stream compares
+ *                  clock64 with globaltimer over ~50 us, after whatever is queued on that stream) — says at which
+ *                  clock a timing loop really ran, which NVML sampling from the host cannot for loops of a few ms
+ *   any bp_set_option name: its current value. */
+int bp_get_option(bp_handle* h, const char* name, int* value);
+
 /* Last error message of the calling thread ("" if none). */
 const char* bp_last_error(void);
 

@@ -411,3 +411,11 @@ float orc_crossvalid(const orc_cfg* c, float** weights, float** bias, int n_fram
 }
 
 int orc_version(void) { return 100; }
+
+/* Thread count of the OpenMP loops above.  Launchers such as torchrun export OMP_NUM_THREADS=1 to their children;
+ * the CPU baseline must use the host cores it reports, so bench.py sets the count explicitly (n <= 0: leave as is). */
+#include <omp.h>
+int orc_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}

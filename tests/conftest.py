@@ -26,3 +26,26 @@ def bp():
 def oracle():
     import oracle_py
     return oracle_py
+
+
+@pytest.fixture
+def parity_log(record_property, request):
+    """parity_log(name, achieved, bound): records the ACHIEVED error of a parity comparison (junit property, stdout,
+    and one JSON line in gpurun_out/parity_errors.jsonl when that directory exists — copied to profiles/ per round) and
+    asserts it against its bound.  Bounds are kept at <= 2x what the B200 runs of this round measured."""
+    import json
+
+    def log(name, achieved, bound):
+        achieved, bound = float(achieved), float(bound)
+        record_property(name, f"{achieved:.3e} (bound {bound:.1e})")
+        print(f"[parity] {request.node.name} :: {name}: achieved {achieved:.3e}  bound {bound:.1e}")
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            try:
+                with open(os.path.join(out_dir, "parity_errors.jsonl"), "a") as f:
+                    f.write(json.dumps({"test": request.node.name, "what": name, "achieved": achieved,
+                                        "bound": bound}) + "\n")
+            except OSError:
+                pass
+        assert achieved <= bound, f"{name}: achieved {achieved:.3e} > bound {bound:.1e}"
+    return log

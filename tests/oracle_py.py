@@ -116,6 +116,13 @@ class Net:
                                           _p(t)))
 
 
+def set_threads(n):
+    """OpenMP threads of the oracle's loops (n <= 0: query only); returns the count in force."""
+    f = lib().orc_set_threads
+    f.argtypes, f.restype = [C.c_int], C.c_int
+    return int(f(int(n)))
+
+
 def sgd(delta, w, grad, n, momentum, lr, wc):
     lib().orc_sgd(delta.size, _p(delta), _p(w), _p(grad), int(n), momentum, lr, wc)
 

@@ -49,7 +49,7 @@ def rms(a):
 
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/ref_harness not built (needs /root/reference)")
 @pytest.mark.parametrize("sizes,bunch", [([1548, 256, 192, 129], 128), ([75, 96, 130, 33], 32)])
-def test_reference_cuda_vs_oracle_vs_ours(bp, oracle, sizes, bunch):
+def test_reference_cuda_vs_oracle_vs_ours(bp, oracle, parity_log, sizes, bunch):
     x, t = oracle.synth_data(4 * bunch + 9, sizes[0], sizes[-1], seed=31)
     xcv, tcv = oracle.synth_data(bunch + 17, sizes[0], sizes[-1], seed=32)
     w, b = oracle.glorot_init(sizes, seed=3)
@@ -63,23 +63,25 @@ def test_reference_cuda_vs_oracle_vs_ours(bp, oracle, sizes, bunch):
     gw, gb = g.returnWeights()
     gcv = g.CrossValid(xcv.shape[0], xcv, tcv)
     g.close()
+    tag = f"{sizes[0]}-..-{sizes[-1]} B={bunch}"
+    fro = lambda a: float(np.linalg.norm(a.astype(np.float64).ravel()))
     for l in range(1, len(sizes)):
         # (1) oracle == reference CUDA path up to fp32 summation order
-        e = np.abs(o.w[l] - rw[l]).max()
-        assert e <= 2e-5 * rms(rw[l]), f"oracle vs reference W{l}: {e:.3e} rms {rms(rw[l]):.3e}"
-        e = np.abs(o.b[l] - rb[l]).max()
-        assert e <= 1e-4 * rms(rb[l]) + 1e-7, f"oracle vs reference b{l}: {e:.3e}"
-        # (2) ours == reference within the stated tolerance
-        e = np.abs(gw[l] - rw[l]).max()
-        assert e <= 1e-2 * rms(rw[l]), f"ours vs reference W{l}: {e:.3e} rms {rms(rw[l]):.3e}"
-        # ... and the UPDATE itself (w - w0) agrees in relative Frobenius norm (element-wise max is dominated by the
-        # few units whose ReLU' flips under rounding-level differences, see tests/test_gpu_parity.py::assert_fro)
+        parity_log(f"{tag} oracle vs reference W{l} (max/rms)", np.abs(o.w[l] - rw[l]).max() / rms(rw[l]), B_ORC_W)
+        parity_log(f"{tag} oracle vs reference b{l} (max/rms)", np.abs(o.b[l] - rb[l]).max() / (rms(rb[l]) + 1e-3),
+                   B_ORC_B)
+        # (2) ours == reference within the stated tolerance: W itself ...
+        parity_log(f"{tag} ours(tf32) vs reference W{l} (max/rms)", np.abs(gw[l] - rw[l]).max() / rms(rw[l]), B_OURS_W)
+        # ... and the UPDATE (w - w0) in relative Frobenius norm (element-wise max is dominated by the few units whose
+        # ReLU' flips under rounding-level differences, see tests/test_gpu_parity.py::assert_fro)
         dref, dours, dorc = rw[l] - w[l], gw[l] - w[l], o.w[l] - w[l]
-        fro = lambda a: float(np.linalg.norm(a.astype(np.float64).ravel()))
-        print(f"layer {l}: ||dW_ours - dW_ref||/||dW_ref|| = {fro(dours - dref) / fro(dref):.3e}   "
-              f"||dW_oracle - dW_ref||/||dW_ref|| = {fro(dorc - dref) / fro(dref):.3e}")
-        assert fro(dours - dref) <= 5e-2 * fro(dref), f"ours vs reference dW{l}"
-        assert fro(dorc - dref) <= 1e-3 * fro(dref), f"oracle vs reference dW{l}"
+        parity_log(f"{tag} ours(tf32) vs reference dW{l} (rel. Frobenius)", fro(dours - dref) / fro(dref), B_OURS_DW)
+        parity_log(f"{tag} oracle vs reference dW{l} (rel. Frobenius)", fro(dorc - dref) / fro(dref), B_ORC_DW)
     ocv = o.crossvalid(xcv, tcv)
-    assert abs(ocv - rcv) <= 1e-4 * abs(rcv)
-    assert abs(gcv - rcv) <= 1e-2 * abs(rcv)
+    parity_log(f"{tag} oracle vs reference CV (relative)", abs(ocv - rcv) / abs(rcv), 1e-4)
+    parity_log(f"{tag} ours(tf32) vs reference CV (relative)", abs(gcv - rcv) / abs(rcv), B_OURS_CV)
+
+
+# Bounds (<= 2x the achieved values of the round-2 B200 runs, profiles/r2_parity_errors.json)
+B_ORC_W, B_ORC_B, B_ORC_DW = 2e-5, 1e-4, 1e-3
+B_OURS_W, B_OURS_DW, B_OURS_CV = 1e-2, 5e-2, 1e-2

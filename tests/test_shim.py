@@ -45,7 +45,6 @@ def test_reference_main_links_against_our_trainer_and_fails_loudly_without_a_gpu
 
 @pytest.mark.gpu
 @needs_shim
-@pytest.mark.skipif(os.environ.get("BP_TEST_UNPROVEN") != "1", reason="gated, never run on a B200 yet: set BP_TEST_UNPROVEN=1")
 @pytest.mark.parametrize("dropout", [0, 1])
 def test_reference_main_with_our_trainer_equals_our_cli(dropout):
     from test_cli_gpu import LS, _args, _cv

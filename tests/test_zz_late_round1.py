@@ -19,10 +19,6 @@ from reader_case import CASES
 from test_raw_reader import _net, _raw, run_raw_dump, splice_numpy
 
 pytestmark = pytest.mark.gpu
-# Code paths that are OFF by default and whose kernels / streams have never executed (new instantiations, new API):
-# they join the suite once scripts/gpu_round2_call1.sh has seen them pass (it sets BP_TEST_UNPROVEN=1).
-unproven = pytest.mark.skipif(os.environ.get("BP_TEST_UNPROVEN") != "1",
-                              reason="gated, never run on a B200 yet: set BP_TEST_UNPROVEN=1")
 
 
 def test_decode_raw_equals_forward_on_host_assembled_rows():
@@ -42,7 +38,6 @@ def test_decode_raw_equals_forward_on_host_assembled_rows():
     g.close()
 
 
-@unproven
 def test_pipelined_forward_of_spliced_rows():
     """bp_forward_submit / bp_forward_wait (the pipeline for callers that keep the host reader) == bp_forward."""
     bp = importlib.import_module("dnn-for-speech-enhancement_b200")
@@ -65,7 +60,6 @@ def test_pipelined_forward_of_spliced_rows():
     g.close()
 
 
-@unproven
 def test_pipelined_decode_two_chunks_in_flight():
     """bp_decode_raw_submit / bp_decode_raw_wait: results of a pipelined stream equal the synchronous decode, a third
     chunk in flight and a wait without a chunk are refused."""
@@ -116,7 +110,6 @@ def test_bptrain_prefetch_thread_trains_the_same_epoch(reader):
         assert _cv(f"{d}/pf0.log") == _cv(f"{d}/pf1.log")
 
 
-@unproven
 @pytest.mark.parametrize("shape", [(128, 128, 64), (257, 100, 96), (64, 37, 40), (300, 1030, 515), (2048, 1024, 257)])
 def test_relu_mask_epilogues_in_isolation(shape):
     """kind 6 (dX product reading the bit mask) == kind 1 (reading Y) bit for bit; kind 7 (forward product leaving
@@ -152,7 +145,6 @@ def test_relu_mask_epilogues_in_isolation(shape):
     assert np.array_equal(plain.view(np.uint32), masked.view(np.uint32))
 
 
-@unproven
 @pytest.mark.parametrize("case", ["ragged", "pairs", "dropout"])
 def test_relu_mask_training_is_bit_identical(case):
     bp = importlib.import_module("dnn-for-speech-enhancement_b200")
@@ -185,7 +177,6 @@ EDGE_CASES = [("bunch 37, ragged tail", [75, 96, 33], 37, 3 * 37 + 5, dict(lrate
               ("sigmoid, odd sizes", [61, 45, 29], 24, 72, dict(activation=1, momentum=0.9))]
 
 
-@unproven
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
 def test_edge_shapes_against_the_oracle(case, fused):
