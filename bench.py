@@ -779,6 +779,12 @@ def main():
         except Exception as e:
             extras["tf32x3"] = {"error": str(e)}
 
+    iso = None
+    if rank == 0 and world == 1 and train and len(sizes) > 3:
+        try:
+            iso = isolated_dominant_gemm(bp, sizes, lb, sampler=sampler)
+        except Exception as e:  # a measurement aid must not hide the bench line
+            iso = {"error": str(e)}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist is not None:
@@ -826,14 +832,10 @@ def main():
             if dom:
                 dom["frac"] = dom["tflops"] / tf32_burst
                 line["roofline"]["dominant_kernel_in_place"] = dom
-        if world == 1 and len(sizes) > 3:
-            try:
-                iso = isolated_dominant_gemm(bp, sizes, lb, sampler=sampler)
-                if iso:
-                    iso["frac"] = iso["tflops"] / tf32_burst
-                    line["roofline"]["isolated_dominant_kernel"] = iso
-            except Exception as e:  # a measurement aid must not hide the bench line
-                line["roofline"]["isolated_dominant_kernel"] = {"error": str(e)}
+        if iso:
+            if "tflops" in iso:
+                iso["frac"] = iso["tflops"] / tf32_burst
+            line["roofline"]["isolated_dominant_kernel"] = iso
         if world == 1 and prof["sgd"] / nprof >= 0.003:
             sgd_ms = prof["sgd"] / nprof
             # algorithmic minimum 20 B/parameter over the parameters the timed launch updates: layer 1

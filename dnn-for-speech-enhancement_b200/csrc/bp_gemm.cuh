@@ -64,6 +64,107 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
   return ((1.0f - y) * y) * e;
 }
 
+// Hidden-layer forward epilogue of one 32-column chunk with every loop-invariant switch a template parameter:
+// ACT 0 ReLU / 1 sigmoid; FL bit 0 dropout, bit 1 low part wanted (3xTF32), bit 2 ragged chunk (some columns >= N).
+// All 32 values are formed first, then stored back to back (32 independent coalesced 128-byte warp stores in flight).
+// Same operations in the same order as before the split: y = act(fma(scale, acc, bias)); dropped -> 0.
+template <int ACT, int FL, bool kMask>
+__device__ __forceinline__ uint32_t epi_fwd_hid_chunk(const GemmParams& p, const uint32_t (&v)[32], int m, int nc,
+                                                      float bias) {
+  constexpr bool kDrop = (FL & 1) != 0, kLo = (FL & 2) != 0, kRagged = (FL & 4) != 0;
+  float y[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = fmaf(p.scale, __uint_as_float(v[j]), bias);
+    if constexpr (ACT == 0) y[j] = x > 0.0f ? x : 0.0f;
+    else y[j] = 1.0f / (1.0f + expf(-x));
+  }
+  if constexpr (kDrop) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float u4[4];
+      philox_uniform4(p.seed_lo, p.seed_hi, uint32_t(p.frame0 + nc + j4 * 4) >> 2, uint32_t(m), p.layer, p.step, u4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (u4[jj] < p.drop_p) y[j4 * 4 + jj] = 0.0f;
+    }
+  }
+  float* o = p.out + size_t(nc) * p.ldo + m;
+  const int valid = kRagged ? p.N - nc : 32;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (!kRagged || j < valid) o[size_t(j) * p.ldo] = y[j];
+  if constexpr (kLo) {
+    float* ol = p.out_lo + size_t(nc) * p.ldo + m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!kRagged || j < valid) ol[size_t(j) * p.ldo] = tf32_lo(y[j]);
+  }
+  uint32_t bits = 0;
+  if constexpr (kMask) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!kRagged || j < valid) bits |= (y[j] > 0.0f ? 1u : 0u) << j;
+  }
+  return bits;
+}
+
+// Output-layer epilogue of one chunk (kernSubClean, DevFunc.cu:253-268, + the squared-error monitor), switches compiled
+// in: kAux targets present, kOut store (2/B)(o - targ), kOut2 store o, kLo low part of kOut, kRagged columns >= N exist.
+// Returns sq + this chunk's sum of (o - targ)^2, accumulated in column order with one fma per term as before.
+template <bool kAux, bool kOut, bool kOut2, bool kLo, bool kRagged>
+__device__ __forceinline__ float epi_fwd_out_chunk(const GemmParams& p, const uint32_t (&v)[32], int m, int nc,
+                                                   float bias, float sq) {
+  const int valid = kRagged ? p.N - nc : 32;
+  float tg[32];
+  if constexpr (kAux) {
+    const float* a = p.aux + size_t(nc) * p.ldaux + m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tg[j] = (!kRagged || j < valid) ? __ldg(a + size_t(j) * p.ldaux) : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (!kRagged || j < valid) {
+      const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
+      if constexpr (kOut2) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
+      if constexpr (kAux) {
+        const float diff = o - tg[j];
+        if constexpr (kOut) {
+          const float dv = p.gscale * diff;
+          p.out[size_t(nc + j) * p.ldo + m] = dv;
+          if constexpr (kLo) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+        }
+        sq = fmaf(diff, diff, sq);
+      }
+    }
+  }
+  return sq;
+}
+
+// dX epilogue of one chunk, same treatment: out = act'(y) * acc (kernDsigmoid + kernVecMul, DevFunc.cu:81-97, 244-250).
+template <int ACT, bool kLo, bool kRagged>
+__device__ __forceinline__ void epi_dx_chunk(const GemmParams& p, const uint32_t (&v)[32], const float (&yv)[32], int m,
+                                             int nc) {
+  float d[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = __uint_as_float(v[j]);
+    if constexpr (ACT == 0) d[j] = yv[j] > 0.0f ? e : 0.0f;
+    else d[j] = ((1.0f - yv[j]) * yv[j]) * e;
+  }
+  float* o = p.out + size_t(nc) * p.ldo + m;
+  const int valid = kRagged ? p.N - nc : 32;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (!kRagged || j < valid) o[size_t(j) * p.ldo] = d[j];
+  if constexpr (kLo) {
+    float* ol = p.out_lo + size_t(nc) * p.ldo + m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!kRagged || j < valid) ol[size_t(j) * p.ldo] = tf32_lo(d[j]);
+  }
+}
+
 // Fused epilogue math for one chunk of 32 accumulator columns [nc, nc+32) of TMEM lane (= output row) m.
 template <int kEpi>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_t (&v)[32], int m, bool m_ok, int nc,
@@ -86,50 +187,77 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
     }
   } else if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_HID_MASK) {
     if (m_ok) {
-      float* o = p.out + size_t(nc) * p.ldo + m;
-      const bool drop = p.drop_p > 0.0f;
-      uint32_t bits = 0;  // EPI_FWD_HID_MASK: bit j = (y_j > 0) of the values as stored
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float u4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-        if (drop)
-          philox_uniform4(p.seed_lo, p.seed_hi, uint32_t(p.frame0 + nc + j4 * 4) >> 2, uint32_t(m), p.layer,
-                          p.step, u4);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj, o += p.ldo) {
-          const int j = j4 * 4 + jj;
-          float y = act_fwd(fmaf(p.scale, __uint_as_float(v[j]), bias), p.act);
-          if (drop && u4[jj] < p.drop_p) y = 0.0f;
-          if (whole || nc + j < p.N) {
-            *o = y;
-            if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(y);
-            if constexpr (kEpi == EPI_FWD_HID_MASK) bits |= (y > 0.0f ? 1u : 0u) << j;
-          }
+      // warp-uniform switches, hoisted out of the 32-column loop: with them inside, every element carried ~6 branches
+      // (activation kind, dropout, ragged tail, low part) and the hidden-layer forward product took 26 us where the
+      // plain-epilogue product of the same shape takes 17 (profiles/r2b)
+      const int flags = (p.drop_p > 0.0f ? 1 : 0) | (p.out_lo != nullptr ? 2 : 0) | (whole ? 0 : 4);
+      uint32_t bits = 0;
+#define BP_HID(ACT, FL) bits = epi_fwd_hid_chunk<ACT, FL, kEpi == EPI_FWD_HID_MASK>(p, v, m, nc, bias)
+      if (p.act == 0) {
+        switch (flags) {
+          case 0: BP_HID(0, 0); break;
+          case 1: BP_HID(0, 1); break;
+          case 2: BP_HID(0, 2); break;
+          case 3: BP_HID(0, 3); break;
+          case 4: BP_HID(0, 4); break;
+          case 5: BP_HID(0, 5); break;
+          case 6: BP_HID(0, 6); break;
+          default: BP_HID(0, 7); break;
+        }
+      } else {
+        switch (flags) {
+          case 0: BP_HID(1, 0); break;
+          case 1: BP_HID(1, 1); break;
+          case 2: BP_HID(1, 2); break;
+          case 3: BP_HID(1, 3); break;
+          case 4: BP_HID(1, 4); break;
+          case 5: BP_HID(1, 5); break;
+          case 6: BP_HID(1, 6); break;
+          default: BP_HID(1, 7); break;
         }
       }
+#undef BP_HID
       if constexpr (kEpi == EPI_FWD_HID_MASK) p.relu_mask[size_t(nc >> 5) * p.ldmask + m] = bits;
     }
   } else if constexpr (kEpi == EPI_FWD_OUT) {
     if (m_ok) {
-      float tg[32];
-      if (p.aux != nullptr) {
-        const float* a = p.aux + size_t(nc) * p.ldaux + m;
+      // the combinations the runtime issues, each with its switches compiled in (see epi_fwd_out_chunk); anything else
+      // takes the generic loop
+      const bool aux = p.aux != nullptr, out = p.out != nullptr, out2 = p.out2 != nullptr, lo = p.out_lo != nullptr;
+      if (aux && out && !out2) {                       // training: D_L = (2/B)(o - targ), loss monitor
+        if (whole) { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, false>(p, v, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, true, false, false, false>(p, v, m, nc, bias, sq_local); }
+        else       { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, true>(p, v, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, true, false, false, true>(p, v, m, nc, bias, sq_local); }
+      } else if (!aux && !out && out2) {               // decode: raw linear output
+        if (whole) epi_fwd_out_chunk<false, false, true, false, false>(p, v, m, nc, bias, 0.0f);
+        else epi_fwd_out_chunk<false, false, true, false, true>(p, v, m, nc, bias, 0.0f);
+      } else if (aux && !out) {                        // cross-validation: score, optionally the output too
+        if (whole) { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, false>(p, v, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, false, false, false, false>(p, v, m, nc, bias, sq_local); }
+        else       { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, true>(p, v, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, false, false, false, true>(p, v, m, nc, bias, sq_local); }
+      } else {
+        float tg[32];
+        if (aux) {
+          const float* a = p.aux + size_t(nc) * p.ldaux + m;
 #pragma unroll
-        for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
-      }
+          for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
+        }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (whole || nc + j < p.N) {
-          const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
-          if (p.out2 != nullptr) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
-          if (p.aux != nullptr) {
-            const float diff = o - tg[j];
-            if (p.out != nullptr) {
-              const float dv = p.gscale * diff;
-              p.out[size_t(nc + j) * p.ldo + m] = dv;
-              if (p.out_lo != nullptr) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+        for (int j = 0; j < 32; ++j) {
+          if (whole || nc + j < p.N) {
+            const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
+            if (out2) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
+            if (aux) {
+              const float diff = o - tg[j];
+              if (out) {
+                const float dv = p.gscale * diff;
+                p.out[size_t(nc + j) * p.ldo + m] = dv;
+                if (lo) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+              }
+              sq_local = fmaf(diff, diff, sq_local);
             }
-            sq_local = fmaf(diff, diff, sq_local);
           }
         }
       }
@@ -177,15 +305,15 @@ struct DxPrefetch {
 __device__ __forceinline__ void gemm_dx_store(const GemmParams& p, const uint32_t (&v)[32], const float (&yv)[32], int m,
                                               bool m_ok, int nc) {
   if (!m_ok) return;
-  const bool whole = nc + 32 <= p.N;
-  float* o = p.out + size_t(nc) * p.ldo + m;
-#pragma unroll
-  for (int j = 0; j < 32; ++j, o += p.ldo)
-    if (whole || nc + j < p.N) {
-      const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
-      *o = dv;
-      if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
-    }
+  const bool whole = nc + 32 <= p.N;      // warp-uniform, like act and out_lo: dispatched once per chunk
+  const bool lo = p.out_lo != nullptr;
+  if (p.act == 0) {
+    if (whole) { if (lo) epi_dx_chunk<0, true, false>(p, v, yv, m, nc); else epi_dx_chunk<0, false, false>(p, v, yv, m, nc); }
+    else       { if (lo) epi_dx_chunk<0, true, true>(p, v, yv, m, nc);  else epi_dx_chunk<0, false, true>(p, v, yv, m, nc); }
+  } else {
+    if (whole) { if (lo) epi_dx_chunk<1, true, false>(p, v, yv, m, nc); else epi_dx_chunk<1, false, false>(p, v, yv, m, nc); }
+    else       { if (lo) epi_dx_chunk<1, true, true>(p, v, yv, m, nc);  else epi_dx_chunk<1, false, true>(p, v, yv, m, nc); }
+  }
 }
 
 // EPI_DW_SGD: momentum-SGD update applied by the weight-gradient GEMM's own epilogue.  Operation for operation the

@@ -12,6 +12,7 @@
 
 #include "../../include/bp_gpu.h"
 #include "bp_gemm_params.h"
+#include "bp_chain_params.h"
 
 namespace bp {
 
@@ -75,6 +76,9 @@ int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, c
 // Second half of the split-K output-layer product (bp_out_finish_kernel): ws = the planes, ldw their row stride.
 int launch_out_finish(cudaStream_t st, const float* ws, long long ldw, const GemmParams& p, long long cells);
 void init_cluster_capacity(int num_sms);
+// Chained products (bp_chain.cuh): co-resident CTA pairs on the current device; one launch over a schedule.
+int chain_max_pairs(int num_sms);
+int launch_chain(cudaStream_t st, const ChainArgs& a, int pairs);
 
 // Process-wide scheduling / kernel-choice switches.  Each starts from its environment variable (scripts/SWITCHES.md),
 // read once at first use, and can be changed between launches through bp_set_option(h, name, value) — so that

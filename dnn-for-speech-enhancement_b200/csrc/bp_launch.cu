@@ -13,6 +13,7 @@
 
 #include "bp_gemm.cuh"
 #include "bp_gemm2.cuh"
+#include "bp_chain.cuh"
 #include "bp_internal.h"
 #include "bp_microbench.cuh"
 
@@ -350,6 +351,56 @@ int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, c
     case PROD_DX_MASK: return launch_gemm<false, false, EPI_DX_MASK>(st, num_sms, a, b, p, b64);
   }
   return fail(BP_EINVAL, "launch_product: unknown product %d", (int)prod);
+}
+
+// ------------------------------------------------------------------------------------------------ chained products
+// CTA pairs of bp_chain_kernel that can be co-resident on this device (the schedule must not use more: its pairs wait
+// for each other inside the launch).
+int chain_max_pairs(int num_sms) {
+  static std::mutex mu;
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cached[dev] > 0) return cached[dev];
+  int cap = 0;
+  if (cudaFuncSetAttribute(bp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes()) ==
+      cudaSuccess) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(num_sms / 2 * 2);
+    qc.blockDim = dim3(GEMM_THREADS);
+    qc.dynamicSmemBytes = chain_smem_bytes();
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, bp_chain_kernel, &qc) == cudaSuccess && n > 0) cap = std::min(n, num_sms / 2);
+  }
+  cudaGetLastError();
+  cached[dev] = cap;
+  return cap;
+}
+
+int launch_chain(cudaStream_t st, const ChainArgs& a, int pairs) {
+  if (pairs <= 0) return fail(BP_EINVAL, "launch_chain: no pairs");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = chain_smem_bytes();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, bp_chain_kernel, a));
+  return BP_OK;
 }
 
 int launch_out_finish(cudaStream_t st, const float* ws, long long ldw, const GemmParams& p, long long cells) {

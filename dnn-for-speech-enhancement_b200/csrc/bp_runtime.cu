@@ -229,6 +229,24 @@ struct Rank {
   cudaEvent_t loss_done[2] = {nullptr, nullptr};
   int loss_cur = 0;
   SgdBiasRanges bias_ranges{};
+  // Chained products (bp_chain.cuh): the forward products of a train bunch in ONE launch, the dX chain + every dW
+  // product in a second one.  Built lazily (after the peer-memory slabs are known), rebuilt when an option changes.
+  struct ChainPlan {
+    int n_prods = 0, n_items = 0;
+    ChainProd* d_prods = nullptr;
+    ChainItem* d_items = nullptr;
+    int* d_pair_off = nullptr;
+    long long makespan = 0;      // the scheduler's estimate, SM cycles
+    int pair_n_l1 = 128;         // tile width of the product whose B operand is this bunch's input rows
+  };
+  static constexpr int kChainCounters = 1024;
+  int use_chain = 1;             // bp_set_option("chain", 0) restores one launch per product
+  bool chain_built = false;
+  int chain_pairs = 0;
+  ChainPlan chain_fwd, chain_bwd;
+  CUtensorMap* chain_maps = nullptr;
+  uint32_t* chain_counters = nullptr;   // 2 sets of kChainCounters
+  int chain_set = 0;
 
   int gemm_sms() const { return nccl_comm ? std::max(8, num_sms - comm_sms) : num_sms; }
   int Nout() const { return cfg.layersizes[L]; }
@@ -988,6 +1006,248 @@ int peer_exchange_part(Rank* r, int part, unsigned long long step, long long beg
     r->launches++;
   }
   CU_TRY(cudaGetLastError());
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ chained products
+void chain_release(Rank* r) {
+  for (Rank::ChainPlan* pl : {&r->chain_fwd, &r->chain_bwd}) {
+    cudaFree(pl->d_prods);
+    cudaFree(pl->d_items);
+    cudaFree(pl->d_pair_off);
+    *pl = Rank::ChainPlan{};
+  }
+  cudaFree(r->chain_maps);
+  r->chain_maps = nullptr;
+  r->chain_built = false;
+}
+
+// Tile width of a product inside a chain: 256-wide pair tiles (shared-memory roof = tensor roof) when they still cover
+// >= 60 % of the pairs, else 128-wide ones (twice the tiles, shorter dependency chain) — the rule of pick_kernel.
+inline int chain_pair_n(int M, int N, int pairs, bool have_narrow_b) {
+  const int mt = (M + 255) / 256;
+  if (!have_narrow_b) return 256;
+  return mt * ((N + 255) / 256) * 10 >= pairs * 6 ? 256 : 128;
+}
+
+int chain_upload_plan(Rank* r, Rank::ChainPlan& pl, std::vector<ChainProd>& prods, std::vector<ChainShape>& shapes) {
+  std::vector<ChainItem> items;
+  std::vector<int> pair_off;
+  pl.makespan = chain_schedule(shapes, r->chain_pairs, items, pair_off);
+  if (pl.makespan < 0) return fail(BP_EINVAL, "chain: dependency cycle in the product table");
+  pl.n_prods = (int)prods.size();
+  pl.n_items = (int)items.size();
+  CU_TRY(cudaMalloc(&pl.d_prods, prods.size() * sizeof(ChainProd)));
+  CU_TRY(cudaMalloc(&pl.d_items, std::max<size_t>(1, items.size()) * sizeof(ChainItem)));
+  CU_TRY(cudaMalloc(&pl.d_pair_off, pair_off.size() * sizeof(int)));
+  CU_TRY(cudaMemcpy(pl.d_prods, prods.data(), prods.size() * sizeof(ChainProd), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_items, items.data(), items.size() * sizeof(ChainItem), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_pair_off, pair_off.data(), pair_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return BP_OK;
+}
+
+// Product tables and schedules of a train bunch of r->local_bunch rows.  The parameters mirror forward_rows /
+// launch_dx / launch_dw below (the one-launch-per-product path), which stays as the A/B baseline and the fallback.
+int chain_build(Rank* r) {
+  chain_release(r);
+  const bp_config& cf = r->cfg;
+  const int n = r->local_bunch;
+  r->chain_pairs = chain_max_pairs(r->num_sms);
+  if (r->chain_pairs <= 0) return fail(BP_ECUDA, "chain: no co-resident CTA pairs");
+  if (!r->chain_counters) {
+    CU_TRY(cudaMalloc(&r->chain_counters, 2 * Rank::kChainCounters * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(r->chain_counters, 0, 2 * Rank::kChainCounters * sizeof(uint32_t)));
+    r->chain_set = 0;
+  }
+  std::vector<CUtensorMap> maps;
+  auto add = [&](const MapPair& mp, int* idx, int* idx_lo) {
+    *idx = (int)maps.size();
+    maps.push_back(mp.m);
+    *idx_lo = (int)maps.size();
+    maps.push_back(mp.lo);
+  };
+  const bool drop = cf.dropoutflag == 1;
+  const bool hints = tunable(TUN_TMA_HINT) != 0;
+  const int kb_mul = r->passes == 3 ? 3 : 1;
+  int cnt = 0;
+  auto shape_of = [&](const ChainProd& q, int dep, int dep_all, int prio) {
+    ChainShape sh{};
+    sh.m_tiles = q.m_tiles;
+    sh.n_tiles = q.n_tiles;
+    sh.n_cols = q.p.N;
+    sh.kb = (q.p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K * kb_mul;
+    sh.pair_n = q.pair_n;
+    sh.dep_prod = dep;
+    sh.dep_all = dep_all;
+    sh.prio = prio;
+    return sh;
+  };
+  auto finish_prod = [&](ChainProd& q) {
+    q.m_tiles = (q.p.M + 255) / 256;
+    q.n_tiles = (q.p.N + q.pair_n - 1) / q.pair_n;
+    q.cnt_base = cnt;
+    cnt += q.n_tiles;
+  };
+  // ---- forward: layer l = product l-1
+  {
+    std::vector<ChainProd> prods;
+    std::vector<ChainShape> shapes;
+    cnt = 0;
+    for (int l = 1; l <= r->L; ++l) {
+      LayerState& ls = r->layer[l];
+      ChainProd q{};
+      GemmParams& p = q.p;
+      p.M = ls.N;
+      p.N = n;
+      p.K = ls.K;
+      p.bias = r->w + ls.off + (long long)ls.K * ls.ldN;
+      p.act = cf.activation;
+      p.scale = 1.0f;
+      p.seed_lo = (uint32_t)cf.seed;
+      p.seed_hi = (uint32_t)(cf.seed >> 32);
+      p.layer = (uint32_t)l;
+      p.frame0 = cf.rank * r->local_bunch;
+      p.passes = r->passes;
+      p.hint_a = hints ? kEvictLast : 0;
+      q.amn = 1;
+      q.bmn = 0;
+      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs, true);
+      add(ls.w_fwd.full, &q.map_a, &q.map_a_lo);
+      if (l == 1) {
+        q.map_b = -1;
+        q.map_b_lo = -2;
+        r->chain_fwd.pair_n_l1 = q.pair_n;
+      } else {
+        add(q.pair_n == 256 ? ls.yprev_fwd : ls.yprev_fwd64, &q.map_b, &q.map_b_lo);
+      }
+      q.dep_prod = l >= 2 ? l - 2 : -1;
+      q.dep_all = 0;
+      if (l < r->L) {
+        q.epi = EPI_FWD_HID;
+        p.out = ls.y;
+        p.out_lo = ls.y_lo;
+        p.ldo = ls.ldy;
+        p.drop_p = drop ? cf.hid_omit : 0.0f;
+      } else {
+        q.epi = EPI_FWD_OUT;
+        q.per_bunch = 1;  // targets + loss slot of the bunch
+        p.out = ls.d;
+        p.out_lo = ls.d_lo;
+        p.ldo = ls.ldd;
+        p.ldaux = ls.N;
+        p.gscale = 2.0f / (float)cf.bunchsize;  // (2.0f/rows), rows = GLOBAL bunch (DevFunc.cu:263)
+      }
+      finish_prod(q);
+      shapes.push_back(shape_of(q, q.dep_prod, 0, l));
+      prods.push_back(q);
+    }
+    if (cnt > Rank::kChainCounters) return fail(BP_EINVAL, "chain: too many tiles per product row (%d counters)", cnt);
+    const int pn1 = r->chain_fwd.pair_n_l1;
+    BP_TRY(chain_upload_plan(r, r->chain_fwd, prods, shapes));
+    r->chain_fwd.pair_n_l1 = pn1;
+  }
+  // ---- back-propagation: dX_L .. dX_2 (the chain) and dW_L .. dW_1 (the filler)
+  {
+    std::vector<ChainProd> prods;
+    std::vector<ChainShape> shapes;
+    cnt = 0;
+    int dx_index[BP_MAXLAYER + 1];
+    for (auto& v : dx_index) v = -1;
+    for (int l = r->L; l >= 2; --l) {  // dX_l: dE/dX_{l-1} = act'(Y_{l-1}) .* (dE/dX_l W_l^T)
+      LayerState& ls = r->layer[l];
+      LayerState& lp = r->layer[l - 1];
+      ChainProd q{};
+      GemmParams& p = q.p;
+      p.M = ls.K;
+      p.N = n;
+      p.K = ls.N;
+      p.out = lp.d;
+      p.out_lo = lp.d_lo;
+      p.ldo = lp.ldd;
+      p.aux = lp.y;
+      p.ldaux = lp.ldy;
+      p.act = cf.activation;
+      p.passes = r->passes;
+      p.hint_a = hints ? kEvictLast : 0;
+      q.epi = EPI_DX;
+      q.amn = 0;
+      q.bmn = 0;
+      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs, true);
+      add(ls.w_dx.full, &q.map_a, &q.map_a_lo);
+      add(q.pair_n == 256 ? ls.d_dx : ls.d_dx64, &q.map_b, &q.map_b_lo);
+      q.dep_prod = l < r->L ? dx_index[l + 1] : -1;  // D_l comes from the product that back-propagated through l+1
+      q.dep_all = 0;
+      finish_prod(q);
+      dx_index[l] = (int)prods.size();
+      shapes.push_back(shape_of(q, q.dep_prod, 0, 0));
+      prods.push_back(q);
+    }
+    for (int l = r->L; l >= 1; --l) {  // dW_l (+ bias gradient as row K of the block)
+      LayerState& ls = r->layer[l];
+      ChainProd q{};
+      GemmParams& p = q.p;
+      p.M = ls.N;
+      p.N = ls.K + 1;
+      p.K = n;
+      p.out = r->g + ls.off;
+      p.ldo = ls.ldN;
+      p.passes = r->passes;
+      p.stream_out = tunable(TUN_DW_STREAM);
+      if (r->dp_p2p) {  // reduce-scatter fused into the epilogue: chunks go straight to their owners' receive slabs
+        p.scatter_n = cf.world_size;
+        p.chunk_base = r->chunk_base[l];
+        for (int o = 0; o < cf.world_size; ++o)
+          p.scatter[o] = r->peer[o].recv + (long long)cf.rank * r->arena_floats + ls.off;
+      }
+      q.epi = EPI_PLAIN;
+      q.amn = 1;
+      q.bmn = 1;
+      q.pair_n = 256;
+      add(ls.d_dw.full, &q.map_a, &q.map_a_lo);
+      if (l == 1) {
+        q.map_b = -1;
+        q.map_b_lo = -2;
+      } else {
+        add(ls.yprev_dw, &q.map_b, &q.map_b_lo);
+      }
+      q.dep_prod = l < r->L ? dx_index[l + 1] : -1;  // needs all of D_l
+      q.dep_all = 1;
+      finish_prod(q);
+      shapes.push_back(shape_of(q, q.dep_prod, 1, 1 + (r->L - l)));
+      prods.push_back(q);
+    }
+    if (cnt > Rank::kChainCounters) return fail(BP_EINVAL, "chain: too many tiles per product row (%d counters)", cnt);
+    if ((int)prods.size() > CHAIN_MAX_PROD) return fail(BP_EINVAL, "chain: %d products", (int)prods.size());
+    BP_TRY(chain_upload_plan(r, r->chain_bwd, prods, shapes));
+  }
+  CU_TRY(cudaMalloc(&r->chain_maps, maps.size() * sizeof(CUtensorMap)));
+  CU_TRY(cudaMemcpy(r->chain_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  r->chain_built = true;
+  if (getenv("BP_VERBOSE"))
+    fprintf(stderr, "libbpgpu: chained products on %d pairs: forward %d tiles (~%.1f us), back-propagation %d tiles "
+            "(~%.1f us by the cost model)\n", r->chain_pairs, r->chain_fwd.n_items, r->chain_fwd.makespan / 1965.0,
+            r->chain_bwd.n_items, r->chain_bwd.makespan / 1965.0);
+  return BP_OK;
+}
+
+int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float* targ, double* sqerr) {
+  ChainArgs a{};
+  a.prods = pl.d_prods;
+  a.n_prods = pl.n_prods;
+  a.items = pl.d_items;
+  a.pair_off = pl.d_pair_off;
+  a.maps = r->chain_maps;
+  a.dyn[0] = dyn_b.m;
+  a.dyn[1] = dyn_b.lo;
+  a.counters = r->chain_counters + (size_t)r->chain_set * Rank::kChainCounters;
+  a.counters_next = r->chain_counters + (size_t)(r->chain_set ^ 1) * Rank::kChainCounters;
+  a.n_counters = Rank::kChainCounters;
+  a.targ = targ;
+  a.sqerr = sqerr;
+  a.step = r->step;
+  BP_TRY(launch_chain(r->compute, a, r->chain_pairs));
+  r->chain_set ^= 1;
+  r->launches++;
   return BP_OK;
 }
 
