@@ -41,6 +41,14 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Bounded poll of one dependency counter (one lane of the producer warp).
@@ -57,26 +65,59 @@ __device__ __forceinline__ void chain_wait_counter(const uint32_t* c, uint32_t t
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_constant__ ChainArgs a) {
-  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, kStages = CHAIN_STAGES;
-  constexpr uint32_t A_BYTES = CHAIN_A_BYTES, STAGE_BYTES = CHAIN_STAGE_BYTES;
-  constexpr uint32_t TMEM_COLS = 512;
+// MMA issue loop of ONE tile (leader CTA's warp 1), operand majors and tile width compiled in: see the call site.
+template <bool kAMN, bool kBMN, int PAIR_N>
+__device__ __forceinline__ void chain_mma_item(uint64_t* full, uint64_t* empty, uint64_t* tfull, uint32_t smem_base,
+                                               uint32_t d_tmem, int num_it, int as, int& s, uint32_t& ph, int lane,
+                                               uint32_t stage_bytes, int n_stages) {
+  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
   constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
   constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (kLayoutSW128Base32 << 29);
   constexpr uint32_t kDescLoK = (16u >> 4) << 16;
   constexpr uint32_t kDescLoMN = ((uint32_t(BLOCK_K) * 128u) >> 4) << 16;
-  constexpr uint32_t kAsub = BLOCK_M * 128;
+  constexpr uint32_t kAsub = BLOCK_M * 128, kBsub = (PAIR_N / 2) * 128;
+  constexpr uint32_t idesc = make_idesc_tf32(2 * BLOCK_M, PAIR_N, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
+  constexpr int kPollLane = 1;
+  for (int kb = 0; kb < num_it; ++kb) {
+    if (lane == kPollLane) mbar_wait(&full[s], ph);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t sa = smem_base + uint32_t(s) * stage_bytes;
+    const uint32_t sb = sa + CHAIN_A_BYTES;
+    if (elect_one()) {
+      const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + ((sa >> 4) & 0x3FFFu);
+      const uint32_t b_lo = (kBMN ? kDescLoMN : kDescLoK) + ((sb >> 4) & 0x3FFFu);
+#pragma unroll
+      for (int k = 0; k < BLOCK_K / 8; ++k) {
+        const uint32_t a_off = kAMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kAsub + uint32_t(k % 4) * 32u;
+        const uint32_t b_off = kBMN ? uint32_t(k) * 1024u : uint32_t(k / 4) * kBsub + uint32_t(k % 4) * 32u;
+        umma_tf32_2sm(d_tmem, a_lo + (a_off >> 4), kAMN ? kDescHiMN : kDescHiK, b_lo + (b_off >> 4),
+                      kBMN ? kDescHiMN : kDescHiK, idesc, (k != 0 || kb != 0) ? 1u : 0u);
+      }
+      umma_commit_2sm(&empty[s], uint16_t(0x3u));
+      if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u));
+    }
+    __syncwarp();
+    if (++s == n_stages) { s = 0; ph ^= 1u; }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_constant__ ChainArgs a) {
+  constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
+  constexpr uint32_t A_BYTES = CHAIN_A_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;
+  const int kStages = a.n_stages;                 // kernel parameters: uniform
+  const uint32_t STAGE_BYTES = a.stage_bytes;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw_addr);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * STAGE_BYTES);
-  uint64_t* empty = full + kStages;
-  uint64_t* tfull = empty + kStages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + CHAIN_RING_BYTES);
+  uint64_t* empty = full + CHAIN_MAX_STAGES;
+  uint64_t* tfull = empty + CHAIN_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  ChainProd* sprod = reinterpret_cast<ChainProd*>(smem + size_t(kStages) * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,13 +127,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
 
-  // product table -> shared memory, with this bunch's patches
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.prods);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sprod);
-    const int words = a.n_prods * int(sizeof(ChainProd) / 4);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < a.n_counters; i += blockDim.x) a.counters_next[i] = 0u;
   if (warp == 0 && lane == 0) {
@@ -111,21 +145,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
     tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
     tmem_relinquish_2sm();
   }
-  __syncthreads();
-  if (threadIdx.x < a.n_prods) {
-    ChainProd& q = sprod[threadIdx.x];
-    q.p.step = a.step;
-    if (q.per_bunch & 1) {
-      q.p.aux = a.targ;
-      q.p.sqerr = a.sqerr;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int it0 = __ldg(a.pair_off + pair), it1 = __ldg(a.pair_off + pair + 1);
+  const int it0 = a.pair_off[pair], it1 = a.pair_off[pair + 1];
+  if (warp >= 2 && lane == 0 && a.n_pf > 0) {  // the epilogue warps have nothing to do until the first accumulator
+    constexpr unsigned long long kPf = 16384;
+    const unsigned long long w = (unsigned long long)blockIdx.x * 4 + (warp - 2), nw = (unsigned long long)gridDim.x * 4;
+    for (int rgn = 0; rgn < a.n_pf; ++rgn) {
+      const char* base = static_cast<const char*>(a.pf_base[rgn]);
+      const unsigned long long chunks = a.pf_bytes[rgn] / kPf;
+      for (unsigned long long c = w; c < chunks; c += nw) bulk_prefetch_l2(base + c * kPf, (uint32_t)kPf);
+    }
+  }
   auto map_ptr = [&](int idx) -> const CUtensorMap* { return idx >= 0 ? a.maps + idx : &a.dyn[-1 - idx]; };
 
   if (warp == 0) {
@@ -134,7 +168,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
     uint32_t ph = 0;
     for (int i = it0; i < it1; ++i) {
       const ChainItem itm = a.items[i];
-      const ChainProd& q = sprod[itm.prod];
+      const ChainProd& q = a.prods[itm.prod];
       const int pair_n = q.pair_n, half_n = pair_n >> 1;
       const bool amn = q.amn != 0, bmn = q.bmn != 0;
       const int m0 = itm.mt * 2 * BLOCK_M + int(rank) * BLOCK_M;
@@ -148,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
       const CUtensorMap* mBlo = map_ptr(q.map_b_lo);
       const unsigned long long hint_a = q.p.hint_a, hint_b = q.p.hint_b;
       if (q.dep_prod >= 0) {  // operands written inside this launch: wait until the tiles that hold them are stored
-        const ChainProd& d = sprod[q.dep_prod];
+        const ChainProd& d = a.prods[q.dep_prod];
         int j0 = 0, j1 = d.n_tiles;
         if (!q.dep_all) {
           const int f0 = itm.nt * pair_n, f1 = min(q.p.N, f0 + pair_n);
@@ -161,6 +195,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
         __syncwarp();
         fence_proxy_async_global();  // generic-proxy writes (acquired above) -> visible to my async-proxy (TMA) reads
       }
+      if (a.trace != nullptr && leader && lane == 0) a.trace[4 * i + 0] = global_timer_ns();
       for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
         if (kb == num_kb) { kb = 0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? mAlo : mA;
@@ -191,43 +226,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
       uint32_t aph = 0;
       for (int i = it0; i < it1; ++i) {
         const ChainItem itm = a.items[i];
-        const ChainProd& q = sprod[itm.prod];
+        const ChainProd& q = a.prods[itm.prod];
         const int pair_n = q.pair_n;
         const bool amn = q.amn != 0, bmn = q.bmn != 0;
         const int num_it = ((q.p.K + BLOCK_K - 1) / BLOCK_K) * (q.p.passes == 3 ? 3 : 1);
-        const uint32_t idesc = make_idesc_tf32(2 * BLOCK_M, uint32_t(pair_n), amn ? 1u : 0u, bmn ? 1u : 0u);
-        const uint32_t kBsub = uint32_t(pair_n >> 1) * 128u;
-        const uint32_t a_hi = amn ? kDescHiMN : kDescHiK, b_hi = bmn ? kDescHiMN : kDescHiK;
-        const uint32_t a_lo_c = amn ? kDescLoMN : kDescLoK, b_lo_c = bmn ? kDescLoMN : kDescLoK;
-        // byte step of the descriptor start address per 8-deep k-step: MN-major 1024 each; K-major 32 within a
-        // 32-wide k-chunk, then the next chunk (k = 4) starts kAsub / kBsub further
-        const uint32_t a_s1 = amn ? 1024u : 32u, a_s4 = amn ? 4096u : kAsub;
-        const uint32_t b_s1 = bmn ? 1024u : 32u, b_s4 = bmn ? 4096u : kBsub;
         if (lane == kPollLane) mbar_wait(&tempty[as], aph ^ 1u);
         __syncwarp();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * 256);
-        for (int kb = 0; kb < num_it; ++kb) {
-          if (lane == kPollLane) mbar_wait(&full[s], ph);
-          __syncwarp();
-          tc_fence_after();
-          const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
-          const uint32_t sb = sa + A_BYTES;
-          if (elect_one()) {
-            const uint32_t a_lo = a_lo_c + ((sa >> 4) & 0x3FFFu);
-            const uint32_t b_lo = b_lo_c + ((sb >> 4) & 0x3FFFu);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 8; ++k) {
-              const uint32_t a_off = uint32_t(k / 4) * a_s4 + uint32_t(k % 4) * a_s1;
-              const uint32_t b_off = uint32_t(k / 4) * b_s4 + uint32_t(k % 4) * b_s1;
-              umma_tf32_2sm(d_tmem, a_lo + (a_off >> 4), a_hi, b_lo + (b_off >> 4), b_hi, idesc,
-                            (k != 0 || kb != 0) ? 1u : 0u);
-            }
-            umma_commit_2sm(&empty[s], uint16_t(0x3u));
-            if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u));
-          }
-          __syncwarp();
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+        // The instruction and shared-memory descriptors must reach tcgen05.mma in UNIFORM registers.  Per-product
+        // values read from the table are ordinary (vector) registers to the compiler, and every one of them would be
+        // moved across for every MMA (~5 moves x 8 MMAs per k-block: the first version of this loop ran at 1120 cycles
+        // per k-block where bp_gemm2_kernel needs 590).  So the product's (majors, width) only SELECTS one of the
+        // compile-time variants below, in which all of them are immediates.
+        const int variant = (amn ? 2 : 0) + (bmn ? 1 : 0) + (pair_n == 256 ? 4 : 0);
+        switch (variant) {
+          case 2: chain_mma_item<true, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 0: chain_mma_item<false, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 3: chain_mma_item<true, true, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 6: chain_mma_item<true, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 4: chain_mma_item<false, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 7: chain_mma_item<true, true, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          default: __trap();  // K-major A with MN-major B: no product of the path has it
         }
         as ^= 1;
         if (as == 0) aph ^= 1u;
@@ -240,26 +260,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
     uint32_t aph = 0;
     for (int i = it0; i < it1; ++i) {
       const ChainItem itm = a.items[i];
-      const ChainProd& q = sprod[itm.prod];
-      const GemmParams& p = q.p;
+      const ChainProd& q = a.prods[itm.prod];
+      const GemmParams& p = q.p;   // constant bank: uniform, read-only to the compiler
+      const int epi = q.epi, has_consumer = q.has_consumer, cnt_base = q.cnt_base;
       const int pair_n = q.pair_n;
       const int m0 = itm.mt * 2 * BLOCK_M + int(rank) * BLOCK_M;
       const int n0 = itm.nt * pair_n;
       const int m = m0 + qd * 32 + lane;
       const bool m_ok = m < p.M;
       DxPrefetch pre;
-      if (q.epi == EPI_DX) pre.start(p, m, m_ok, n0);  // Y of the first chunks, under the main loop
+      // Y (EPI_DX) / the targets (training output layer) of the first chunks, fetched under the main loop
+      const bool out_train = epi == EPI_FWD_OUT && p.aux != nullptr && p.out != nullptr && p.out2 == nullptr;
+      if (epi == EPI_DX || out_train) pre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
       tc_fence_after();
+      if (a.trace != nullptr && leader && warp == 2 && lane == 0) a.trace[4 * i + 2] = global_timer_ns();
       const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + uint32_t(as * 256);
       float sq_local = 0.0f;
-      if (q.epi == EPI_DX) {
+      if (epi == EPI_DX) {
         if (pair_n == 256) gemm_dx_epilogue<256>(p, pre, taddr, m, m_ok, n0);
         else gemm_dx_epilogue<128>(p, pre, taddr, m, m_ok, n0);
+      } else if (out_train) {
+        const float bias = m_ok ? __ldg(p.bias + m) : 0.0f;
+        if (pair_n == 256) sq_local = gemm_fwdout_train_epilogue<256>(p, pre, taddr, m, m_ok, n0, bias, sq_local);
+        else sq_local = gemm_fwdout_train_epilogue<128>(p, pre, taddr, m, m_ok, n0, bias, sq_local);
       } else {
         float bias = 0.0f;
-        if (q.epi != EPI_PLAIN && m_ok) bias = __ldg(p.bias + m);
+        if (epi != EPI_PLAIN && m_ok) bias = __ldg(p.bias + m);
         const int chunks = pair_n >> 5;
 #pragma unroll 1
         for (int c = 0; c < chunks; ++c) {
@@ -268,8 +296,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
           uint32_t v[32];
           tmem_ld32(taddr + uint32_t(c * 32), v);
           tmem_ld_wait();
-          if (q.epi == EPI_FWD_HID) gemm_epilogue_chunk<EPI_FWD_HID>(p, v, m, m_ok, nc, bias, sq_local);
-          else if (q.epi == EPI_FWD_OUT) gemm_epilogue_chunk<EPI_FWD_OUT>(p, v, m, m_ok, nc, bias, sq_local);
+          if (epi == EPI_FWD_HID) gemm_epilogue_chunk<EPI_FWD_HID>(p, v, m, m_ok, nc, bias, sq_local);
+          else if (epi == EPI_FWD_OUT) gemm_epilogue_chunk<EPI_FWD_OUT>(p, v, m, m_ok, nc, bias, sq_local);
           else gemm_epilogue_chunk<EPI_PLAIN>(p, v, m, m_ok, nc, bias, sq_local);
         }
       }
@@ -279,12 +307,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_
         if (leader) mbar_arrive(&tempty[as]);
         else mbar_arrive_remote(&tempty[as], crank & ~1u);
       }
-      // my part of the tile is stored: publish it to the consumers' producer warps
-      fence_proxy_async_global();
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) red_release_gpu_add_u32(a.counters + q.cnt_base + itm.nt, 1u);
-      if (q.epi == EPI_FWD_OUT && p.sqerr != nullptr) {
+      if (a.trace != nullptr && leader && warp == 2 && lane == 0) a.trace[4 * i + 1] = global_timer_ns();
+      // my part of the tile is stored: publish it to the consumers' producer warps (products nobody waits for inside
+      // this launch — the dW gradients — are complete at kernel end like any kernel's output)
+      if (has_consumer) {
+        fence_proxy_async_global();
+        __syncwarp();  // orders the other lanes' stores before lane 0's release (cumulative at gpu scope)
+        if (lane == 0) red_release_gpu_add_u32(a.counters + cnt_base + itm.nt, 1u);
+      }
+      if (a.trace != nullptr && leader && warp == 2 && lane == 0) a.trace[4 * i + 3] = global_timer_ns();
+      if (epi == EPI_FWD_OUT && p.sqerr != nullptr) {
         double sq = static_cast<double>(sq_local);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);

@@ -11,10 +11,14 @@
 
 namespace bp {
 
-constexpr int CHAIN_STAGES = 3;
+constexpr int CHAIN_MAX_STAGES = 4;
 constexpr uint32_t CHAIN_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 4;   // 32 KB: my 128 rows of A
-constexpr uint32_t CHAIN_STAGE_BYTES = 2 * CHAIN_A_BYTES;             // + up to 32 KB: my half of B
+constexpr uint32_t CHAIN_RING_BYTES = 6 * CHAIN_A_BYTES;              // 192 KB: 3 slots of 64 KB (some product has
+                                                                      // 256-wide tiles: 32 KB of B per CTA) or 4 of 48 KB
 constexpr int CHAIN_MAX_PROD = 20;
+constexpr int CHAIN_MAX_ITEMS = 1400;   // tiles of one launch (C4's back-propagation: 562); larger nets use one launch
+                                        // per product
+constexpr int CHAIN_MAX_PAIRS = 80;
 constexpr int CHAIN_ARRIVALS_PER_TILE = 8;                            // epilogue warps of a pair
 
 struct ChainProd {
@@ -28,31 +32,43 @@ struct ChainProd {
   int cnt_base;          // my counters: counters[cnt_base + n_tile]
   int dep_prod;          // product that writes an operand of mine inside this launch, or -1
   int dep_all;           // 1: wait for all its n-tiles; 0: for those covering my tile's columns (frames)
-  int per_bunch;         // bit 0: p.aux = ChainArgs::targ, p.sqerr = ChainArgs::sqerr (output layer, training)
+  int per_bunch;         // bit 0: the host sets p.aux / p.sqerr to this bunch's targets / loss slot (output layer)
+  int has_consumer;      // 1: some product of this launch waits for my tiles -> publish them (fence + counter)
 };
 
 struct ChainItem {
   short prod, mt, nt, pad;
 };
 
+// The whole launch description travels BY VALUE in the kernel parameters (constant bank, ~20 KB): the kernel indexes
+// the item list and the product table with warp-uniform indices, so every per-tile quantity (tensor-map addresses,
+// coordinates, descriptors, extents) is a UNIFORM value to the compiler and reaches the TMA / tcgen05 instructions
+// without per-instruction vector-to-uniform register moves.  (A first version kept the tables in global / shared
+// memory: ~20 R2UR per k-block in the producer, 40 in the MMA issuer, and a main loop 1.5x slower than bp_gemm2_kernel's.)
 struct ChainArgs {
-  const ChainProd* prods;
+  ChainProd prods[CHAIN_MAX_PROD];
+  ChainItem items[CHAIN_MAX_ITEMS];
+  int pair_off[CHAIN_MAX_PAIRS + 1];   // items of pair i: [pair_off[i], pair_off[i+1])
   int n_prods;
-  const ChainItem* items;
-  const int* pair_off;       // items of pair i: [pair_off[i], pair_off[i+1])
   const CUtensorMap* maps;   // static tensor maps, global memory
   CUtensorMap dyn[4];        // per-bunch maps (this bunch's input rows as B operand of layer 1: fwd, dW; + low parts)
+  uint32_t stage_bytes;      // ring slot: 32 KB of A + the widest product's B half (48 or 64 KB)
+  int n_stages;              // CHAIN_RING_BYTES / stage_bytes (4 or 3)
   uint32_t* counters;        // this launch's counter set (all zero at launch)
   uint32_t* counters_next;   // the other set: zeroed by this launch
   int n_counters;
-  const float* targ;         // per-bunch patches, see ChainProd::per_bunch
-  double* sqerr;
-  uint32_t step;             // dropout step of this bunch (Philox counter)
+  // L2 prefetch at kernel start (cp.async.bulk.prefetch.L2), spread over all CTAs: operands of LATER products of
+  // this launch (the next layers' weights) and of the NEXT launch (the next bunch's input rows).
+  const void* pf_base[6];
+  unsigned long long pf_bytes[6];
+  int n_pf;
+  unsigned long long* trace; // bring-up aid (null in production): per item 4 globaltimer stamps written by the leader
+                             // CTA: dependencies satisfied, stores issued, accumulator complete, published
 };
+static_assert(sizeof(ChainArgs) < 32000, "kernel parameter space");
 
 constexpr size_t chain_smem_bytes() {
-  return size_t(CHAIN_STAGES) * CHAIN_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-         CHAIN_MAX_PROD * sizeof(ChainProd);
+  return size_t(CHAIN_RING_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 

@@ -55,6 +55,17 @@ constexpr size_t gemm_smem_bytes() {
 __device__ __forceinline__ float tf32_lo(float x) {
   return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
+// Output stores of the epilogues: explicitly to the GLOBAL space and invisible to the compiler's alias analysis.  When
+// the parameter block does not come from the constant bank (bp_chain.cuh keeps a table of them in shared memory) its
+// pointers are generic to the compiler: a plain `*o = y` becomes a generic ST that may alias the table itself, and every
+// field (p.ldo, p.out, p.N ...) is re-read from shared memory after every store — 3x slower epilogues (measured).  No
+// epilogue reads back what it stores, so no "memory" clobber is needed.
+__device__ __forceinline__ void st_global_f32(float* p, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+__device__ __forceinline__ void st_global_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == 0) return x > 0.0f ? x : 0.0f;
   return 1.0f / (1.0f + expf(-x));
@@ -93,12 +104,12 @@ __device__ __forceinline__ uint32_t epi_fwd_hid_chunk(const GemmParams& p, const
   const int valid = kRagged ? p.N - nc : 32;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
-    if (!kRagged || j < valid) o[size_t(j) * p.ldo] = y[j];
+    if (!kRagged || j < valid) st_global_f32(o + size_t(j) * p.ldo, y[j]);
   if constexpr (kLo) {
     float* ol = p.out_lo + size_t(nc) * p.ldo + m;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (!kRagged || j < valid) ol[size_t(j) * p.ldo] = tf32_lo(y[j]);
+      if (!kRagged || j < valid) st_global_f32(ol + size_t(j) * p.ldo, tf32_lo(y[j]));
   }
   uint32_t bits = 0;
   if constexpr (kMask) {
@@ -110,29 +121,23 @@ __device__ __forceinline__ uint32_t epi_fwd_hid_chunk(const GemmParams& p, const
 }
 
 // Output-layer epilogue of one chunk (kernSubClean, DevFunc.cu:253-268, + the squared-error monitor), switches compiled
-// in: kAux targets present, kOut store (2/B)(o - targ), kOut2 store o, kLo low part of kOut, kRagged columns >= N exist.
+// in: kAux targets present (tg = targ[nc..nc+32)[m], loaded by the caller), kOut store (2/B)(o - targ), kOut2 store o, kLo low part of kOut, kRagged columns >= N exist.
 // Returns sq + this chunk's sum of (o - targ)^2, accumulated in column order with one fma per term as before.
 template <bool kAux, bool kOut, bool kOut2, bool kLo, bool kRagged>
-__device__ __forceinline__ float epi_fwd_out_chunk(const GemmParams& p, const uint32_t (&v)[32], int m, int nc,
-                                                   float bias, float sq) {
+__device__ __forceinline__ float epi_fwd_out_chunk(const GemmParams& p, const uint32_t (&v)[32], const float (&tg)[32],
+                                                   int m, int nc, float bias, float sq) {
   const int valid = kRagged ? p.N - nc : 32;
-  float tg[32];
-  if constexpr (kAux) {
-    const float* a = p.aux + size_t(nc) * p.ldaux + m;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) tg[j] = (!kRagged || j < valid) ? __ldg(a + size_t(j) * p.ldaux) : 0.0f;
-  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (!kRagged || j < valid) {
       const float o = fmaf(p.scale, __uint_as_float(v[j]), bias);
-      if constexpr (kOut2) p.out2[size_t(nc + j) * p.ldo2 + m] = o;
+      if constexpr (kOut2) st_global_f32(p.out2 + size_t(nc + j) * p.ldo2 + m, o);
       if constexpr (kAux) {
         const float diff = o - tg[j];
         if constexpr (kOut) {
           const float dv = p.gscale * diff;
-          p.out[size_t(nc + j) * p.ldo + m] = dv;
-          if constexpr (kLo) p.out_lo[size_t(nc + j) * p.ldo + m] = tf32_lo(dv);
+          st_global_f32(p.out + size_t(nc + j) * p.ldo + m, dv);
+          if constexpr (kLo) st_global_f32(p.out_lo + size_t(nc + j) * p.ldo + m, tf32_lo(dv));
         }
         sq = fmaf(diff, diff, sq);
       }
@@ -156,12 +161,12 @@ __device__ __forceinline__ void epi_dx_chunk(const GemmParams& p, const uint32_t
   const int valid = kRagged ? p.N - nc : 32;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
-    if (!kRagged || j < valid) o[size_t(j) * p.ldo] = d[j];
+    if (!kRagged || j < valid) st_global_f32(o + size_t(j) * p.ldo, d[j]);
   if constexpr (kLo) {
     float* ol = p.out_lo + size_t(nc) * p.ldo + m;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (!kRagged || j < valid) ol[size_t(j) * p.ldo] = tf32_lo(d[j]);
+      if (!kRagged || j < valid) st_global_f32(ol + size_t(j) * p.ldo, tf32_lo(d[j]));
   }
 }
 
@@ -182,7 +187,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j, o += p.ldo)
-          if (whole || nc + j < p.N) *o = __uint_as_float(v[j]);
+          if (whole || nc + j < p.N) st_global_f32(o, __uint_as_float(v[j]));
       }
     }
   } else if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_HID_MASK) {
@@ -217,33 +222,33 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
         }
       }
 #undef BP_HID
-      if constexpr (kEpi == EPI_FWD_HID_MASK) p.relu_mask[size_t(nc >> 5) * p.ldmask + m] = bits;
+      if constexpr (kEpi == EPI_FWD_HID_MASK) st_global_u32(p.relu_mask + size_t(nc >> 5) * p.ldmask + m, bits);
     }
   } else if constexpr (kEpi == EPI_FWD_OUT) {
     if (m_ok) {
       // the combinations the runtime issues, each with its switches compiled in (see epi_fwd_out_chunk); anything else
       // takes the generic loop
       const bool aux = p.aux != nullptr, out = p.out != nullptr, out2 = p.out2 != nullptr, lo = p.out_lo != nullptr;
-      if (aux && out && !out2) {                       // training: D_L = (2/B)(o - targ), loss monitor
-        if (whole) { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, false>(p, v, m, nc, bias, sq_local);
-                     else sq_local = epi_fwd_out_chunk<true, true, false, false, false>(p, v, m, nc, bias, sq_local); }
-        else       { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, true>(p, v, m, nc, bias, sq_local);
-                     else sq_local = epi_fwd_out_chunk<true, true, false, false, true>(p, v, m, nc, bias, sq_local); }
-      } else if (!aux && !out && out2) {               // decode: raw linear output
-        if (whole) epi_fwd_out_chunk<false, false, true, false, false>(p, v, m, nc, bias, 0.0f);
-        else epi_fwd_out_chunk<false, false, true, false, true>(p, v, m, nc, bias, 0.0f);
-      } else if (aux && !out) {                        // cross-validation: score, optionally the output too
-        if (whole) { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, false>(p, v, m, nc, bias, sq_local);
-                     else sq_local = epi_fwd_out_chunk<true, false, false, false, false>(p, v, m, nc, bias, sq_local); }
-        else       { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, true>(p, v, m, nc, bias, sq_local);
-                     else sq_local = epi_fwd_out_chunk<true, false, false, false, true>(p, v, m, nc, bias, sq_local); }
-      } else {
-        float tg[32];
-        if (aux) {
-          const float* a = p.aux + size_t(nc) * p.ldaux + m;
+      float tg[32];
+      if (aux) {
+        const float* a = p.aux + size_t(nc) * p.ldaux + m;
 #pragma unroll
-          for (int j = 0; j < 32; ++j, a += p.ldaux) tg[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
-        }
+        for (int j = 0; j < 32; ++j) tg[j] = (whole || nc + j < p.N) ? __ldg(a + size_t(j) * p.ldaux) : 0.0f;
+      }
+      if (aux && out && !out2) {                       // training: D_L = (2/B)(o - targ), loss monitor
+        if (whole) { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, false>(p, v, tg, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, true, false, false, false>(p, v, tg, m, nc, bias, sq_local); }
+        else       { if (lo) sq_local = epi_fwd_out_chunk<true, true, false, true, true>(p, v, tg, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, true, false, false, true>(p, v, tg, m, nc, bias, sq_local); }
+      } else if (!aux && !out && out2) {               // decode: raw linear output
+        if (whole) epi_fwd_out_chunk<false, false, true, false, false>(p, v, tg, m, nc, bias, 0.0f);
+        else epi_fwd_out_chunk<false, false, true, false, true>(p, v, tg, m, nc, bias, 0.0f);
+      } else if (aux && !out) {                        // cross-validation: score, optionally the output too
+        if (whole) { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, false>(p, v, tg, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, false, false, false, false>(p, v, tg, m, nc, bias, sq_local); }
+        else       { if (out2) sq_local = epi_fwd_out_chunk<true, false, true, false, true>(p, v, tg, m, nc, bias, sq_local);
+                     else sq_local = epi_fwd_out_chunk<true, false, false, false, true>(p, v, tg, m, nc, bias, sq_local); }
+      } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (whole || nc + j < p.N) {
@@ -455,6 +460,37 @@ __device__ __forceinline__ void gemm_dx_epilogue(const GemmParams& p, DxPrefetch
     gemm_dx_store(p, v, pre.y[1], m, m_ok, nc + 32);
     if (c + 3 < BLOCK_N / 32) pre.load(p, 1, m, m_ok, nc + 96);
   }
+}
+
+// Output-layer epilogue for training (targets present, D_L stored, no raw output) with the targets software-pipelined
+// like EPI_DX's Y operand: the first two chunks are in registers before the accumulator is complete.
+template <int BLOCK_N>
+__device__ __forceinline__ float gemm_fwdout_train_epilogue(const GemmParams& p, DxPrefetch& pre, uint32_t taddr, int m,
+                                                            bool m_ok, int n0, float bias, float sq) {
+  auto one = [&](const uint32_t (&v)[32], const float (&tg)[32], int nc) {
+    if (!m_ok) return;
+    const bool whole = nc + 32 <= p.N, lo = p.out_lo != nullptr;
+    if (whole) { if (lo) sq = epi_fwd_out_chunk<true, true, false, true, false>(p, v, tg, m, nc, bias, sq);
+                 else sq = epi_fwd_out_chunk<true, true, false, false, false>(p, v, tg, m, nc, bias, sq); }
+    else       { if (lo) sq = epi_fwd_out_chunk<true, true, false, true, true>(p, v, tg, m, nc, bias, sq);
+                 else sq = epi_fwd_out_chunk<true, true, false, false, true>(p, v, tg, m, nc, bias, sq); }
+  };
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N / 32; c += 2) {
+    const int nc = n0 + c * 32;
+    if (nc >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + uint32_t(c * 32), v);
+    tmem_ld_wait();
+    one(v, pre.y[0], nc);
+    if (c + 2 < BLOCK_N / 32) pre.load(p, 0, m, m_ok, nc + 64);
+    if (nc + 32 >= p.N) break;
+    tmem_ld32(taddr + uint32_t((c + 1) * 32), v);
+    tmem_ld_wait();
+    one(v, pre.y[1], nc + 32);
+    if (c + 3 < BLOCK_N / 32) pre.load(p, 1, m, m_ok, nc + 96);
+  }
+  return sq;
 }
 
 template <bool kAMN, bool kBMN, int kEpi, int BLOCK_N>

@@ -477,4 +477,39 @@ int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue,
   return rc;
 }
 
+// Bring-up aid: aggregate GB/s of the epilogue store pattern into a buffer of `mb` megabytes (larger than L2 so that
+// every line is a write miss with a dirty victim), `reps` passes.  layout 0: tiles of a row-major [rows x ld] matrix
+// (128 row segments of 512 B, ld*4 bytes apart); layout 1: every tile one contiguous 64 KB region.
+int bp_debug_store_pattern(int layout, int ld, int mb, int reps, int ctas, double* gbs) {
+  if (!gbs || ld < 128 || ld % 128 != 0 || mb <= 0 || reps <= 0 || ctas <= 0) return fail(BP_EINVAL, "bad argument");
+  float* buf = nullptr;
+  const long long floats = (long long)mb * 1024 * 1024 / 4;
+  const long long rows = floats / ld / 128 * 128;      // whole 128-row panels
+  const long long n_tiles = rows / 128 * (ld / 128);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = [&]() -> int {
+    CU_TRY(cudaMalloc(&buf, floats * 4));
+    CU_TRY(cudaMemset(buf, 0, floats * 4));
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    for (int rep = 0; rep <= reps; ++rep) {
+      if (rep == 1) CU_TRY(cudaEventRecord(e0));
+      if (layout == 0)  // panel = 128 rows of the matrix; tiles of a panel 128 floats apart
+        bp_store_pattern_kernel<<<ctas, 128>>>(buf, ld, 128, ld / 128, 128LL * ld, n_tiles, (float)rep);
+      else              // same tiles, each contiguous
+        bp_store_pattern_kernel<<<ctas, 128>>>(buf, 128, 128 * 128, ld / 128, 128LL * ld, n_tiles, (float)rep);
+    }
+    CU_TRY(cudaEventRecord(e1));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs = (double)n_tiles * 65536.0 * reps / (ms * 1e-3) / 1e9;
+    return BP_OK;
+  }();
+  cudaFree(buf);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
+}
+
 }  // extern "C"

@@ -68,4 +68,18 @@ __global__ void __launch_bounds__(64, 1) bp_mma_rate_kernel(int iters, int mode,
   }
 }
 
+// Store-pattern microbenchmark: what the memory system does with an epilogue's writes.  Every CTA (128 threads) writes
+// tiles of 128 rows x 128 floats: thread t writes float t of every row (one coalesced 512-byte row segment per CTA and
+// row, 128 bytes per warp instruction — exactly the GEMM epilogues' pattern).  row_stride = 128: the tile is ONE
+// contiguous 64 KB region; row_stride = ld of an activation matrix: 128 segments of 512 B, ld*4 bytes apart.
+__global__ void __launch_bounds__(128) bp_store_pattern_kernel(float* buf, long long row_stride, long long tile_stride,
+                                                               int tiles_per_panel, long long panel_stride,
+                                                               long long n_tiles, float v) {
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    float* base = buf + (t / tiles_per_panel) * panel_stride + (t % tiles_per_panel) * tile_stride + threadIdx.x;
+#pragma unroll 32
+    for (int n = 0; n < 128; ++n) base[n * row_stride] = v;
+  }
+}
+
 }  // namespace bp

@@ -233,11 +233,12 @@ struct Rank {
   // product in a second one.  Built lazily (after the peer-memory slabs are known), rebuilt when an option changes.
   struct ChainPlan {
     int n_prods = 0, n_items = 0;
-    ChainProd* d_prods = nullptr;
-    ChainItem* d_items = nullptr;
-    int* d_pair_off = nullptr;
+    std::vector<ChainProd> h_prods;   // the launch description is assembled from these per bunch (kernel parameters)
     long long makespan = 0;      // the scheduler's estimate, SM cycles
+    std::vector<ChainItem> h_items;   // host copies for bp_debug_chain_trace
+    std::vector<int> h_pair_off;
     int pair_n_l1 = 128;         // tile width of the product whose B operand is this bunch's input rows
+    int max_pair_n = 128;        // widest tile of the plan: decides the ring geometry (4 x 48 KB or 3 x 64 KB)
   };
   static constexpr int kChainCounters = 1024;
   int use_chain = 1;             // bp_set_option("chain", 0) restores one launch per product
@@ -246,6 +247,10 @@ struct Rank {
   ChainPlan chain_fwd, chain_bwd;
   CUtensorMap* chain_maps = nullptr;
   uint32_t* chain_counters = nullptr;   // 2 sets of kChainCounters
+  int chain_prefetch = 1;        // bp_set_option("chain_prefetch", 0): no L2 prefetch of later operands
+  int chain_fwd_only = 0;        // measurement aid: a train bunch stops after the forward launch
+  unsigned long long* chain_trace = nullptr;  // bp_set_option("chain_trace", 1): stamps of the most recent launches
+  int chain_trace_on = 0;
   int chain_set = 0;
 
   int gemm_sms() const { return nccl_comm ? std::max(8, num_sms - comm_sms) : num_sms; }
@@ -281,6 +286,7 @@ int ensure_chunk(Rank* r, ChunkBuf& c, long long rows) {
 }
 
 void rank_p2p_release(Rank* r);
+void chain_release(Rank* r);
 
 int rank_destroy(Rank* r) {
   if (!r) return BP_OK;
@@ -288,6 +294,9 @@ int rank_destroy(Rank* r) {
   cudaDeviceSynchronize();
   if (r->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(r->nccl_comm);
   rank_p2p_release(r);
+  chain_release(r);
+  cudaFree(r->chain_counters);
+  cudaFree(r->chain_trace);
   for (auto& c : r->chunk) {
     cudaFree(c.x);
     cudaFree(c.x_lo);
@@ -436,6 +445,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
   if (const char* e = getenv("BP_RELU_MASK")) r->relu_mask = atoi(e) != 0;
+  if (const char* e = getenv("BP_CHAIN")) r->use_chain = atoi(e) != 0;
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
@@ -712,6 +722,27 @@ static const char* const kDxLabel[BP_MAXLAYER] = {"", "dx1", "dx2", "dx3", "dx4"
 static const char* const kDwLabel[BP_MAXLAYER] = {"", "dw1 (side)", "dw2 (side)", "dw3 (side)", "dw4 (side)", "dw5 (side)",
                                                   "dw6 (side)", "dw7 (side)", "dw8 (side)", "dw9 (side)"};
 
+// kernDropout on the device copy of the input bunch (BP_GPU.cu:536-540): rows [f0, f0+n) of the resident chunk, in place.
+int input_dropout(Rank* r, ChunkBuf& c, int f0, int n) {
+  const bp_config& cf = r->cfg;
+  if (cf.dropoutflag != 1 || !(cf.visible_omit > 0.0f)) return BP_OK;
+  const uint32_t seed_lo = (uint32_t)cf.seed, seed_hi = (uint32_t)(cf.seed >> 32);
+  const int frame0 = cf.rank * r->local_bunch;
+  dim3 grid((r->K0() + 255) / 256, (n + 3) / 4);
+  bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(c.x + (long long)f0 * r->ldx, r->ldx, n, r->K0(),
+                                                        cf.visible_omit, seed_lo, seed_hi, r->step, frame0);
+  CU_TRY(cudaGetLastError());
+  r->launches++;
+  tl_mark(r, r->compute, "input dropout");
+  if (r->passes == 3) {  // the same mask on the low part
+    bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(c.x_lo + (long long)f0 * r->ldx, r->ldx, n, r->K0(),
+                                                          cf.visible_omit, seed_lo, seed_hi, r->step, frame0);
+    CU_TRY(cudaGetLastError());
+    r->launches++;
+  }
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // Forward over rows [f0, f0+n) of the resident chunk.  train=true: masks + D_L; train=false: keep-scaling (CV).
 int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, long long ldo2, double* sqerr) {
@@ -722,20 +753,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
   const int frame0 = cf.rank * r->local_bunch;
   float* xb = c.x + (long long)f0 * r->ldx;
 
-  if (train && drop && cf.visible_omit > 0.0f) {
-    dim3 grid((r->K0() + 255) / 256, (n + 3) / 4);
-    bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(xb, r->ldx, n, r->K0(), cf.visible_omit, seed_lo, seed_hi,
-                                                          r->step, frame0);
-    CU_TRY(cudaGetLastError());
-    r->launches++;
-    if (train) tl_mark(r, r->compute, "input dropout");
-    if (r->passes == 3) {  // the same mask on the low part
-      bp_input_dropout_kernel<<<grid, 256, 0, r->compute>>>(c.x_lo + (long long)f0 * r->ldx, r->ldx, n, r->K0(),
-                                                            cf.visible_omit, seed_lo, seed_hi, r->step, frame0);
-      CU_TRY(cudaGetLastError());
-      r->launches++;
-    }
-  }
+  if (train) BP_TRY(input_dropout(r, c, f0, n));
   for (int l = 1; l <= r->L; ++l) {
     LayerState& ls = r->layer[l];
     GemmParams p{};
@@ -923,6 +941,7 @@ int rank_p2p_connect_ipc(Rank* r) {
   CU_TRY(cudaMemcpyAsync(&bad, dbad, sizeof(float), cudaMemcpyDeviceToHost, r->compute));
   CU_TRY(cudaStreamSynchronize(r->compute));
   CU_TRY(cudaFree(dev));
+  r->chain_built = false;  // the dW products' scatter targets are the peers' slabs
   if (bad == 0.0f) {
     r->dp_p2p = 1;
     if (me == 0 && getenv("BP_VERBOSE")) fprintf(stderr, "libbpgpu: gradient exchange over peer memory, %d ranks\n", W);
@@ -1012,9 +1031,6 @@ int peer_exchange_part(Rank* r, int part, unsigned long long step, long long beg
 // ------------------------------------------------------------------------------------------------ chained products
 void chain_release(Rank* r) {
   for (Rank::ChainPlan* pl : {&r->chain_fwd, &r->chain_bwd}) {
-    cudaFree(pl->d_prods);
-    cudaFree(pl->d_items);
-    cudaFree(pl->d_pair_off);
     *pl = Rank::ChainPlan{};
   }
   cudaFree(r->chain_maps);
@@ -1031,18 +1047,23 @@ inline int chain_pair_n(int M, int N, int pairs, bool have_narrow_b) {
 }
 
 int chain_upload_plan(Rank* r, Rank::ChainPlan& pl, std::vector<ChainProd>& prods, std::vector<ChainShape>& shapes) {
+  pl.max_pair_n = 128;
+  for (const ChainProd& q : prods) {
+    if (q.dep_prod >= 0) prods[q.dep_prod].has_consumer = 1;
+    pl.max_pair_n = std::max(pl.max_pair_n, q.pair_n);
+  }
   std::vector<ChainItem> items;
   std::vector<int> pair_off;
   pl.makespan = chain_schedule(shapes, r->chain_pairs, items, pair_off);
   if (pl.makespan < 0) return fail(BP_EINVAL, "chain: dependency cycle in the product table");
   pl.n_prods = (int)prods.size();
   pl.n_items = (int)items.size();
-  CU_TRY(cudaMalloc(&pl.d_prods, prods.size() * sizeof(ChainProd)));
-  CU_TRY(cudaMalloc(&pl.d_items, std::max<size_t>(1, items.size()) * sizeof(ChainItem)));
-  CU_TRY(cudaMalloc(&pl.d_pair_off, pair_off.size() * sizeof(int)));
-  CU_TRY(cudaMemcpy(pl.d_prods, prods.data(), prods.size() * sizeof(ChainProd), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(pl.d_items, items.data(), items.size() * sizeof(ChainItem), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(pl.d_pair_off, pair_off.data(), pair_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (pl.n_items > CHAIN_MAX_ITEMS || r->chain_pairs > CHAIN_MAX_PAIRS || pl.n_prods > CHAIN_MAX_PROD)
+    return fail(BP_EINVAL, "chain: %d tiles / %d pairs / %d products exceed the launch description", pl.n_items,
+                r->chain_pairs, pl.n_prods);
+  pl.h_prods = prods;
+  pl.h_items = items;
+  pl.h_pair_off = pair_off;
   return BP_OK;
 }
 
@@ -1230,30 +1251,132 @@ int chain_build(Rank* r) {
   return BP_OK;
 }
 
-int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float* targ, double* sqerr) {
-  ChainArgs a{};
-  a.prods = pl.d_prods;
+struct ChainPrefetch {
+  const void* base[6];
+  unsigned long long bytes[6];
+  int n = 0;
+  void add(const void* p, unsigned long long b) {
+    if (n < 6 && p && b >= 16384) { base[n] = p; bytes[n] = b; ++n; }
+  }
+};
+
+int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float* targ, double* sqerr,
+                 const ChainPrefetch& pf) {
+  static thread_local ChainArgs a;   // ~20 KB: keep it off the stack of deep call chains
+  memset(&a, 0, sizeof a);
+  if (r->chain_prefetch)
+    for (int i = 0; i < pf.n; ++i) {
+      a.pf_base[i] = pf.base[i];
+      a.pf_bytes[i] = pf.bytes[i];
+      a.n_pf = i + 1;
+    }
   a.n_prods = pl.n_prods;
-  a.items = pl.d_items;
-  a.pair_off = pl.d_pair_off;
+  for (int i = 0; i < pl.n_prods; ++i) {
+    a.prods[i] = pl.h_prods[i];
+    a.prods[i].p.step = r->step;
+    if (a.prods[i].per_bunch & 1) {
+      a.prods[i].p.aux = targ;
+      a.prods[i].p.sqerr = sqerr;
+    }
+  }
+  memcpy(a.items, pl.h_items.data(), pl.h_items.size() * sizeof(ChainItem));
+  memcpy(a.pair_off, pl.h_pair_off.data(), pl.h_pair_off.size() * sizeof(int));
   a.maps = r->chain_maps;
   a.dyn[0] = dyn_b.m;
   a.dyn[1] = dyn_b.lo;
   a.counters = r->chain_counters + (size_t)r->chain_set * Rank::kChainCounters;
   a.counters_next = r->chain_counters + (size_t)(r->chain_set ^ 1) * Rank::kChainCounters;
   a.n_counters = Rank::kChainCounters;
-  a.targ = targ;
-  a.sqerr = sqerr;
-  a.step = r->step;
+  a.stage_bytes = CHAIN_A_BYTES + (uint32_t)(pl.max_pair_n / 2) * GEMM_BLOCK_K * 4;
+  a.n_stages = (int)(CHAIN_RING_BYTES / a.stage_bytes);
+  if (r->chain_trace_on) {
+    if (!r->chain_trace) CU_TRY(cudaMalloc(&r->chain_trace, 2 * 4096 * 4 * sizeof(unsigned long long)));
+    a.trace = r->chain_trace + (&pl == &r->chain_bwd ? 4096 * 4 : 0);
+  }
   BP_TRY(launch_chain(r->compute, a, r->chain_pairs));
   r->chain_set ^= 1;
   r->launches++;
   return BP_OK;
 }
 
+// Momentum-SGD update of arena floats [4*begin4, 4*end4) (kernUpdatedelta + kernAccSum, DevFunc.cu:313-318, 270-277).
+int launch_sgd_range(Rank* r, long long begin4, long long end4, int blocks_per_sm) {
+  const bp_config& cf = r->cfg;
+  const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
+  const float c1 = (1 - cf.momentum) * cf.lrate;
+  const int sgd_stream = tunable(TUN_SGD_STREAM);
+  const int grid = r->num_sms * blocks_per_sm;
+  if (cf.weightcost != 0.0f)
+    bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4, end4,
+                                                      nf, cf.momentum, c1, cf.weightcost, r->bias_ranges,
+                                                      (float4*)r->w_lo, sgd_stream);
+  else
+    bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4, end4,
+                                                       nf, cf.momentum, c1, 0.0f, r->bias_ranges, (float4*)r->w_lo,
+                                                       sgd_stream);
+  CU_TRY(cudaGetLastError());
+  r->launches++;
+  return BP_OK;
+}
+
+int peer_exchange(Rank* r);
+
+// One train bunch as two chained launches (forward products; dX chain + dW products) and the update.
+int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
+  const int n = r->local_bunch;
+  if (!r->chain_built) BP_TRY(chain_build(r));
+  const bool prof = r->profiling;
+  int pe = 7 * (int)(r->prof_cnt % Rank::kProfCap);
+  auto mark = [&]() { if (prof) cudaEventRecord(r->pev[pe++], r->compute); };
+  mark();                                               // 0
+  r->tl_idx = 0;
+  tl_mark(r, r->compute, "start");
+  BP_TRY(input_dropout(r, c, f0, n));
+  float* xb = c.x + (long long)f0 * r->ldx;
+  const float* xlo = c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr;
+  MapPair xfwd, xdw;
+  BP_TRY(make_map(&xfwd, xb, xlo, r->K0(), n, r->ldx, r->chain_fwd.pair_n_l1 / 2, false));
+  ChainPrefetch pf_fwd, pf_bwd;
+  for (int l = 2; l <= r->L; ++l)  // the weights of the layers after the first, needed 15-60 us into the launch
+    pf_fwd.add(r->w + r->layer[l].off, (unsigned long long)r->layer[l].size * 4);
+  BP_TRY(chain_launch(r, r->chain_fwd, xfwd, c.t + (long long)f0 * r->Nout(), loss_slot, pf_fwd));
+  tl_mark(r, r->compute, "forward chain");
+  mark();                                               // 1: forward done
+  if (r->chain_fwd_only) {
+    for (int k = 0; k < 5; ++k) mark();
+    r->step++;
+    r->bunches++;
+    if (prof) r->prof_cnt++;
+    return BP_OK;
+  }
+  BP_TRY(make_map(&xdw, xb, xlo, r->K0() + 1, n, r->ldx, r->dw_bn, true));
+  if ((long long)f0 + 2LL * n <= c.rows)  // the next bunch's input rows (this chunk), for its first forward product
+    pf_bwd.add(xb + (long long)n * r->ldx, (unsigned long long)n * r->ldx * 4);
+  BP_TRY(chain_launch(r, r->chain_bwd, xdw, nullptr, nullptr, pf_bwd));
+  tl_mark(r, r->compute, "back-propagation chain");
+  mark();                                               // 2: dX chain and all dW done
+  mark();                                               // 3
+  mark();                                               // 4
+  mark();                                               // 5
+  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
+  else BP_TRY(launch_sgd_range(r, 0, r->arena_floats / 4, 8));
+  tl_mark(r, r->compute, "update / exchange, end of bunch");
+  mark();                                               // 6
+  r->step++;
+  r->bunches++;
+  if (prof) r->prof_cnt++;
+  if (r->timeline && r->tl_bunches < (uint64_t)Rank::kTlBunches) {
+    r->tl_marks = r->tl_idx;
+    r->tl_bunches++;
+  }
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ one train bunch
 int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
+  if (r->use_chain && (!r->nccl_comm || r->dp_p2p) && !(r->dp_p2p && r->peer_early))
+    return train_bunch_chain(r, c, f0, loss_slot);
   const int n = r->local_bunch;
   const bool prof = r->profiling;
   int pe = 7 * (int)(r->prof_cnt % Rank::kProfCap);
@@ -1662,7 +1785,10 @@ int group_p2p_connect(bp_handle* h) {
       pm.recv = h->ranks[j]->recv;
       pm.flags = h->ranks[j]->flags;
     }
-  for (Rank* r : h->ranks) r->dp_p2p = 1;
+  for (Rank* r : h->ranks) {
+    r->dp_p2p = 1;
+    r->chain_built = false;
+  }
   if (getenv("BP_VERBOSE")) fprintf(stderr, "libbpgpu: gradient exchange over peer memory, %d ranks (one process)\n", W);
   return BP_OK;
 }
@@ -1935,9 +2061,14 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
     else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
     else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
     else if (strcmp(name, "relu_mask") == 0) r->relu_mask = value != 0;    // between bunches only (bp_train* has returned)
+    else if (strcmp(name, "chain") == 0) r->use_chain = value != 0;        // 0: one launch per product
+    else if (strcmp(name, "chain_trace") == 0) r->chain_trace_on = value != 0;
+    else if (strcmp(name, "chain_prefetch") == 0) r->chain_prefetch = value != 0;
+    else if (strcmp(name, "chain_fwd_only") == 0) r->chain_fwd_only = value != 0;
     else if (strcmp(name, "l2_persist") == 0) rank_set_l2_persist(r, value);   // value = MB, <= 0 removes the window
     else if (set_tunable(name, value) != BP_OK)                            // process-wide switches (bp_internal.h)
       return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
+    r->chain_built = false;  // the product tables capture the switches (hints, streaming stores): rebuild lazily
   }
   return BP_OK;
 }
@@ -1978,8 +2109,38 @@ int bp_get_option(bp_handle* h, const char* name, int* value) {
   }
   if (strcmp(name, "peer_early") == 0) { *value = r->peer_early; return BP_OK; }
   if (strcmp(name, "relu_mask") == 0) { *value = r->relu_mask; return BP_OK; }
+  if (strcmp(name, "chain") == 0) { *value = r->use_chain; return BP_OK; }
   if (get_tunable(name, value) == BP_OK) return BP_OK;
   return fail(BP_EINVAL, "bp_get_option: unknown option '%s'", name);
+}
+
+// Bring-up aid: the stamps of the most recent chained launch (which: 0 forward, 1 back-propagation) as CSV text,
+// one line per tile: item,pair,prod,mt,nt,deps_ns,first_full_ns,acc_ready_ns,epilogue_done_ns (relative to the earliest).
+int bp_debug_chain_trace(bp_handle* h, int which, char* buf, int len) {
+  if (!h || !buf || len <= 0) return fail(BP_EINVAL, "bp_debug_chain_trace: null argument");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  if (!r->chain_trace || !r->chain_built) return fail(BP_EINVAL, "bp_debug_chain_trace: no traced launch yet");
+  CU_TRY(cudaStreamSynchronize(r->compute));
+  Rank::ChainPlan& pl = which ? r->chain_bwd : r->chain_fwd;
+  const int n = std::min(pl.n_items, 4096);
+  std::vector<unsigned long long> t((size_t)n * 4);
+  CU_TRY(cudaMemcpy(t.data(), r->chain_trace + (which ? 4096 * 4 : 0), t.size() * 8, cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (auto v : t) if (v && v < t0) t0 = v;
+  std::string out;
+  char line[160];
+  for (int p = 0; p + 1 < (int)pl.h_pair_off.size(); ++p)
+    for (int i = pl.h_pair_off[p]; i < pl.h_pair_off[p + 1] && i < n; ++i) {
+      const ChainItem& it = pl.h_items[i];
+      snprintf(line, sizeof line, "%d,%d,%d,%d,%d,%lld,%lld,%lld,%lld\n", i, p, it.prod, it.mt, it.nt,
+               (long long)(t[4 * i] - t0), (long long)(t[4 * i + 1] - t0), (long long)(t[4 * i + 2] - t0),
+               (long long)(t[4 * i + 3] - t0));
+      out += line;
+    }
+  if ((int)out.size() + 1 > len) return fail(BP_EINVAL, "bp_debug_chain_trace: buffer too small (%d needed)", (int)out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BP_OK;
 }
 
 int bp_sync(bp_handle* h) {

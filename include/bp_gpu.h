@@ -249,6 +249,13 @@ int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bun
  * shared memory.  combo 0 = A MN-major/B K-major, 1 = K/K, 2 = MN/MN, 3 = K/MN. */
 int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total);
 
+/* Bring-up aid of the chained launches (bp_set_option(h, "chain_trace", 1) first): per-tile timestamps of the most
+ * recent forward (which = 0) or back-propagation (which = 1) launch, CSV text. */
+int bp_debug_chain_trace(bp_handle* h, int which, char* buf, int len);
+
+/* Bring-up aid: GB/s of the GEMM epilogues' store pattern (layout 0: tiles of a row-major matrix, 1: contiguous tiles). */
+int bp_debug_store_pattern(int layout, int ld, int mb, int reps, int ctas, double* gbs);
+
 int bp_version(void);
 
 #ifdef __cplusplus
