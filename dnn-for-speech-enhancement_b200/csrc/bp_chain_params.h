@@ -34,6 +34,12 @@ struct ChainProd {
   int dep_all;           // 1: wait for all its n-tiles; 0: for those covering my tile's columns (frames)
   int per_bunch;         // bit 0: the host sets p.aux / p.sqerr to this bunch's targets / loss slot (output layer)
   int has_consumer;      // 1: some product of this launch waits for my tiles -> publish them (fence + counter)
+  // Data-parallel runs: my weights are rewritten by their owners' all-gather stores of the PREVIOUS step (bp_peer.cuh),
+  // which runs on another stream beside this launch: wait until each of the ext_n owners' "rows of this layer landed"
+  // counters (in this device's memory, system scope) has reached ext_target.  ext_n = 0: no such wait.
+  const unsigned long long* ext_flags;
+  int ext_n;
+  unsigned long long ext_target;
 };
 
 struct ChainItem {
@@ -62,6 +68,7 @@ struct ChainArgs {
   const void* pf_base[6];
   unsigned long long pf_bytes[6];
   int n_pf;
+  long long spin_limit;      // cycles after which a stalled wait traps: ~2 s; ~65 s when some product waits for peers
   unsigned long long* trace; // bring-up aid (null in production): per item 4 globaltimer stamps written by the leader
                              // CTA: dependencies satisfied, stores issued, accumulator complete, published
 };

@@ -57,11 +57,14 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parit
   return ok;
 }
 // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// `limit` (cycles): ~2 s by default; a kernel whose pipeline may legitimately stand still while one of its warps waits
+// for ANOTHER GPU (bp_chain.cuh, data-parallel runs) passes that wait's own, much longer limit.
+constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, long long limit = kSpinLimit) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > limit) {
       printf("bp_gemm: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
@@ -83,11 +86,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t p
       : "memory");
   return ok;
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, long long limit = kSpinLimit) {
   if (mbar_try_wait_hint(bar, parity, 1000u)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 1000u)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > limit) {
       printf("bp_gemm: mbarrier timeout (epilogue) block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }

@@ -133,7 +133,8 @@ struct ChunkBuf {
   bool consumed_valid = false;
 };
 
-constexpr int kPeerFlagGroups = 4;  // counter groups of the peer-memory exchange (Rank::flags)
+constexpr int kPeerFlagGroups = 4 + BP_MAXLAYER;  // counter groups of the peer-memory exchange (Rank::flags):
+                                                  // 0-3 see Rank::flags, 4 + l: weights of layer l landed (peer_overlap)
 
 struct Rank {
   bp_config cfg{};
@@ -200,7 +201,12 @@ struct Rank {
   unsigned long long* flags = nullptr;   // kPeerFlagGroups x kMaxPeers counters, group g at flags + g*kMaxPeers:
                                          // 0 gradients of step s landed from src, 1 weights landed from src;
                                          // BP_PEER_EARLY: 0/1 = layers >= 2, 2/3 = the same two for layer 1
-  int peer_early = 0;                    // BP_PEER_EARLY=1 (off by default, not yet run on GPUs)
+  int peer_early = 0;                    // BP_PEER_EARLY=1 (one-launch-per-product path only; measured slower at N = 2)
+  int peer_overlap = 1;                  // chained path: the owner update + all-gather of step s runs layer by layer on
+                                         // the communication stream BESIDE the forward launch of step s+1, whose
+                                         // products wait per layer for their weights (BP_PEER_OVERLAP=0: serial)
+  cudaEvent_t ev_bwd = nullptr, ev_exch = nullptr;
+  bool exch_pending = false;             // an overlapped exchange is in flight on comm_stream
   PeerMem peer[kMaxPeers];
   unsigned long long dp_step = 0;
   PeerLayers peer_layers{};
@@ -241,13 +247,17 @@ struct Rank {
     int max_pair_n = 128;        // widest tile of the plan: decides the ring geometry (4 x 48 KB or 3 x 64 KB)
   };
   static constexpr int kChainCounters = 1024;
-  int use_chain = 1;             // bp_set_option("chain", 0) restores one launch per product
+  int use_chain = -1;            // -1 automatic: chained launches for data-parallel ranks on peer memory (measured
+                                 // +6 % at 8 GPUs on C2, +13 % on C4, and the exchange overlaps the next forward
+                                 // launch), one launch per product on a single GPU (C2 5-9 % faster that way, C3
+                                 // equal, C4's net 3 % slower: profiles/r2d-f); 0 / 1 force (BP_CHAIN, option "chain")
   bool chain_built = false;
   int chain_pairs = 0;
   ChainPlan chain_fwd, chain_bwd;
   CUtensorMap* chain_maps = nullptr;
   uint32_t* chain_counters = nullptr;   // 2 sets of kChainCounters
   int chain_prefetch = 1;        // bp_set_option("chain_prefetch", 0): no L2 prefetch of later operands
+  int chain_pairs_cap = 0;       // > 0: use at most this many CTA pairs (leaves SMs to kernels of other streams)
   int chain_fwd_only = 0;        // measurement aid: a train bunch stops after the forward launch
   unsigned long long* chain_trace = nullptr;  // bp_set_option("chain_trace", 1): stamps of the most recent launches
   int chain_trace_on = 0;
@@ -323,7 +333,8 @@ int rank_destroy(Rank* r) {
   cudaFree(r->raw_targ);
   cudaFree(r->raw_tab);
   cudaFree(r->raw_norm);
-  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side, r->ev_upper, r->ev_comm_upper})
+  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side, r->ev_upper, r->ev_comm_upper, r->ev_bwd,
+                 r->ev_exch})
     if (e) cudaEventDestroy(e);
   for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
@@ -401,6 +412,24 @@ void rank_set_l2_persist(Rank* r, int mb) {
             v.accessPolicyWindow.hitRatio);
 }
 
+// CUDA loads kernels lazily, at their first launch, and a load may have to wait for the kernels that are running.  The
+// overlapped data-parallel exchange launches its kernels BESIDE a forward launch that is waiting for them, so every
+// kernel of this translation unit is loaded up front (the GEMM kernels are launched long before they matter).
+int preload_runtime_kernels() {
+  cudaFuncAttributes fa;
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_signal_kernel));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_wait_kernel));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_wait2_kernel));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, false>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, false>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, true>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, true>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<false>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<true>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_input_dropout_kernel));
+  return BP_OK;
+}
+
 int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* const* bias) {
   if (!cfg || !weights || !bias) return fail(BP_EINVAL, "bp_create: null argument");
   if (cfg->numlayers < 2 || cfg->numlayers > BP_MAXLAYER)
@@ -432,6 +461,7 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     return fail(BP_ENODEV, "device %d is sm_%d%d; libbpgpu is built for sm_100a only", cfg->device, prop.major,
                 prop.minor);
   CU_TRY(cudaSetDevice(cfg->device));
+  BP_TRY(preload_runtime_kernels());
 
   Rank* r = new Rank();
   r->cfg = *cfg;
@@ -445,13 +475,17 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
   if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
   if (const char* e = getenv("BP_RELU_MASK")) r->relu_mask = atoi(e) != 0;
-  if (const char* e = getenv("BP_CHAIN")) r->use_chain = atoi(e) != 0;
+  if (const char* e = getenv("BP_CHAIN")) r->use_chain = atoi(e) < 0 ? -1 : atoi(e) != 0;
+  if (const char* e = getenv("BP_PEER_OVERLAP")) r->peer_overlap = atoi(e) != 0;
+  if (const char* e = getenv("BP_CHAIN_PAIRS")) r->chain_pairs_cap = atoi(e);
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_side, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_bwd, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&r->ev_exch, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_upper, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_comm_upper, cudaEventDisableTiming));
     for (auto& e : r->ev_d) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1075,6 +1109,7 @@ int chain_build(Rank* r) {
   const int n = r->local_bunch;
   r->chain_pairs = chain_max_pairs(r->num_sms);
   if (r->chain_pairs <= 0) return fail(BP_ECUDA, "chain: no co-resident CTA pairs");
+  if (r->chain_pairs_cap > 0) r->chain_pairs = std::min(r->chain_pairs, r->chain_pairs_cap);
   if (!r->chain_counters) {
     CU_TRY(cudaMalloc(&r->chain_counters, 2 * Rank::kChainCounters * sizeof(uint32_t)));
     CU_TRY(cudaMemset(r->chain_counters, 0, 2 * Rank::kChainCounters * sizeof(uint32_t)));
@@ -1143,6 +1178,10 @@ int chain_build(Rank* r) {
       }
       q.dep_prod = l >= 2 ? l - 2 : -1;
       q.dep_all = 0;
+      if (r->dp_p2p && r->peer_overlap) {  // patched per bunch with the step to wait for (chain_launch)
+        q.ext_flags = r->flags + (size_t)(4 + l) * kMaxPeers;
+        q.ext_n = cf.world_size;
+      }
       if (l < r->L) {
         q.epi = EPI_FWD_HID;
         p.out = ls.y;
@@ -1271,9 +1310,13 @@ int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float
       a.n_pf = i + 1;
     }
   a.n_prods = pl.n_prods;
+  a.spin_limit = 4000000000LL;
   for (int i = 0; i < pl.n_prods; ++i) {
+    if (pl.h_prods[i].ext_n > 0 && r->cfg.world_size > 1)
+      a.spin_limit = 130000000000LL;  // the whole pipeline may wait for a late peer
     a.prods[i] = pl.h_prods[i];
     a.prods[i].p.step = r->step;
+    a.prods[i].ext_target = r->dp_step;  // the exchange of the previous bunch
     if (a.prods[i].per_bunch & 1) {
       a.prods[i].p.aux = targ;
       a.prods[i].p.sqerr = sqerr;
@@ -1321,6 +1364,53 @@ int launch_sgd_range(Rank* r, long long begin4, long long end4, int blocks_per_s
 
 int peer_exchange(Rank* r);
 
+// Overlapped exchange of the chained path.  Compute stream: publish "my partial gradients of step s have landed".
+// Communication stream, behind that: for l = 1..L the owner-side reduce + update + all-gather of layer l's rows
+// (2 blocks per SM: they fit beside a resident bp_chain_kernel CTA), then "my rows of layer l have landed" to every
+// peer.  Nothing waits on the compute stream: the next bunch's forward launch starts at once and ITS products wait,
+// layer by layer, for the owners' counters (ChainProd::ext_flags) — so the all-gather of the layers >= 2 hides under
+// the forward products before them.  Safe: a layer's weights are read by the forward product only after every
+// owner's rows landed; the receive slabs are rewritten by the NEXT back-propagation launch, which starts after that
+// forward launch, i.e. after every owner has published — and therefore finished reading — all its layers.
+int peer_exchange_layered(Rank* r) {
+  const bp_config& cf = r->cfg;
+  const int W = cf.world_size, me = cf.rank;
+  const unsigned long long step = ++r->dp_step;
+  PeerFlags fg{};
+  PeerArenas pa{};
+  for (int p = 0; p < W; ++p) {
+    fg.slot[p] = r->peer[p].flags + me;
+    pa.w[p] = (float4*)r->peer[p].w;
+    pa.w_lo[p] = (float4*)r->peer[p].w_lo;
+  }
+  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fg, W, step);
+  CU_TRY(cudaEventRecord(r->ev_bwd, r->compute));
+  CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_bwd, 0));
+  const float nf = (float)cf.bunchsize;
+  const float c1 = (1 - cf.momentum) * cf.lrate;
+  const int grid = r->num_sms * 2;
+  for (int l = 1; l <= r->L; ++l) {
+    const LayerState& ls = r->layer[l];
+    const long long b4 = ls.off / 4, e4 = (ls.off + ls.size) / 4;
+    if (cf.weightcost != 0.0f)
+      bp_peer_sgd_kernel<true, true><<<grid, 256, 0, r->comm_stream>>>((float4*)r->dw, (const float4*)r->recv,
+                                                                       r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                                       cf.momentum, c1, cf.weightcost, r->flags, step, b4, e4);
+    else
+      bp_peer_sgd_kernel<false, true><<<grid, 256, 0, r->comm_stream>>>((float4*)r->dw, (const float4*)r->recv,
+                                                                        r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
+                                                                        cf.momentum, c1, 0.0f, r->flags, step, b4, e4);
+    PeerFlags fw{};
+    for (int p = 0; p < W; ++p) fw.slot[p] = r->peer[p].flags + (size_t)(4 + l) * kMaxPeers + me;
+    bp_peer_signal_kernel<<<1, 32, 0, r->comm_stream>>>(fw, W, step);
+  }
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(r->ev_exch, r->comm_stream));
+  r->exch_pending = true;
+  r->launches += 1 + 2 * r->L;
+  return BP_OK;
+}
+
 // One train bunch as two chained launches (forward products; dX chain + dW products) and the update.
 int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const int n = r->local_bunch;
@@ -1358,7 +1448,8 @@ int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   mark();                                               // 3
   mark();                                               // 4
   mark();                                               // 5
-  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
+  if (r->dp_p2p && r->peer_overlap) BP_TRY(peer_exchange_layered(r));  // ... beside the next bunch's forward launch
+  else if (r->dp_p2p) BP_TRY(peer_exchange(r));         // owner-side reduce + update + all-gather
   else BP_TRY(launch_sgd_range(r, 0, r->arena_floats / 4, 8));
   tl_mark(r, r->compute, "update / exchange, end of bunch");
   mark();                                               // 6
@@ -1375,7 +1466,8 @@ int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
 // ------------------------------------------------------------------------------------------------ one train bunch
 int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
-  if (r->use_chain && (!r->nccl_comm || r->dp_p2p) && !(r->dp_p2p && r->peer_early))
+  const bool want_chain = r->use_chain == 1 || (r->use_chain < 0 && r->dp_p2p);
+  if (want_chain && (!r->nccl_comm || r->dp_p2p) && !(r->dp_p2p && r->peer_early))
     return train_bunch_chain(r, c, f0, loss_slot);
   const int n = r->local_bunch;
   const bool prof = r->profiling;
@@ -1592,6 +1684,10 @@ int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   r->loss_cur = li;
   for (int b = 0; b < n_bunches; ++b)
     BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev[li] + b));
+  if (r->exch_pending) {  // whatever follows this call on the compute stream sees the exchanged weights
+    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_exch, 0));
+    r->exch_pending = false;
+  }
   CU_TRY(cudaEventRecord(r->loss_done[li], r->compute));
   CU_TRY(cudaEventRecord(c.consumed, r->compute));
   c.consumed_valid = true;
@@ -1944,7 +2040,8 @@ int bp_decode_raw_wait(bp_handle* h) {
 int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
   if (!h || !rc) return fail(BP_EINVAL, "null argument");
   if (!rc->targ_records) return fail(BP_EINVAL, "bp_train_raw: no target records");
-  const int B = h->ranks[0]->cfg.bunchsize;
+  // a rank handle (one process per GPU) is given ITS rows of every global bunch, as in bp_train
+  const int B = (h->ranks.size() == 1) ? h->ranks[0]->local_bunch : h->ranks[0]->cfg.bunchsize;
   const int nb = rc->n_samples / B;
   if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
@@ -2061,9 +2158,14 @@ int bp_set_option(bp_handle* h, const char* name, int value) {
     else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
     else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
     else if (strcmp(name, "relu_mask") == 0) r->relu_mask = value != 0;    // between bunches only (bp_train* has returned)
-    else if (strcmp(name, "chain") == 0) r->use_chain = value != 0;        // 0: one launch per product
+    else if (strcmp(name, "chain") == 0) r->use_chain = value < 0 ? -1 : value != 0;  // -1 auto, 0 per product, 1 chained
     else if (strcmp(name, "chain_trace") == 0) r->chain_trace_on = value != 0;
     else if (strcmp(name, "chain_prefetch") == 0) r->chain_prefetch = value != 0;
+    else if (strcmp(name, "peer_overlap") == 0) {  // every rank the same value, and only before the first bunch: the
+      if (r->dp_step > 0)                          // per-layer counters of the two modes are not kept in step
+        return fail(BP_EINVAL, "bp_set_option: peer_overlap can only be changed before the first train bunch");
+      r->peer_overlap = value != 0;
+    }
     else if (strcmp(name, "chain_fwd_only") == 0) r->chain_fwd_only = value != 0;
     else if (strcmp(name, "l2_persist") == 0) rank_set_l2_persist(r, value);   // value = MB, <= 0 removes the window
     else if (set_tunable(name, value) != BP_OK)                            // process-wide switches (bp_internal.h)
@@ -2110,8 +2212,85 @@ int bp_get_option(bp_handle* h, const char* name, int* value) {
   if (strcmp(name, "peer_early") == 0) { *value = r->peer_early; return BP_OK; }
   if (strcmp(name, "relu_mask") == 0) { *value = r->relu_mask; return BP_OK; }
   if (strcmp(name, "chain") == 0) { *value = r->use_chain; return BP_OK; }
+  if (strcmp(name, "peer_overlap") == 0) { *value = r->peer_overlap; return BP_OK; }
   if (get_tunable(name, value) == BP_OK) return BP_OK;
   return fail(BP_EINVAL, "bp_get_option: unknown option '%s'", name);
+}
+
+// Bring-up aid: can a small kernel become resident BESIDE a running bp_chain_kernel?  The forward launch of one bunch
+// is made to wait (all products) for a counter that only a later launch on another stream sets: `blocks_per_sm` x
+// `threads` filler blocks spinning ~20 us, then a one-thread kernel that releases the counter.  Returns BP_OK and the
+// elapsed ms if the forward launch completed, a CUDA error (its waits trap after ~2 s) if the two cannot co-reside.
+__global__ void bp_coreside_filler_kernel(unsigned long long* sink) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < 40000) {}
+  if (threadIdx.x == 0 && blockIdx.x == 0) sink[1] = (unsigned long long)clock64();
+}
+__global__ void bp_coreside_release_kernel(unsigned long long* flag) {
+  __threadfence_system();
+  st_release_sys(flag, 1ull);
+}
+int bp_debug_coresidency(bp_handle* h, int blocks_per_sm, int threads, float* ms) {
+  if (!h || !ms) return fail(BP_EINVAL, "bp_debug_coresidency: null argument");
+  Rank* r = h->ranks[0];
+  CU_TRY(cudaSetDevice(r->cfg.device));
+  {  // kernels are loaded lazily and loading may synchronise with running kernels: load these two now
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, bp_coreside_filler_kernel));
+    CU_TRY(cudaFuncGetAttributes(&fa, bp_coreside_release_kernel));
+  }
+  ChunkBuf& c = r->chunk[r->cur];
+  if (!c.x || !c.has_targ || c.rows < r->local_bunch) return fail(BP_EINVAL, "bp_debug_coresidency: upload a chunk first");
+  if (!r->chain_built) BP_TRY(chain_build(r));
+  unsigned long long* flag = nullptr;
+  CU_TRY(cudaMalloc(&flag, 64));
+  CU_TRY(cudaMemset(flag, 0, 64));
+  std::vector<ChainProd> keep = r->chain_fwd.h_prods;
+  for (ChainProd& q : r->chain_fwd.h_prods) {
+    q.ext_flags = flag;
+    q.ext_n = 1;
+  }
+  const unsigned long long keep_step = r->dp_step;
+  r->dp_step = 1;  // ext_target
+  MapPair xfwd;
+  int rc = make_map(&xfwd, c.x, c.x_lo, r->K0(), r->local_bunch, r->ldx, r->chain_fwd.pair_n_l1 / 2, false);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (rc == BP_OK) {
+    cudaStreamSynchronize(r->compute);
+    cudaEventRecord(e0, r->compute);
+    ChainPrefetch pf;
+    rc = chain_launch(r, r->chain_fwd, xfwd, c.t, r->sqerr_dev, pf);
+    // NB chain_launch sets the ~65 s limit because of ext_n; a failure shows as a long stall, so keep the box safe:
+    cudaEventRecord(e1, r->compute);
+    if (getenv("BP_CORESIDE_CARVEOUT")) {  // same shared-memory carve-out as the resident kernel's SMs
+      cudaFuncSetAttribute(bp_coreside_filler_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(bp_coreside_release_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+    }
+    size_t dyn = 0;
+    if (const char* e = getenv("BP_CORESIDE_SMEM")) {  // same carve-out CLASS as the resident kernel: same dynamic size
+      dyn = (size_t)atoi(e) * 1024;
+      cudaFuncSetAttribute(bp_coreside_filler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(bp_coreside_release_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    }
+    if (blocks_per_sm > 0) bp_coreside_filler_kernel<<<blocks_per_sm, threads, dyn, r->comm_stream>>>(flag + 2);
+    bp_coreside_release_kernel<<<1, 1, dyn, r->comm_stream>>>(flag);
+    if (cudaGetLastError() != cudaSuccess) fprintf(stderr, "coreside: launch of the small kernels failed\n");
+  }
+  r->chain_fwd.h_prods = keep;
+  r->dp_step = keep_step;
+  cudaError_t e = cudaStreamSynchronize(r->compute);
+  cudaStreamSynchronize(r->comm_stream);
+  if (rc == BP_OK && e == cudaSuccess) cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(flag);
+  if (rc != BP_OK) return rc;
+  CU_TRY(e);
+  return BP_OK;
 }
 
 // Bring-up aid: the stamps of the most recent chained launch (which: 0 forward, 1 back-propagation) as CSV text,

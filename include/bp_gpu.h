@@ -256,6 +256,9 @@ int bp_debug_chain_trace(bp_handle* h, int which, char* buf, int len);
 /* Bring-up aid: GB/s of the GEMM epilogues' store pattern (layout 0: tiles of a row-major matrix, 1: contiguous tiles). */
 int bp_debug_store_pattern(int layout, int ld, int mb, int reps, int ctas, double* gbs);
 
+/* Bring-up aid: does a kernel of blocks_per_sm x threads become resident beside a running chained forward launch? */
+int bp_debug_coresidency(bp_handle* h, int blocks_per_sm, int threads, float* ms);
+
 int bp_version(void);
 
 #ifdef __cplusplus
