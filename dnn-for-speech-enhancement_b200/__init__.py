@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     lib.bp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.bp_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     lib.bp_begin_epoch.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
+    lib.bp_set_dropout_seed.argtypes = [C.c_void_p, C.c_uint64]
     lib.bp_upload_raw_chunk.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_train_raw.argtypes = [C.c_void_p, C.POINTER(BpRawChunk)]
     lib.bp_decode_raw_submit.argtypes = [C.c_void_p, C.POINTER(BpRawChunk), _fp]
@@ -376,6 +377,10 @@ class BP_GPU:
         _check(load_library().bp_begin_epoch(self._h, lrate, momentum, weightcost, int(reset_dropout_step)),
                "bp_begin_epoch")
 
+    def set_dropout_seed(self, seed: int) -> None:
+        """Re-key the dropout masks from the next bunch on (bp_set_dropout_seed)."""
+        _check(load_library().bp_set_dropout_seed(self._h, C.c_uint64(seed & (2 ** 64 - 1))), "bp_set_dropout_seed")
+
     def timer_start(self) -> None:
         _check(load_library().bp_timer_start(self._h), "bp_timer_start")
 
@@ -434,9 +439,13 @@ def dropout_mask(seed: int, step: int, layer: int, frame: int, unit: int, p: flo
     return int(load_library().bp_dropout_mask(seed, step, layer, frame, unit, p))
 
 
-def declared_symbols() -> List[str]:
-    """Entry points declared in include/bp_gpu.h (parsed from the header)."""
+def declared_symbols(debug: bool = True) -> List[str]:
+    """Entry points declared in include/bp_gpu.h (the drop-in boundary) and, with debug=True, include/bp_gpu_debug.h
+    (test and bring-up aids) — parsed from the headers."""
     import re
-    txt = open(HEADER_PATH).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(bp_[a-z_0-9]+)\s*\(", txt)))
+    names = set()
+    for path in [HEADER_PATH] + ([HEADER_PATH.replace("bp_gpu.h", "bp_gpu_debug.h")] if debug else []):
+        txt = open(path).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"\b(bp_[a-z_0-9]+)\s*\(", txt))
+    return sorted(names)

@@ -38,11 +38,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned long long chain_ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -51,18 +46,15 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Bounded poll of one dependency counter (one lane of the producer warp).
-__device__ __forceinline__ void chain_wait_counter(const uint32_t* c, uint32_t target, long long limit) {
+__device__ __forceinline__ void chain_wait_counter(const uint32_t* c, uint32_t target) {
   if (ld_acquire_gpu_u32(c) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire_gpu_u32(c) < target) {
     __nanosleep(40);
-    if (clock64() - t0 > limit) {  // a scheduling bug becomes a CUDA error, never a hung box
+    if (clock64() - t0 > kSpinLimit) {  // ~2 s: a scheduling bug becomes a CUDA error, never a hung box
       printf("bp_chain: dependency timeout block %d (counter %p = %u < %u)\n", (int)blockIdx.x, (const void*)c,
              ld_acquire_gpu_u32(c), target);
       __trap();
@@ -74,7 +66,7 @@ __device__ __forceinline__ void chain_wait_counter(const uint32_t* c, uint32_t t
 template <bool kAMN, bool kBMN, int PAIR_N>
 __device__ __forceinline__ void chain_mma_item(uint64_t* full, uint64_t* empty, uint64_t* tfull, uint32_t smem_base,
                                                uint32_t d_tmem, int num_it, int as, int& s, uint32_t& ph, int lane,
-                                               uint32_t stage_bytes, int n_stages, long long spin_limit) {
+                                               uint32_t stage_bytes, int n_stages) {
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
   constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
   constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (kLayoutSW128Base32 << 29);
@@ -84,7 +76,7 @@ __device__ __forceinline__ void chain_mma_item(uint64_t* full, uint64_t* empty, 
   constexpr uint32_t idesc = make_idesc_tf32(2 * BLOCK_M, PAIR_N, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
   constexpr int kPollLane = 1;
   for (int kb = 0; kb < num_it; ++kb) {
-    if (lane == kPollLane) mbar_wait(&full[s], ph, spin_limit);
+    if (lane == kPollLane) mbar_wait(&full[s], ph);
     __syncwarp();
     tc_fence_after();
     const uint32_t sa = smem_base + uint32_t(s) * stage_bytes;
@@ -107,11 +99,7 @@ __device__ __forceinline__ void chain_mma_item(uint64_t* full, uint64_t* empty, 
   }
 }
 
-// __maxnreg__(192): registers are allocated to a CTA in units of 4 warps, so this 6-warp kernel is charged for 8; at
-// 255 registers per thread that is the whole register file of the SM and nothing else can become resident beside it —
-// the data-parallel exchange kernels (bp_peer.cuh, 2 blocks x 256 threads x 32 registers per SM) must, because the
-// forward launch of the next bunch waits for them (peer_exchange_layered).  8 x 32 x 192 = 48 K leaves them 16 K.
-__global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainArgs a) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) bp_chain_kernel(const __grid_constant__ ChainArgs a) {
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K;
   constexpr uint32_t A_BYTES = CHAIN_A_BYTES;
   constexpr uint32_t TMEM_COLS = 512;
@@ -160,15 +148,6 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int it0 = a.pair_off[pair], it1 = a.pair_off[pair + 1];
-  if (warp >= 2 && lane == 0 && a.n_pf > 0) {  // the epilogue warps have nothing to do until the first accumulator
-    constexpr unsigned long long kPf = 16384;
-    const unsigned long long w = (unsigned long long)blockIdx.x * 4 + (warp - 2), nw = (unsigned long long)gridDim.x * 4;
-    for (int rgn = 0; rgn < a.n_pf; ++rgn) {
-      const char* base = static_cast<const char*>(a.pf_base[rgn]);
-      const unsigned long long chunks = a.pf_bytes[rgn] / kPf;
-      for (unsigned long long c = w; c < chunks; c += nw) bulk_prefetch_l2(base + c * kPf, (uint32_t)kPf);
-    }
-  }
   auto map_ptr = [&](int idx) -> const CUtensorMap* { return idx >= 0 ? a.maps + idx : &a.dyn[-1 - idx]; };
 
   if (warp == 0) {
@@ -190,22 +169,6 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
       const CUtensorMap* mAlo = map_ptr(q.map_a_lo);
       const CUtensorMap* mBlo = map_ptr(q.map_b_lo);
       const unsigned long long hint_a = q.p.hint_a, hint_b = q.p.hint_b;
-      if (q.ext_n > 0) {  // data-parallel: every owner's rows of these weights (previous step) have landed
-        if (lane == kPollLane) {
-          for (int pr = 0; pr < q.ext_n; ++pr) {
-            const long long t0 = clock64();
-            while (chain_ld_acquire_sys(q.ext_flags + pr) < q.ext_target) {
-              __nanosleep(100);
-              if (clock64() - t0 > 120000000000LL) {  // ~60 s: a peer that died, not one that is late
-                printf("bp_chain: timeout waiting for the weights of rank %d (step %llu)\n", pr, q.ext_target);
-                __trap();
-              }
-            }
-          }
-        }
-        __syncwarp();
-        fence_proxy_async_global();
-      }
       if (q.dep_prod >= 0) {  // operands written inside this launch: wait until the tiles that hold them are stored
         const ChainProd& d = a.prods[q.dep_prod];
         int j0 = 0, j1 = d.n_tiles;
@@ -216,7 +179,7 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
         }
         const uint32_t target = uint32_t(d.m_tiles) * CHAIN_ARRIVALS_PER_TILE;
         if (lane == kPollLane)
-          for (int j = j0; j < j1; ++j) chain_wait_counter(a.counters + d.cnt_base + j, target, a.spin_limit);
+          for (int j = j0; j < j1; ++j) chain_wait_counter(a.counters + d.cnt_base + j, target);
         __syncwarp();
         fence_proxy_async_global();  // generic-proxy writes (acquired above) -> visible to my async-proxy (TMA) reads
       }
@@ -225,7 +188,7 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
         if (kb == num_kb) { kb = 0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? mAlo : mA;
         const CUtensorMap* mapB = pass == 2 ? mBlo : mB;
-        if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u, a.spin_limit);
+        if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);
         __syncwarp();
         if (elect_one()) {
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
@@ -255,7 +218,7 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
         const int pair_n = q.pair_n;
         const bool amn = q.amn != 0, bmn = q.bmn != 0;
         const int num_it = ((q.p.K + BLOCK_K - 1) / BLOCK_K) * (q.p.passes == 3 ? 3 : 1);
-        if (lane == kPollLane) mbar_wait(&tempty[as], aph ^ 1u, a.spin_limit);
+        if (lane == kPollLane) mbar_wait(&tempty[as], aph ^ 1u);
         __syncwarp();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * 256);
@@ -266,12 +229,12 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
         // compile-time variants below, in which all of them are immediates.
         const int variant = (amn ? 2 : 0) + (bmn ? 1 : 0) + (pair_n == 256 ? 4 : 0);
         switch (variant) {
-          case 2: chain_mma_item<true, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
-          case 0: chain_mma_item<false, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
-          case 3: chain_mma_item<true, true, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
-          case 6: chain_mma_item<true, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
-          case 4: chain_mma_item<false, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
-          case 7: chain_mma_item<true, true, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages, a.spin_limit); break;
+          case 2: chain_mma_item<true, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 0: chain_mma_item<false, false, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 3: chain_mma_item<true, true, 128>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 6: chain_mma_item<true, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 4: chain_mma_item<false, false, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
+          case 7: chain_mma_item<true, true, 256>(full, empty, tfull, smem_base, d_tmem, num_it, as, s, ph, lane, STAGE_BYTES, kStages); break;
           default: __trap();  // K-major A with MN-major B: no product of the path has it
         }
         as ^= 1;
@@ -297,7 +260,7 @@ __global__ void __maxnreg__(192) bp_chain_kernel(const __grid_constant__ ChainAr
       // Y (EPI_DX) / the targets (training output layer) of the first chunks, fetched under the main loop
       const bool out_train = epi == EPI_FWD_OUT && p.aux != nullptr && p.out != nullptr && p.out2 == nullptr;
       if (epi == EPI_DX || out_train) pre.start(p, m, m_ok, n0);
-      if (lane == 0) mbar_wait_backoff(&tfull[as], aph, a.spin_limit);
+      if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
       tc_fence_after();
       if (a.trace != nullptr && leader && warp == 2 && lane == 0) a.trace[4 * i + 2] = global_timer_ns();

@@ -34,12 +34,6 @@ struct ChainProd {
   int dep_all;           // 1: wait for all its n-tiles; 0: for those covering my tile's columns (frames)
   int per_bunch;         // bit 0: the host sets p.aux / p.sqerr to this bunch's targets / loss slot (output layer)
   int has_consumer;      // 1: some product of this launch waits for my tiles -> publish them (fence + counter)
-  // Data-parallel runs: my weights are rewritten by their owners' all-gather stores of the PREVIOUS step (bp_peer.cuh),
-  // which runs on another stream beside this launch: wait until each of the ext_n owners' "rows of this layer landed"
-  // counters (in this device's memory, system scope) has reached ext_target.  ext_n = 0: no such wait.
-  const unsigned long long* ext_flags;
-  int ext_n;
-  unsigned long long ext_target;
 };
 
 struct ChainItem {
@@ -63,12 +57,6 @@ struct ChainArgs {
   uint32_t* counters;        // this launch's counter set (all zero at launch)
   uint32_t* counters_next;   // the other set: zeroed by this launch
   int n_counters;
-  // L2 prefetch at kernel start (cp.async.bulk.prefetch.L2), spread over all CTAs: operands of LATER products of
-  // this launch (the next layers' weights) and of the NEXT launch (the next bunch's input rows).
-  const void* pf_base[6];
-  unsigned long long pf_bytes[6];
-  int n_pf;
-  long long spin_limit;      // cycles after which a stalled wait traps: ~2 s; ~65 s when some product waits for peers
   unsigned long long* trace; // bring-up aid (null in production): per item 4 globaltimer stamps written by the leader
                              // CTA: dependencies satisfied, stores issued, accumulator complete, published
 };
@@ -89,6 +77,48 @@ struct ChainShape {
   int dep_prod, dep_all; // as ChainProd
   int prio;              // smaller = scheduled first among ready items (the dX chain before the dW filler)
 };
+
+// Tile width of a product inside a chain: 256-wide pair tiles (shared-memory roof = tensor roof) when they still cover
+// >= 60 % of the pairs, else 128-wide ones (twice the tiles, shorter dependency chain) — the rule of pick_kernel.
+inline int chain_pair_n(int M, int N, int pairs) {
+  const int mt = (M + 255) / 256;
+  return mt * ((N + 255) / 256) * 10 >= pairs * 6 ? 256 : 128;
+}
+
+// The products of one train bunch of `rows` frames as the scheduler sees them (sizes[0..L] = layer sizes).
+//   which = 0, forward: product l-1 = layer l (M = units of l, N = frames, K = fan-in), waits for the tiles of layer
+//           l-1 that cover its frames.
+//   which = 1, back-propagation: dX_L .. dX_2 (product that turns dE/dX_l into dE/dX_{l-1}: M = units of l-1,
+//           N = frames, K = units of l; waits for the dX product before it, same frames; priority 0 = the chain), then
+//           dW_L .. dW_1 (M = units of l, N = fan-in + 1, K = frames, 256-wide; waits for ALL of dE/dX_l; the filler).
+// bp_runtime.cu builds its product tables in exactly this order and checks them against this function.
+inline std::vector<ChainShape> chain_shapes(const int* sizes, int L, int rows, int pairs, int passes, int which) {
+  std::vector<ChainShape> v;
+  const int mul = passes == 3 ? 3 : 1;
+  auto mk = [&](int M, int N, int K, int pair_n, int dep, int dep_all, int prio) {
+    ChainShape sh{};
+    sh.m_tiles = (M + 255) / 256;
+    sh.n_tiles = (N + pair_n - 1) / pair_n;
+    sh.n_cols = N;
+    sh.kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K * mul;
+    sh.pair_n = pair_n;
+    sh.dep_prod = dep;
+    sh.dep_all = dep_all;
+    sh.prio = prio;
+    v.push_back(sh);
+  };
+  if (which == 0) {
+    for (int l = 1; l <= L; ++l) mk(sizes[l], rows, sizes[l - 1], chain_pair_n(sizes[l], rows, pairs), l >= 2 ? l - 2 : -1, 0, l);
+  } else {
+    std::vector<int> dx_index(L + 2, -1);
+    for (int l = L; l >= 2; --l) {
+      dx_index[l] = (int)v.size();
+      mk(sizes[l - 1], rows, sizes[l], chain_pair_n(sizes[l - 1], rows, pairs), l < L ? dx_index[l + 1] : -1, 0, 0);
+    }
+    for (int l = L; l >= 1; --l) mk(sizes[l], sizes[l - 1] + 1, rows, 256, l < L ? dx_index[l + 1] : -1, 1, 1 + (L - l));
+  }
+  return v;
+}
 
 // Cost model in SM cycles, from the clock64 traces of the pair kernels (profiles/r2b): a 64-deep k-block of a
 // 128-wide pair tile takes ~600 cycles in steady state, of a 256-wide one ~1100; an epilogue ~2600 / ~4000.

@@ -63,9 +63,6 @@ __device__ __forceinline__ float tf32_lo(float x) {
 __device__ __forceinline__ void st_global_f32(float* p, float v) {
   asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
 }
-__device__ __forceinline__ void st_global_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v));
-}
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == 0) return x > 0.0f ? x : 0.0f;
   return 1.0f / (1.0f + expf(-x));
@@ -79,8 +76,8 @@ __device__ __forceinline__ float act_bwd(float y, float e, int act) {
 // ACT 0 ReLU / 1 sigmoid; FL bit 0 dropout, bit 1 low part wanted (3xTF32), bit 2 ragged chunk (some columns >= N).
 // All 32 values are formed first, then stored back to back (32 independent coalesced 128-byte warp stores in flight).
 // Same operations in the same order as before the split: y = act(fma(scale, acc, bias)); dropped -> 0.
-template <int ACT, int FL, bool kMask>
-__device__ __forceinline__ uint32_t epi_fwd_hid_chunk(const GemmParams& p, const uint32_t (&v)[32], int m, int nc,
+template <int ACT, int FL>
+__device__ __forceinline__ void epi_fwd_hid_chunk(const GemmParams& p, const uint32_t (&v)[32], int m, int nc,
                                                       float bias) {
   constexpr bool kDrop = (FL & 1) != 0, kLo = (FL & 2) != 0, kRagged = (FL & 4) != 0;
   float y[32];
@@ -111,13 +108,6 @@ __device__ __forceinline__ uint32_t epi_fwd_hid_chunk(const GemmParams& p, const
     for (int j = 0; j < 32; ++j)
       if (!kRagged || j < valid) st_global_f32(ol + size_t(j) * p.ldo, tf32_lo(y[j]));
   }
-  uint32_t bits = 0;
-  if constexpr (kMask) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (!kRagged || j < valid) bits |= (y[j] > 0.0f ? 1u : 0u) << j;
-  }
-  return bits;
 }
 
 // Output-layer epilogue of one chunk (kernSubClean, DevFunc.cu:253-268, + the squared-error monitor), switches compiled
@@ -180,24 +170,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
       float* base = p.out + plane_off;
       if (p.scatter_n > 0) base = p.scatter[(p.chunk_base + (nc >> 5)) % p.scatter_n];
       float* o = base + size_t(nc) * p.ldo + m;
-      if (p.stream_out) {  // gradient tile: read once by the update, should not displace the weights in L2
 #pragma unroll
-        for (int j = 0; j < 32; ++j, o += p.ldo)
-          if (whole || nc + j < p.N) __stcs(o, __uint_as_float(v[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j, o += p.ldo)
-          if (whole || nc + j < p.N) st_global_f32(o, __uint_as_float(v[j]));
-      }
+      for (int j = 0; j < 32; ++j, o += p.ldo)
+        if (whole || nc + j < p.N) st_global_f32(o, __uint_as_float(v[j]));
     }
-  } else if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_HID_MASK) {
+  } else if constexpr (kEpi == EPI_FWD_HID) {
     if (m_ok) {
       // warp-uniform switches, hoisted out of the 32-column loop: with them inside, every element carried ~6 branches
       // (activation kind, dropout, ragged tail, low part) and the hidden-layer forward product took 26 us where the
       // plain-epilogue product of the same shape takes 17 (profiles/r2b)
       const int flags = (p.drop_p > 0.0f ? 1 : 0) | (p.out_lo != nullptr ? 2 : 0) | (whole ? 0 : 4);
-      uint32_t bits = 0;
-#define BP_HID(ACT, FL) bits = epi_fwd_hid_chunk<ACT, FL, kEpi == EPI_FWD_HID_MASK>(p, v, m, nc, bias)
+#define BP_HID(ACT, FL) epi_fwd_hid_chunk<ACT, FL>(p, v, m, nc, bias)
       if (p.act == 0) {
         switch (flags) {
           case 0: BP_HID(0, 0); break;
@@ -222,7 +205,6 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
         }
       }
 #undef BP_HID
-      if constexpr (kEpi == EPI_FWD_HID_MASK) st_global_u32(p.relu_mask + size_t(nc >> 5) * p.ldmask + m, bits);
     }
   } else if constexpr (kEpi == EPI_FWD_OUT) {
     if (m_ok) {
@@ -267,21 +249,6 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
         }
       }
     }
-  } else if constexpr (kEpi == EPI_DX) {
-    if (m_ok) {
-      float yv[32];
-      const float* a = p.aux + size_t(nc) * p.ldaux + m;
-#pragma unroll
-      for (int j = 0; j < 32; ++j, a += p.ldaux) yv[j] = (whole || nc + j < p.N) ? __ldg(a) : 0.0f;
-      float* o = p.out + size_t(nc) * p.ldo + m;
-#pragma unroll
-      for (int j = 0; j < 32; ++j, o += p.ldo)
-        if (whole || nc + j < p.N) {
-          const float dv = act_bwd(yv[j], __uint_as_float(v[j]), p.act);
-          *o = dv;
-          if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
-        }
-    }
   }
 }
 
@@ -318,127 +285,6 @@ __device__ __forceinline__ void gemm_dx_store(const GemmParams& p, const uint32_
   } else {
     if (whole) { if (lo) epi_dx_chunk<1, true, false>(p, v, yv, m, nc); else epi_dx_chunk<1, false, false>(p, v, yv, m, nc); }
     else       { if (lo) epi_dx_chunk<1, true, true>(p, v, yv, m, nc);  else epi_dx_chunk<1, false, true>(p, v, yv, m, nc); }
-  }
-}
-
-// EPI_DW_SGD: momentum-SGD update applied by the weight-gradient GEMM's own epilogue.  Operation for operation the
-// arithmetic of bp_sgd_kernel (bp_elementwise.cuh), so fused and unfused runs give identical bits:
-//   t = g/n (+ wc*w);  delta = m*delta - c1*t;  w = delta + w          one rounding per operation, no contraction.
-// Every parameter is read and written by exactly one thread of one CTA, once per launch.  Like EPI_DX's Y operand the
-// delta/w values of a 32-column chunk are fetched one chunk ahead of their use (the first chunk before the accumulator
-// is waited for), and the whole tile's lines are pulled into L2 while the main loop runs (upd_prefetch).
-struct SgdPrefetch {
-  float d[2][32], x[2][32];
-  __device__ __forceinline__ void load(const GemmParams& p, int slot, int m, bool m_ok, int nc) {
-    if (!m_ok || nc >= p.N) return;
-    const size_t off = size_t(nc) * p.ldo + m;
-    const float* pd = p.upd_delta + off;
-    const float* px = p.upd_w + off;   // plain loads: this kernel writes the arena (never the non-coherent path)
-    const bool whole = nc + 32 <= p.N;
-#pragma unroll
-    for (int j = 0; j < 32; ++j, pd += p.ldo, px += p.ldo) {
-      const bool ok = whole || nc + j < p.N;
-      d[slot][j] = ok ? __ldcs(pd) : 0.0f;   // deltas are touched by nobody else until the next update: streamed
-      x[slot][j] = ok ? *px : 0.0f;
-    }
-  }
-};
-
-__device__ __forceinline__ void gemm_sgd_l2_prefetch(const GemmParams& p, int m_base, int n0, int block_n, int lane) {
-  if (!p.upd_prefetch || m_base >= p.M) return;
-  for (int c = 0; c < block_n; c += 32) {
-    const int n = n0 + c + lane;   // lane j <-> the line of row n0+c+j that holds columns [m_base, m_base+32)
-    if (n < p.N) {
-      const size_t off = size_t(n) * p.ldo + m_base;
-      prefetch_l2(p.upd_delta + off);
-      prefetch_l2(p.upd_w + off);
-    }
-  }
-}
-
-__device__ __forceinline__ void gemm_sgd_store(const GemmParams& p, const uint32_t (&v)[32], const float (&dv)[32],
-                                               const float (&xv)[32], int m, bool m_ok, int nc) {
-  if (!m_ok) return;
-  const bool whole = nc + 32 <= p.N;
-  const size_t off = size_t(nc) * p.ldo + m;
-  float* pd = p.upd_delta + off;
-  float* px = p.upd_w + off;
-  float* pl = p.upd_w_lo != nullptr ? p.upd_w_lo + off : nullptr;
-  const bool has_wc = p.upd_wc != 0.0f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j, pd += p.ldo, px += p.ldo) {
-    if (whole || nc + j < p.N) {
-      const float g = __uint_as_float(v[j]);
-      float t = p.upd_inv_nf != 0.0f ? __fmul_rn(g, p.upd_inv_nf) : __fdiv_rn(g, p.upd_nf);
-      if (has_wc) t = __fadd_rn(t, __fmul_rn(nc + j == p.upd_bias_col ? 0.0f : p.upd_wc, xv[j]));
-      const float nd = __fsub_rn(__fmul_rn(p.upd_momentum, dv[j]), __fmul_rn(p.upd_c1, t));
-      const float xn = __fadd_rn(nd, xv[j]);
-      __stcs(pd, nd);
-      *px = xn;
-      if (pl != nullptr) pl[size_t(j) * p.ldo] = tf32_lo(xn);
-    }
-  }
-}
-
-template <int BLOCK_N>
-__device__ __forceinline__ void gemm_sgd_epilogue(const GemmParams& p, SgdPrefetch& pre, uint32_t taddr, int m, bool m_ok,
-                                                  int n0) {
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N / 32; c += 2) {
-    const int nc = n0 + c * 32;
-    if (nc >= p.N) break;
-    uint32_t v[32];
-    pre.load(p, 1, m, m_ok, nc + 32);          // next chunk's delta/w in flight while this one is processed
-    tmem_ld32(taddr + uint32_t(c * 32), v);
-    tmem_ld_wait();
-    gemm_sgd_store(p, v, pre.d[0], pre.x[0], m, m_ok, nc);
-    if (nc + 32 >= p.N) break;
-    if (c + 2 < BLOCK_N / 32) pre.load(p, 0, m, m_ok, nc + 64);
-    tmem_ld32(taddr + uint32_t((c + 1) * 32), v);
-    tmem_ld_wait();
-    gemm_sgd_store(p, v, pre.d[1], pre.x[1], m, m_ok, nc + 32);
-  }
-}
-
-// EPI_DX_MASK: the ReLU-derivative predicate comes from the forward epilogue's bit mask (one word per lane and
-// 32-column chunk) instead of Y itself.  All of a tile's words are fetched before the accumulator is waited for — a
-// handful of registers where DxPrefetch needs 64 for two chunks — and the result is bit-identical with EPI_DX at
-// act == 0 (y > 0 ? acc : 0, DevFunc.cu:81-97 + 244-250).
-template <int BLOCK_N>
-struct DxMaskPrefetch {
-  uint32_t w[BLOCK_N / 32];
-  __device__ __forceinline__ void start(const GemmParams& p, int m, bool m_ok, int n0) {
-#pragma unroll
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      const int nc = n0 + c * 32;
-      w[c] = (m_ok && nc < p.N) ? __ldg(p.relu_mask + size_t(nc >> 5) * p.ldmask + m) : 0u;
-    }
-  }
-};
-
-template <int BLOCK_N>
-__device__ __forceinline__ void gemm_dxmask_epilogue(const GemmParams& p, const DxMaskPrefetch<BLOCK_N>& pre,
-                                                     uint32_t taddr, int m, bool m_ok, int n0) {
-#pragma unroll
-  for (int c = 0; c < BLOCK_N / 32; ++c) {  // unrolled: pre.w[c] stays in registers
-    const int nc = n0 + c * 32;
-    if (nc < p.N) {                         // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(taddr + uint32_t(c * 32), v);
-      tmem_ld_wait();
-      if (m_ok) {
-        const bool whole = nc + 32 <= p.N;
-        const uint32_t bits = pre.w[c];
-        float* o = p.out + size_t(nc) * p.ldo + m;
-#pragma unroll
-        for (int j = 0; j < 32; ++j, o += p.ldo)
-          if (whole || nc + j < p.N) {
-            const float dv = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.0f;
-            *o = dv;
-            if (p.out_lo != nullptr) p.out_lo[o - p.out] = tf32_lo(dv);
-          }
-      }
-    }
   }
 }
 
@@ -532,8 +378,6 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // returns when the committed MMAs have COMPLETED — which serialises issue with execution (measured: ~480 idle
   // tensor-pipe cycles per k-block).
   constexpr int kPollLane = 1;
-  const bool tracing = p.dbg_trace != nullptr && blockIdx.x == 0;
-  if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
 
   const int num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n_tiles = (p.N - p.n_begin + BLOCK_N - 1) / BLOCK_N;
@@ -591,26 +435,15 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);  // ONE lane polls (see header)
         __syncwarp();
         if (elect_one()) {
-          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[kb] = clock64();
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if (p.dbg_flags & 2u) {  // measurement aid: no loads, the stage is "full" at once
-            mbar_arrive(&full[s]);
-          } else {
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
-            const int b1 = kBMN ? kb * BLOCK_K : n0, b2 = kBMN ? n0 / 32 : kb * (BLOCK_K / 32);
-            if (p.hint_a) tma_load_3d_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
-            else tma_load_3d(sa, mapA, &full[s], 0, a1, a2);
-            if (p.hint_b) tma_load_3d_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
-            else tma_load_3d(sb, mapB, &full[s], 0, b1, b2);
-            if (p.l2_prefetch > 0 && kb + p.l2_prefetch < kb1) {
-              const int kp = kb + p.l2_prefetch;
-              tma_prefetch_l2_3d(mapA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
-              tma_prefetch_l2_3d(mapB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
-            }
-          }
-          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[256 + kb] = clock64();
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
+          const int b1 = kBMN ? kb * BLOCK_K : n0, b2 = kBMN ? n0 / 32 : kb * (BLOCK_K / 32);
+          if (p.hint_a) tma_load_3d_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
+          else tma_load_3d(sa, mapA, &full[s], 0, a1, a2);
+          if (p.hint_b) tma_load_3d_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
+          else tma_load_3d(sb, mapB, &full[s], 0, b1, b2);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -637,10 +470,7 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
         if (elect_one()) {
-          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[512 + kb] = clock64();
-          if (p.dbg_flags & 1u) {  // measurement aid: consume the stage without multiplying
-            mbar_arrive(&empty[s]);
-          } else {
+          {
             // descriptor low words: one base per operand per stage, then base + constant per k-step (the tensor pipe's
             // instruction queue is shallow, so every cycle of issue overhead beyond ~250 per k-block idles the pipe)
             const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + (sa >> 4);
@@ -655,7 +485,6 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&empty[s]);  // slot s is free again once these MMAs have read it
           }
           if (kb == num_it - 1) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
-          if (tracing && kb < 256 && t == (int)blockIdx.x) p.dbg_trace[768 + kb] = clock64();
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -678,28 +507,16 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool m_ok = m < p.M;
       DxPrefetch pre;
       if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);  // under the main loop (see gemm_dx_epilogue)
-      SgdPrefetch upd;
-      if constexpr (kEpi == EPI_DW_SGD) {
-        upd.load(p, 0, m, m_ok, n0);
-        gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
-      }
-      DxMaskPrefetch<BLOCK_N> mpre;
-      if constexpr (kEpi == EPI_DX_MASK) mpre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);  // one poller per warp, long suspend hint
       __syncwarp();
-      if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1024] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
-      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT || kEpi == EPI_FWD_HID_MASK) {
+      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
-      } else if constexpr (kEpi == EPI_DW_SGD) {
-        gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
-      } else if constexpr (kEpi == EPI_DX_MASK) {
-        gemm_dxmask_epilogue<BLOCK_N>(p, mpre, taddr, m, m_ok, n0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -713,7 +530,6 @@ bp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (tracing && threadIdx.x == 64 && t == (int)blockIdx.x) p.dbg_trace[1025] = clock64();
       if (lane == 0) mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aph ^= 1u;

@@ -19,18 +19,11 @@
 //                its own copy.
 //   * tempty[b] (leader only, count 8): one arrival per epilogue warp of BOTH CTAs (the peer's arrive remotely).
 //   The peer CTA's warp 1 only allocates / frees TMEM.  Everything else (3-D tensor maps, descriptors, warp-uniform
-//   role loops, elect.sync, one polling lane, PDL, 3xTF32 passes, column slices) is as in bp_gemm.cuh.
+//   role loops, elect.sync, one polling lane, PDL, 3xTF32 passes) is as in bp_gemm.cuh.
 //
-// Multicast clusters (CP = 2 or 4 pairs per cluster).  The ncu captures of the pair kernels show the L2 -> SM path, not
-// the tensor pipe, as the binding roof: 4.0-5.2 KB/clk chip-wide against a ~6.3 KB/clk cap (profiles/r1c, B300_MICROARCH
-// "LTS throughput cap"), i.e. ~42 B/clk/SM where a 256 x 128 pair tile of fp32 operands asks for 96.  CP pairs of one
-// cluster therefore work on CP neighbouring N tiles of the SAME 256 rows of A, and every CTA fetches only 1/CP of its A
-// block and multicasts it to the CTAs of the same parity in all pairs (cp.async.bulk.tensor ... .cta_group::2
-// .multicast::cluster; each destination's bytes complete on ITS pair leader's full barrier).  Per CTA and k-block the L2
-// traffic drops from 32 KB + B to 32/CP KB + B.  Protocol changes: empty[s] counts CP arrivals — every pair leader's
-// commit is multicast to ALL CTAs of the cluster, because a CTA's A slice is written into every pair's shared memory;
-// tfull commits go to the own pair only; tempty arrivals go to the own pair's leader.  Pairs whose columns lie beyond N
-// run the same protocol on zero-filled boxes and store nothing.
+// Tried and removed (measurements in DESIGN.md section 8): clusters of 2 / 4 pairs sharing their A rows by TMA multicast
+// (no gain alone, -3 % forward / +15 % dW inside a bunch), a 2-deep ring with two CTAs per SM (-25 %), L2-only TMA
+// prefetch ahead of the ring (-4..-9 %).
 #pragma once
 #include "bp_gemm.cuh"
 
@@ -40,32 +33,21 @@ namespace bp {
 // PAIR_N = 128 (for products too small to fill the machine with 256-wide pair tiles, e.g. 2048 x 1024 outputs):
 // 48 KB stages x 4, each CTA stages 64 B columns; 96 KB of shared-memory traffic per 512 pipe cycles -> 67 % roof
 // instead of the lone CTA's 50 %.
-// kStagesOv (experiment, BP_STAGES=2): a 2-deep ring of 48 KB stages makes a 128-wide pair CTA small enough (97 KB,
-// 256 TMEM columns) for two CTAs per SM, so that the next kernel's main loop (PDL) or the side stream's dW can run under
-// this kernel's fill, epilogue and drain — at the price of less latency tolerance in the ring.  0 = the defaults.
-template <int PAIR_N, int kStagesOv = 0>
-__host__ __device__ constexpr int gemm2_stages() { return kStagesOv > 0 ? kStagesOv : (PAIR_N == 256 ? 3 : 4); }
+template <int PAIR_N>
+__host__ __device__ constexpr int gemm2_stages() { return PAIR_N == 256 ? 3 : 4; }
 
-template <int PAIR_N, int kStagesOv = 0>
+template <int PAIR_N>
 constexpr size_t gemm2_smem_bytes() {
-  return size_t(gemm2_stages<PAIR_N, kStagesOv>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
+  return size_t(gemm2_stages<PAIR_N>()) * (GEMM_BLOCK_M + PAIR_N / 2) * GEMM_BLOCK_K * 4 + 1024 + 256;
 }
 
-// A-slice boxes of the multicast variant (host side builds the tensor maps with these, see make_map1):
-//   MN-major A: {32, 64 k-rows, (128/CP)/32 mn-chunks}      slice pi = mn-chunks [pi*4/CP, (pi+1)*4/CP) of the 128-row block
-//   K-major  A: {32, 128 rows (CP=2) | 64 rows (CP=4), 1 k-chunk}   slice pi = k-chunk pi/(CP/2), row part pi%(CP/2)
-// In both layouts slice pi occupies bytes [pi, pi+1) * A_BYTES/CP of the stage's A block.
-// kTrace: separate instantiation (bp_debug_gemm with BP_DBG_TRACE only) in which the leader CTA of pair 0 records a
-// clock64 timeline of its first tile into p.dbg_trace, same slots as bp_gemm_kernel's (see GemmParams::dbg_trace); the
-// product kernels (kTrace = false) contain none of it.
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP = 1, bool kTrace = false, int kStagesOv = 0>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                 const GemmParams p) {
-  static_assert(CP == 1 || CP == 2 || CP == 4, "pairs per cluster");
   constexpr int BLOCK_M = GEMM_BLOCK_M, BLOCK_K = GEMM_BLOCK_K, BLOCK_N = PAIR_N;
-  constexpr int kStages = gemm2_stages<PAIR_N, kStagesOv>();
+  constexpr int kStages = gemm2_stages<PAIR_N>();
   static_assert(PAIR_N == 128 || PAIR_N == 256, "PAIR_N");
   constexpr int HALF_N = BLOCK_N / 2;                    // B columns staged by each CTA
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 4;    // my 128 rows of A
@@ -93,30 +75,22 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kPollLane = 1;
-  const uint32_t crank = cluster_ctarank();    // rank in the cluster of 2*CP CTAs
-  const uint32_t rank = crank & 1u;            // position in my pair (0 = leader)
-  const uint32_t pi = crank >> 1;              // my pair's index in the cluster
+  const uint32_t rank = cluster_ctarank();     // position in my pair (0 = leader)
   const bool leader = rank == 0;
 
   const int num_m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);            // pair tiles along M
-  const int num_n_tiles = (p.N - p.n_begin + CP * BLOCK_N - 1) / (CP * BLOCK_N);  // cluster tiles along N
+  const int num_n_tiles = (p.N - p.n_begin + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_it = num_kb * (p.passes == 3 ? 3 : 1);
-  const int pair = blockIdx.x / (2 * CP), num_pairs = gridDim.x / (2 * CP);  // cluster index / count
-  constexpr uint16_t kAllCtas = uint16_t((1u << (2 * CP)) - 1u);
-  bool tracing = false;
-  if constexpr (kTrace) {
-    tracing = p.dbg_trace != nullptr && blockIdx.x == 0;
-    if (tracing && threadIdx.x == 0) p.dbg_trace[1026] = clock64();
-  }
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CP);  // one multicast commit per pair of the cluster
+      mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -134,18 +108,6 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (CP == 1 && p.l2_prefetch > 0 && warp == 0 && pair < num_tiles) {
-    // Under the previous kernel's tail (PDL): pull the first k-blocks of my first tile towards L2.
-    if (elect_one()) {
-      const int m0 = (pair % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;
-      const int n0 = p.n_begin + (pair / num_m_tiles) * BLOCK_N + int(rank) * HALF_N;
-      for (int kp = 0; kp < p.l2_prefetch && kp < num_kb; ++kp) {
-        tma_prefetch_l2_3d(&tmA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
-        tma_prefetch_l2_3d(&tmB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
-      }
-    }
-    __syncwarp();
-  }
   griddep_wait();
   griddep_launch_dependents();
 
@@ -155,7 +117,7 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t ph = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;       // my 128 rows of A
-      const int n0 = p.n_begin + ((t / num_m_tiles) * CP + int(pi)) * BLOCK_N + int(rank) * HALF_N;  // my half of B
+      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N + int(rank) * HALF_N;  // my half of B
       for (int it = 0, kb = 0, pass = 0; it < num_it; ++it, ++kb) {
         if (kb == num_kb) { kb = 0; ++pass; }
         const CUtensorMap* mapA = pass == 1 ? &tmAlo : &tmA;
@@ -163,35 +125,15 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == kPollLane) mbar_wait(&empty[s], ph ^ 1u);
         __syncwarp();
         if (elect_one()) {
-          if constexpr (kTrace) {
-            if (tracing && it < 256 && t == pair) p.dbg_trace[it] = clock64();
-          }
           uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);  // both CTAs' bytes land on the leader's barrier
           const int b1 = kBMN ? kb * BLOCK_K : n0, b2 = kBMN ? n0 / 32 : kb * (BLOCK_K / 32);
-          if constexpr (CP == 1) {
-            const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
-            if (p.hint_a) tma_load_3d_2sm_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
-            else tma_load_3d_2sm(sa, mapA, &full[s], 0, a1, a2);
-          } else {
-            // my 1/CP of the A block, to the CTAs of my parity in every pair of the cluster
-            constexpr uint16_t kParityMask = CP == 2 ? 0x5 : 0x55;
-            constexpr int kRowParts = CP / 2;  // K-major: row parts per k-chunk
-            const int a1 = kAMN ? kb * BLOCK_K : m0 + int(pi % kRowParts) * (BLOCK_M / kRowParts);
-            const int a2 = kAMN ? m0 / 32 + int(pi) * (BLOCK_M / 32 / CP) : kb * (BLOCK_K / 32) + int(pi / kRowParts);
-            tma_load_3d_2sm_mc(sa + pi * (A_BYTES / CP), mapA, &full[s], 0, a1, a2, uint16_t(kParityMask << rank));
-          }
+          const int a1 = kAMN ? kb * BLOCK_K : m0, a2 = kAMN ? m0 / 32 : kb * (BLOCK_K / 32);
+          if (p.hint_a) tma_load_3d_2sm_hint(sa, mapA, &full[s], 0, a1, a2, p.hint_a);
+          else tma_load_3d_2sm(sa, mapA, &full[s], 0, a1, a2);
           if (p.hint_b) tma_load_3d_2sm_hint(sb, mapB, &full[s], 0, b1, b2, p.hint_b);
           else tma_load_3d_2sm(sb, mapB, &full[s], 0, b1, b2);
-          if (CP == 1 && p.l2_prefetch > 0 && kb + p.l2_prefetch < num_kb) {  // run ahead of the ring, into L2 only
-            const int kp = kb + p.l2_prefetch;
-            tma_prefetch_l2_3d(mapA, 0, kAMN ? kp * BLOCK_K : m0, kAMN ? m0 / 32 : kp * (BLOCK_K / 32));
-            tma_prefetch_l2_3d(mapB, 0, kBMN ? kp * BLOCK_K : n0, kBMN ? n0 / 32 : kp * (BLOCK_K / 32));
-          }
-          if constexpr (kTrace) {
-            if (tracing && it < 256 && t == pair) p.dbg_trace[256 + it] = clock64();
-          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -217,12 +159,7 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = smem_base + uint32_t(s) * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (elect_one()) {
-            if constexpr (kTrace) {
-              if (tracing && kb < 256 && t == pair) p.dbg_trace[512 + kb] = clock64();
-            }
-            // 14-bit start-address field: the shared-window address of a CTA with cluster rank >= 2 carries its rank
-            // above bit 24, which would spill into the LBO field (bits 16-29) — harmless for K-major operands, whose
-            // LBO is ignored, and the cause of the wrong MN-major products of pairs 1.. in the first multicast runs
+            // 14-bit start-address field (a shared-window address carries the CTA's cluster rank in its high bits)
             const uint32_t a_lo = (kAMN ? kDescLoMN : kDescLoK) + ((sa >> 4) & 0x3FFFu);
             const uint32_t b_lo = (kBMN ? kDescLoMN : kDescLoK) + ((sb >> 4) & 0x3FFFu);
 #pragma unroll
@@ -232,11 +169,8 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               umma_tf32_2sm(d_tmem, a_lo + (a_off >> 4), kAMN ? kDescHiMN : kDescHiK, b_lo + (b_off >> 4),
                             kBMN ? kDescHiMN : kDescHiK, idesc, (k != 0 || kb != 0) ? 1u : 0u);
             }
-            umma_commit_2sm(&empty[s], kAllCtas);                 // this pair is done with slot s: tell every CTA
-            if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u << (2 * pi)));  // accumulators complete
-            if constexpr (kTrace) {
-              if (tracing && kb < 256 && t == pair) p.dbg_trace[768 + kb] = clock64();
-            }
+            umma_commit_2sm(&empty[s], uint16_t(0x3u));                           // slot s is free in both CTAs
+            if (kb == num_it - 1) umma_commit_2sm(&tfull[as], uint16_t(0x3u));    // accumulators complete
           }
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -253,37 +187,28 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float sq_local = 0.0f;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % num_m_tiles) * 2 * BLOCK_M + int(rank) * BLOCK_M;  // my 128 accumulator rows
-      const int n0 = p.n_begin + ((t / num_m_tiles) * CP + int(pi)) * BLOCK_N;  // all columns of my pair's tile
+      const int n0 = p.n_begin + (t / num_m_tiles) * BLOCK_N;  // all columns of my pair's tile
       const int m = m0 + q * 32 + lane;
       const bool m_ok = m < p.M;
       // EPI_DX: the Y values of the first two column chunks are fetched BEFORE waiting for the accumulator, i.e. under
       // the main loop, and the following chunks two steps ahead of their use (see gemm_dx_epilogue).
+      // EPI_FWD_OUT in training (targets present, D_L stored, no raw output): the targets are pipelined like Y
+      bool out_train = false;
+      if constexpr (kEpi == EPI_FWD_OUT) out_train = p.aux != nullptr && p.out != nullptr && p.out2 == nullptr;
       DxPrefetch pre;
-      if constexpr (kEpi == EPI_DX) pre.start(p, m, m_ok, n0);
-      SgdPrefetch upd;  // EPI_DW_SGD: the update's delta/w operands, same software pipeline (see gemm_sgd_epilogue)
-      if constexpr (kEpi == EPI_DW_SGD) {
-        upd.load(p, 0, m, m_ok, n0);
-        gemm_sgd_l2_prefetch(p, m0 + q * 32, n0, BLOCK_N, lane);
-      }
-      DxMaskPrefetch<BLOCK_N> mpre;  // EPI_DX_MASK: the tile's ReLU-mask words (see gemm_dxmask_epilogue)
-      if constexpr (kEpi == EPI_DX_MASK) mpre.start(p, m, m_ok, n0);
+      if (kEpi == EPI_DX || out_train) pre.start(p, m, m_ok, n0);
       if (lane == 0) mbar_wait_backoff(&tfull[as], aph);
       __syncwarp();
-      if constexpr (kTrace) {
-        if (tracing && threadIdx.x == 64 && t == pair) p.dbg_trace[1024] = clock64();
-      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
       float bias = 0.0f;
-      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT || kEpi == EPI_FWD_HID_MASK) {
+      if constexpr (kEpi == EPI_FWD_HID || kEpi == EPI_FWD_OUT) {
         if (m_ok) bias = __ldg(p.bias + m);
       }
       if constexpr (kEpi == EPI_DX) {
         gemm_dx_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0);
-      } else if constexpr (kEpi == EPI_DW_SGD) {
-        gemm_sgd_epilogue<BLOCK_N>(p, upd, taddr, m, m_ok, n0);
-      } else if constexpr (kEpi == EPI_DX_MASK) {
-        gemm_dxmask_epilogue<BLOCK_N>(p, mpre, taddr, m, m_ok, n0);
+      } else if (out_train) {
+        sq_local = gemm_fwdout_train_epilogue<BLOCK_N>(p, pre, taddr, m, m_ok, n0, bias, sq_local);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -297,12 +222,9 @@ bp_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if constexpr (kTrace) {
-        if (tracing && threadIdx.x == 64 && t == pair) p.dbg_trace[1025] = clock64();
-      }
       if (lane == 0) {
         if (leader) mbar_arrive(&tempty[as]);
-        else mbar_arrive_remote(&tempty[as], crank & ~1u);
+        else mbar_arrive_remote(&tempty[as], 0u);
       }
       as ^= 1;
       if (as == 0) aph ^= 1u;

@@ -11,6 +11,7 @@
 #include <string>
 
 #include "../../include/bp_gpu.h"
+#include "../../include/bp_gpu_debug.h"
 #include "bp_gemm_params.h"
 #include "bp_chain_params.h"
 
@@ -42,11 +43,9 @@ struct MapPair {
   CUtensorMap m;
   CUtensorMap lo;
 };
-// The A operand of a product: the whole-block map (128 rows per box) plus the 1/2 and 1/4 slice maps the multicast
-// clusters load (slice[0]: CP = 2, slice[1]: CP = 4).
+// The A operand of a product (128 rows per box).
 struct AMaps {
   MapPair full;
-  MapPair slice[2];
 };
 int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
               int box_outer, bool mn_major, int k_chunks = GEMM_BLOCK_K / 32);
@@ -59,15 +58,10 @@ int make_a_maps(AMaps* am, const float* base, const float* lo_base, long long co
 enum Product : int {
   PROD_FWD_HID,     // A = W^T MN-major, B = Y K-major,    EPI_FWD_HID  hidden-layer forward affine
   PROD_FWD_OUT,     //   "                                 EPI_FWD_OUT  output-layer forward (+ loss gradient)
-  PROD_FWD_PLAIN,   //   "                                 EPI_PLAIN    debug / probes
+  PROD_FWD_PLAIN,   //   "                                 EPI_PLAIN    tests / probes
   PROD_FWD_SPLITK,  //   "    lone-CTA kernel only,        EPI_PLAIN    split-K planes of the output layer (p.k_splits)
-  PROD_FWD_DXEPI,   //   "                                 EPI_DX       probe: forward operands, dX epilogue
   PROD_DX,          // A = W K-major, B = D K-major,       EPI_DX       back-prop through a layer
-  PROD_DX_PLAIN,    //   "                                 EPI_PLAIN    probe: dX operands, plain epilogue
   PROD_DW,          // A = D^T MN-major, B = Y^T MN-major, EPI_PLAIN    weight (+bias) gradient
-  PROD_DW_SGD,      //   "                                 EPI_DW_SGD   ... with the update applied in the epilogue
-  PROD_FWD_HID_MASK,  // PROD_FWD_HID that also leaves the ReLU bit mask (EPI_FWD_HID_MASK)
-  PROD_DX_MASK,       // PROD_DX reading that mask instead of Y (EPI_DX_MASK)
 };
 // Picks the kernel (lone CTAs / 128- / 256-wide CTA pairs, see pick_kernel in bp_launch.cu) and launches it on `st`.
 // b = B map with 128-wide boxes, b64 = the same operand with 64-wide boxes (for 128-wide pairs) or null.
@@ -87,17 +81,10 @@ int launch_chain(cudaStream_t st, const ChainArgs& a, int pairs);
 enum Tunable : int {
   TUN_PDL,          // "pdl"          BP_PDL          1   programmatic dependent launch between consecutive GEMMs
   TUN_TMA_HINT,     // "tma_hint"     BP_TMA_HINT     1   L2 eviction-priority hints on operand loads
-  TUN_L2_PREFETCH,  // "l2_prefetch"  BP_L2_PREFETCH  0   k-blocks of L2-only TMA prefetch ahead of the smem ring
-  TUN_STAGES,       // "stages"       BP_STAGES       0   2 | 3: ring depth of the 128-wide pair kernels (0 = default 4)
   TUN_PAIRS,        // "pairs"        BP_PAIRS        1   0 lone CTAs, 1 automatic, 2 always 256-wide, 3 128-wide pairs
-  TUN_MC,           // "mc"           BP_MC           1   pairs per multicast cluster (1, 2, 4)
-  TUN_SMALL_PAIRS,  // "small_pairs"  BP_SMALL_PAIRS  0   128-wide pairs for small products with M % 256 == 0
-  TUN_DW_STREAM,    // "dw_stream"    BP_DW_STREAM    0   evict-first stores of the gradient tiles
   TUN_SGD_STREAM,   // "sgd_stream"   BP_SGD_STREAM   1   streaming access to the momentum deltas in the update
   TUN_SGD_EARLY,    // "sgd_early"    BP_SGD_EARLY    6   blocks per SM of the early update of layers >= 2 (0 = off)
   TUN_SPLITK,       // "splitk"       BP_SPLITK      -1   output-layer K slices: -1 automatic, 0 never, N force
-  TUN_UPLOAD_WAIT_FIRST,  // "upload_wait_first" BP_UPLOAD_WAIT_FIRST 0  1: bp_train* wait for the H2D before queueing
-                          //                     the bunches (the order used up to round 1d) instead of after
   TUN_COUNT
 };
 int tunable(Tunable t);

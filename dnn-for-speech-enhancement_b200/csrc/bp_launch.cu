@@ -26,11 +26,9 @@ struct TunableDef {
   const char* env;
   int dflt;
 };
-const TunableDef kTunables[TUN_COUNT] = {
-    {"pdl", "BP_PDL", 1},           {"tma_hint", "BP_TMA_HINT", 1},       {"l2_prefetch", "BP_L2_PREFETCH", 0},
-    {"stages", "BP_STAGES", 0},     {"pairs", "BP_PAIRS", 1},             {"mc", "BP_MC", 1},
-    {"small_pairs", "BP_SMALL_PAIRS", 0}, {"dw_stream", "BP_DW_STREAM", 0}, {"sgd_stream", "BP_SGD_STREAM", 1},
-    {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}, {"upload_wait_first", "BP_UPLOAD_WAIT_FIRST", 0}};
+const TunableDef kTunables[TUN_COUNT] = {{"pdl", "BP_PDL", 1},         {"tma_hint", "BP_TMA_HINT", 1},
+                                            {"pairs", "BP_PAIRS", 1},     {"sgd_stream", "BP_SGD_STREAM", 1},
+                                            {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}};
 std::atomic<int> g_tunable[TUN_COUNT];
 std::once_flag g_tunable_once;
 void init_tunables() {
@@ -93,8 +91,6 @@ static int get_encode() {
 //                    SWIZZLE_128B.
 //   MN-major operand (M/N dim contiguous):       rows = exact K extent,   chunks = ceil(MN/32); box {32, 64, box_mn/32};
 //                    SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands).
-//   A-slice maps of the multicast clusters (bp_gemm2.cuh): MN-major box_outer = 128/CP; K-major box_outer = 128 or 64
-//   rows with k_chunks = 1 (one 32-wide k-chunk per box instead of the whole 64-deep stage).
 int make_map1(CUtensorMap* m, const float* base, long long contiguous_extent, long long rows, long long ld,
               int box_outer, bool mn_major, int k_chunks) {
   BP_TRY(get_encode());
@@ -127,15 +123,7 @@ int make_map(MapPair* mp, const float* base, const float* lo_base, long long con
 
 int make_a_maps(AMaps* am, const float* base, const float* lo_base, long long contiguous_extent, long long rows,
                 long long ld, bool mn_major) {
-  BP_TRY(make_map(&am->full, base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, mn_major));
-  if (mn_major) {
-    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, true));
-    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 4, true));
-  } else {
-    BP_TRY(make_map(&am->slice[0], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, false, 1));
-    BP_TRY(make_map(&am->slice[1], base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M / 2, false, 1));
-  }
-  return BP_OK;
+  return make_map(&am->full, base, lo_base, contiguous_extent, rows, ld, GEMM_BLOCK_M, mn_major);
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
@@ -156,14 +144,8 @@ static int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const 
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   if (p.k_splits > 1 && kEpi != EPI_PLAIN) return fail(BP_EINVAL, "gemm: split-K needs the plain epilogue");
   const int grid = std::min(tiles * std::max(1, p.k_splits), num_sms);
-  static const uint32_t env_flags = [] {
-    const char* e = getenv("BP_GEMM_FLAGS");  // measurement aid, see GemmParams::dbg_flags
-    return e ? (uint32_t)atoi(e) : 0u;
-  }();
   const bool use_pdl = tunable(TUN_PDL) != 0;  // programmatic dependent launch between consecutive GEMMs (default on)
   GemmParams q = p;
-  q.l2_prefetch = std::max(0, tunable(TUN_L2_PREFETCH));
-  q.dbg_flags |= env_flags;
   const bool use_hints = tunable(TUN_TMA_HINT) != 0;  // L2 eviction-priority hints on operand loads (default on)
   if (!use_hints) q.hint_a = q.hint_b = 0;
   cudaLaunchConfig_t cfg{};
@@ -180,28 +162,25 @@ static int launch_gemm_bn(cudaStream_t st, int num_sms, const MapPair& a, const 
   return BP_OK;
 }
 
-// CTA-pair (cta_group::2) variant: 256 x PAIR_N pair tiles, CP pairs per cluster sharing their A rows by TMA multicast
-// (CP = 1: plain pairs).  `a` is the A map the kernel loads with: the whole-block map for CP = 1, the slice map else.
-// Clusters that can be co-resident (GPC granularity) per (PAIR_N, CP), filled by the first launch of each shape.
-static int g_max_clusters[2][3] = {{0, 0, 0}, {0, 0, 0}};
-inline int& max_clusters_slot(int pair_n, int cp) { return g_max_clusters[pair_n == 256][cp == 1 ? 0 : cp == 2 ? 1 : 2]; }
+// CTA-pair (cta_group::2) variant: 256 x PAIR_N pair tiles.  Pairs that can be co-resident (GPC granularity) per
+// PAIR_N, filled once per device before the first kernel choice (rank_create / bp_debug_gemm).
+static int g_max_clusters[2] = {0, 0};
+inline int& max_clusters_slot(int pair_n) { return g_max_clusters[pair_n == 256]; }
 
-// Occupancy depends on the cluster size and the shared-memory size only, so one instantiation per (PAIR_N, CP) answers
-// for all of them.  Called once per device before the first kernel choice (rank_create / bp_debug_gemm).
-template <int PAIR_N, int CP>
+// Occupancy depends on the cluster size and the shared-memory size only, so one instantiation per PAIR_N answers for all.
+template <int PAIR_N>
 static void query_cluster_capacity(int num_sms) {
-  auto kern = bp_gemm2_kernel<true, false, EPI_FWD_HID, PAIR_N, CP>;
-  constexpr int kCluster = 2 * CP;
-  int cap = num_sms / kCluster;
+  auto kern = bp_gemm2_kernel<true, false, EPI_FWD_HID, PAIR_N>;
+  int cap = num_sms / 2;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm2_smem_bytes<PAIR_N>()) ==
       cudaSuccess) {
     cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3(num_sms / kCluster * kCluster);
+    qc.gridDim = dim3(num_sms / 2 * 2);
     qc.blockDim = dim3(GEMM_THREADS);
     qc.dynamicSmemBytes = gemm2_smem_bytes<PAIR_N>();
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = kCluster;
+    qa[0].val.clusterDim.x = 2;
     qa[0].val.clusterDim.y = 1;
     qa[0].val.clusterDim.z = 1;
     qc.attrs = qa;
@@ -210,29 +189,23 @@ static void query_cluster_capacity(int num_sms) {
     if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess && n > 0) cap = std::min(n, cap);
   }
   cudaGetLastError();
-  max_clusters_slot(PAIR_N, CP) = cap;
+  max_clusters_slot(PAIR_N) = cap;
 }
 void init_cluster_capacity(int num_sms) {
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
-  if (g_max_clusters[0][0] > 0) return;
-  query_cluster_capacity<128, 2>(num_sms);
-  query_cluster_capacity<128, 4>(num_sms);
-  query_cluster_capacity<256, 1>(num_sms);
-  query_cluster_capacity<256, 2>(num_sms);
-  query_cluster_capacity<256, 4>(num_sms);
-  query_cluster_capacity<128, 1>(num_sms);
+  if (g_max_clusters[0] > 0) return;
+  query_cluster_capacity<256>(num_sms);
+  query_cluster_capacity<128>(num_sms);
   if (getenv("BP_VERBOSE"))
-    fprintf(stderr, "libbpgpu: co-resident clusters  128-wide pairs x1/x2/x4: %d %d %d   256-wide: %d %d %d\n",
-            g_max_clusters[0][0], g_max_clusters[0][1], g_max_clusters[0][2], g_max_clusters[1][0],
-            g_max_clusters[1][1], g_max_clusters[1][2]);
+    fprintf(stderr, "libbpgpu: co-resident CTA pairs  128-wide: %d   256-wide: %d\n", g_max_clusters[0],
+            g_max_clusters[1]);
 }
 
-template <bool kAMN, bool kBMN, int kEpi, int PAIR_N, int CP, bool kTrace = false, int kStagesOv = 0>
+template <bool kAMN, bool kBMN, int kEpi, int PAIR_N>
 static int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const MapPair& b, const GemmParams& p) {
-  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N, CP, kTrace, kStagesOv>;
-  constexpr size_t smem = gemm2_smem_bytes<PAIR_N, kStagesOv>();
-  constexpr int kCluster = 2 * CP;
+  auto kern = bp_gemm2_kernel<kAMN, kBMN, kEpi, PAIR_N>;
+  constexpr size_t smem = gemm2_smem_bytes<PAIR_N>();
   static thread_local int configured_dev = -1;
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
@@ -241,25 +214,22 @@ static int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const Ma
     configured_dev = dev;
   }
   init_cluster_capacity(num_sms);
-  const int max_clusters = max_clusters_slot(PAIR_N, CP);
+  const int max_clusters = max_clusters_slot(PAIR_N);
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const int nt = (p.N - p.n_begin + CP * PAIR_N - 1) / (CP * PAIR_N);
+  const int nt = (p.N - p.n_begin + PAIR_N - 1) / PAIR_N;
   const int tiles = mt * nt;
   if (tiles <= 0 || p.K <= 0) return fail(BP_EINVAL, "gemm2: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   const bool use_pdl = tunable(TUN_PDL) != 0;
-  const bool use_hints = tunable(TUN_TMA_HINT) != 0;  // L2 eviction-priority hints on operand loads (default on)
   GemmParams q = p;
-  q.l2_prefetch = std::max(0, tunable(TUN_L2_PREFETCH));  // k-blocks of L2-only prefetch ahead of the ring (default off)
-  if (!use_hints || CP > 1) q.hint_a = 0;  // the multicast A-slice load carries no hint
-  if (!use_hints) q.hint_b = 0;
+  if (tunable(TUN_TMA_HINT) == 0) q.hint_a = q.hint_b = 0;  // L2 eviction-priority hints on operand loads (default on)
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(std::min(tiles, std::min(max_clusters, num_sms / kCluster)) * kCluster);
+  cfg.gridDim = dim3(std::min(tiles, std::min(max_clusters, num_sms / 2)) * 2);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -270,68 +240,34 @@ static int launch_gemm2(cudaStream_t st, int num_sms, const MapPair& a, const Ma
   return BP_OK;
 }
 
-// Kernel choice per product: {pair_n, cp}; pair_n = 0 -> 128 x 128 tiles on lone CTAs.
+// Kernel choice per product: pair_n = 0 -> 128 x 128 tiles on lone CTAs.
 //   BP_PAIRS: 0 = lone CTAs only, 1 = automatic (default), 2 = 256-wide pairs always, 3 = 128-wide pairs whenever the
 //             narrow B map exists.
-//   BP_MC:    pairs per multicast cluster when a pair kernel is chosen: 1 = none (default), 2, 4 (experimental, see
-//             measured no gain on K-major A, MN-major A slices not yet correct).
 // Automatic: 256 x 256 pair tiles if they fill >= 60 % of the SM pairs, else 256 x 128 pair tiles under the same
-// condition, else 128 x 128 tiles on lone CTAs.  Measured in isolation on the B200 (scripts/gpu_mc_probe.py, r1d):
-// 2048x1024x2048 fwd 18.4 us on 128-wide pairs vs 25.9 us on 256-wide ones (64 CTAs); 2048x2049x1024 dW 17.6 us on
-// 256-wide pairs vs 19.5 us on 128-wide ones — the rule picks the faster one in every product of C2/C3/C5.
-struct KernelChoice {
-  int pair_n;
-  int cp;
-};
-inline KernelChoice pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
+// condition, else 128 x 128 tiles on lone CTAs.  Measured in isolation on the B200 (profiles/r1d): 2048x1024x2048 fwd
+// 18.4 us on 128-wide pairs vs 25.9 us on 256-wide ones (64 CTAs); 2048x2049x1024 dW 17.6 us on 256-wide pairs vs 19.5 us
+// on 128-wide ones — the rule picks the faster one in every product of C2/C3/C5.
+inline int pick_kernel(const GemmParams& p, int num_sms, bool have_b64) {
   const int mode = tunable(TUN_PAIRS);
-  const int mc = tunable(TUN_MC);
-  const int cp = (mc == 2 || mc == 4) ? mc : 1;
-  if (mode == 0) return {0, 1};
-  if (mode == 2) return {256, cp};
-  if (mode == 3) return {have_b64 ? 128 : 0, cp};
+  if (mode == 0) return 0;
+  if (mode == 2) return 256;
+  if (mode == 3) return have_b64 ? 128 : 0;
   const int mt = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
   const int n = p.N - p.n_begin;
-  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return {256, cp};
-  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return {128, cp};
-  // BP_SMALL_PAIRS=1 (off by default, not yet run on a GPU): when the unit count is a multiple of 256 a 128-wide pair
-  // tile is exactly two lone-CTA tiles — the same number of CTAs at the higher shared-memory roof (67 % against 50 %)
-  // — so small products (C4's 512 frames per GPU, the reference script's bunch 128) need not fall back to lone CTAs.
-  const int small_pairs = tunable(TUN_SMALL_PAIRS);
-  if (small_pairs && have_b64 && p.M % (2 * GEMM_BLOCK_M) == 0 && n >= 128) return {128, cp};
-  return {0, 1};
+  if (mt * ((n + 255) / 256) * 10 >= (num_sms / 2) * 6) return 256;
+  if (have_b64 && mt * ((n + 127) / 128) * 10 >= (num_sms / 2) * 6) return 128;
+  return 0;
 }
-
 
 // b = B operand map with 128-wide boxes (lone CTAs and 256-wide pairs); b64 = the same operand with 64-wide boxes
 // (128-wide pairs: each CTA stages 64 B columns), or null.
 template <bool kAMN, bool kBMN, int kEpi>
 static int launch_gemm(cudaStream_t st, int num_sms, const AMaps& a, const MapPair& b, const GemmParams& p,
                        const MapPair* b64 = nullptr) {
-  const KernelChoice k = pick_kernel(p, num_sms, b64 != nullptr);
-  if constexpr (kEpi == EPI_DW_SGD || kEpi == EPI_FWD_HID_MASK || kEpi == EPI_DX_MASK) {
-    // gated variants (fused update, ReLU bit mask): plain pairs / lone CTAs only (no multicast, trace or stage variants)
-    if (k.pair_n == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
-    if (k.pair_n == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
-    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
-  } else {
-    if (k.pair_n == 256) {
-      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 256, 4>(st, num_sms, a.slice[1], b, p);
-      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 256, 2>(st, num_sms, a.slice[0], b, p);
-      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 256, 1, true>(st, num_sms, a.full, b, p);
-      return launch_gemm2<kAMN, kBMN, kEpi, 256, 1>(st, num_sms, a.full, b, p);
-    }
-    if (k.pair_n == 128) {
-      if (k.cp == 4) return launch_gemm2<kAMN, kBMN, kEpi, 128, 4>(st, num_sms, a.slice[1], *b64, p);
-      if (k.cp == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 2>(st, num_sms, a.slice[0], *b64, p);
-      if (p.dbg_trace) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, true>(st, num_sms, a.full, *b64, p);
-      const int stages = tunable(TUN_STAGES);  // experiment: 2 = two co-resident 128-wide pair CTAs per SM (bp_gemm2.cuh)
-      if (stages == 2) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 2>(st, num_sms, a.full, *b64, p);
-      if (stages == 3) return launch_gemm2<kAMN, kBMN, kEpi, 128, 1, false, 3>(st, num_sms, a.full, *b64, p);
-      return launch_gemm2<kAMN, kBMN, kEpi, 128, 1>(st, num_sms, a.full, *b64, p);
-    }
-    return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
-  }
+  const int pair_n = pick_kernel(p, num_sms, b64 != nullptr);
+  if (pair_n == 256) return launch_gemm2<kAMN, kBMN, kEpi, 256>(st, num_sms, a.full, b, p);
+  if (pair_n == 128) return launch_gemm2<kAMN, kBMN, kEpi, 128>(st, num_sms, a.full, *b64, p);
+  return launch_gemm_bn<kAMN, kBMN, kEpi, kBlockN>(st, num_sms, a.full, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
@@ -342,13 +278,8 @@ int launch_product(Product prod, cudaStream_t st, int num_sms, const AMaps& a, c
     case PROD_FWD_OUT: return launch_gemm<true, false, EPI_FWD_OUT>(st, num_sms, a, b, p, b64);
     case PROD_FWD_PLAIN: return launch_gemm<true, false, EPI_PLAIN>(st, num_sms, a, b, p, b64);
     case PROD_FWD_SPLITK: return launch_gemm_bn<true, false, EPI_PLAIN, kBlockN>(st, num_sms, a.full, b, p);
-    case PROD_FWD_DXEPI: return launch_gemm<true, false, EPI_DX>(st, num_sms, a, b, p, b64);
     case PROD_DX: return launch_gemm<false, false, EPI_DX>(st, num_sms, a, b, p, b64);
-    case PROD_DX_PLAIN: return launch_gemm<false, false, EPI_PLAIN>(st, num_sms, a, b, p, b64);
     case PROD_DW: return launch_gemm<true, true, EPI_PLAIN>(st, num_sms, a, b, p, b64);
-    case PROD_DW_SGD: return launch_gemm<true, true, EPI_DW_SGD>(st, num_sms, a, b, p, b64);
-    case PROD_FWD_HID_MASK: return launch_gemm<true, false, EPI_FWD_HID_MASK>(st, num_sms, a, b, p, b64);
-    case PROD_DX_MASK: return launch_gemm<false, false, EPI_DX_MASK>(st, num_sms, a, b, p, b64);
   }
   return fail(BP_EINVAL, "launch_product: unknown product %d", (int)prod);
 }
@@ -425,15 +356,15 @@ int bp_debug_plan(int M, int N, int K, int have_b64, int num_sms, int max_pairs,
   p.M = M;
   p.N = N;
   p.K = K;
-  const KernelChoice k = pick_kernel(p, num_sms, have_b64 != 0);
-  *pair_n = k.pair_n;
+  const int pn = pick_kernel(p, num_sms, have_b64 != 0);
+  *pair_n = pn;
   *k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  if (k.pair_n == 0) {
+  if (pn == 0) {
     *tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + kBlockN - 1) / kBlockN);
     *ctas = std::min(*tiles, num_sms);
   } else {
     const int pairs = max_pairs > 0 ? std::min(max_pairs, num_sms / 2) : num_sms / 2;
-    *tiles = ((M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * ((N + k.pair_n - 1) / k.pair_n);
+    *tiles = ((M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * ((N + pn - 1) / pn);
     *ctas = 2 * std::min(*tiles, pairs);
   }
   return BP_OK;

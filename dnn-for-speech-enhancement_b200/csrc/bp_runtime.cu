@@ -107,8 +107,6 @@ struct LayerState {
   float* d = nullptr;      // dE/dX_l: rows x ldd
   float* d_lo = nullptr;
   long long ldd = 0;
-  uint32_t* mask = nullptr;  // ReLU bit mask of Y_l (hidden layers): ceil(rows/32) x ldmask words, see bp_gemm_params.h
-  long long ldmask = 0;
   // tensor maps that do not depend on the chunk
   AMaps w_fwd;         // W^T as MN-major A: {N, K}
   AMaps w_dx;          // W as K-major A:    {N, K}
@@ -127,14 +125,15 @@ struct ChunkBuf {
   long long cap_rows = 0;
   int rows = 0;            // rows currently resident
   bool has_targ = false;
+  int masked_rows = 0;     // rows [0, masked_rows) have had the input-dropout mask applied IN PLACE (BP_GPU.cu:536-540
+                           // does the same to its device copy): they can be trained once per upload
   cudaEvent_t uploaded = nullptr;  // recorded on the copy stream after the H2D
   cudaEvent_t split_done = nullptr;  // 3xTF32: x_lo has been derived from x
   cudaEvent_t consumed = nullptr;  // recorded on the compute stream after the last kernel that reads the buffer
   bool consumed_valid = false;
 };
 
-constexpr int kPeerFlagGroups = 4 + BP_MAXLAYER;  // counter groups of the peer-memory exchange (Rank::flags):
-                                                  // 0-3 see Rank::flags, 4 + l: weights of layer l landed (peer_overlap)
+constexpr int kPeerFlagGroups = 2;  // counter groups of the peer-memory exchange (Rank::flags)
 
 struct Rank {
   bp_config cfg{};
@@ -145,13 +144,6 @@ struct Rank {
   int dw_bn = 128;              // N-tile of the weight-gradient GEMM
   int ar_slices = 1;            // data-parallel: slices per layer gradient (BP_AR_SLICES; >1 measured slower: many
                                 // small all-reduces are latency-bound)
-  int fused_update = 0;         // single GPU: the dW GEMM's epilogue applies the momentum-SGD update to its own tile
-                                // (EPI_DW_SGD) instead of storing the gradient for bp_sgd_kernel.  BP_FUSED_UPDATE=1 /
-                                // bp_set_option("fused_update"); default off until measured on the B200
-  int fused_prefetch = 1;       // ... with the tile's delta/w lines pulled into L2 under the main loop
-  int relu_mask = 0;            // ReLU nets: the forward epilogues leave a bit mask of Y > 0 and the dX epilogues read it
-                                // instead of Y (1/32 of the bytes, no 32-deep load chains).  BP_RELU_MASK=1 /
-                                // bp_set_option("relu_mask"); bit-identical results; off until measured on the B200
   int comm_sms = 0;             // data-parallel: SMs the persistent GEMMs leave free so that NCCL's kernels can run
                                 // next to them instead of behind them (BP_COMM_SMS; 16/32 measured no better: the
                                 // exposed all-reduce time is that of the last, largest layers' gradients)
@@ -201,12 +193,6 @@ struct Rank {
   unsigned long long* flags = nullptr;   // kPeerFlagGroups x kMaxPeers counters, group g at flags + g*kMaxPeers:
                                          // 0 gradients of step s landed from src, 1 weights landed from src;
                                          // BP_PEER_EARLY: 0/1 = layers >= 2, 2/3 = the same two for layer 1
-  int peer_early = 0;                    // BP_PEER_EARLY=1 (one-launch-per-product path only; measured slower at N = 2)
-  int peer_overlap = 1;                  // chained path: the owner update + all-gather of step s runs layer by layer on
-                                         // the communication stream BESIDE the forward launch of step s+1, whose
-                                         // products wait per layer for their weights (BP_PEER_OVERLAP=0: serial)
-  cudaEvent_t ev_bwd = nullptr, ev_exch = nullptr;
-  bool exch_pending = false;             // an overlapped exchange is in flight on comm_stream
   PeerMem peer[kMaxPeers];
   unsigned long long dp_step = 0;
   PeerLayers peer_layers{};
@@ -256,9 +242,6 @@ struct Rank {
   ChainPlan chain_fwd, chain_bwd;
   CUtensorMap* chain_maps = nullptr;
   uint32_t* chain_counters = nullptr;   // 2 sets of kChainCounters
-  int chain_prefetch = 1;        // bp_set_option("chain_prefetch", 0): no L2 prefetch of later operands
-  int chain_pairs_cap = 0;       // > 0: use at most this many CTA pairs (leaves SMs to kernels of other streams)
-  int chain_fwd_only = 0;        // measurement aid: a train bunch stops after the forward launch
   unsigned long long* chain_trace = nullptr;  // bp_set_option("chain_trace", 1): stamps of the most recent launches
   int chain_trace_on = 0;
   int chain_set = 0;
@@ -320,7 +303,6 @@ int rank_destroy(Rank* r) {
     cudaFree(r->layer[l].d);
     cudaFree(r->layer[l].y_lo);
     cudaFree(r->layer[l].d_lo);
-    cudaFree(r->layer[l].mask);
   }
   cudaFree(r->w);
   cudaFree(r->w_lo);
@@ -333,8 +315,7 @@ int rank_destroy(Rank* r) {
   cudaFree(r->raw_targ);
   cudaFree(r->raw_tab);
   cudaFree(r->raw_norm);
-  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side, r->ev_upper, r->ev_comm_upper, r->ev_bwd,
-                 r->ev_exch})
+  for (auto e : {r->ev_t0, r->ev_t1, r->ev_grad, r->ev_comm, r->ev_side, r->ev_upper, r->ev_comm_upper})
     if (e) cudaEventDestroy(e);
   for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
@@ -375,51 +356,14 @@ int upload_params(Rank* r, float* const* weights, float* const* bias) {
   return BP_OK;
 }
 
-// Experiment (off by default, not yet run on a GPU): pin the weight arena in L2.  Inside a bunch the forward and dX
-// products behave as if their operands were cold (ncu: ~25 MB of DRAM reads per hidden-layer product, the kernel neither
-// DRAM- nor L2-bandwidth bound but ~1.7x slower than with a warm L2) because the update streams ~5x the arena through
-// L2 between two uses of the weights.  BP_L2_PERSIST=<MB> / bp_set_option("l2_persist", MB) sets aside that much L2 for
-// persisting lines (capped by the device limit) and gives every kernel of the compute and side streams an
-// access-policy window over the weight arena: hits persist, everything else keeps the normal policy.  mb <= 0 removes
-// the window and resets the persisting lines.  Best effort: failures leave the default policy in place.
-void rank_set_l2_persist(Rank* r, int mb) {
-  if (!r->w || !r->compute || !r->side) return;
-  cudaSetDevice(r->cfg.device);
-  cudaStreamAttrValue v{};
-  v.accessPolicyWindow.base_ptr = r->w;
-  v.accessPolicyWindow.num_bytes = 0;
-  v.accessPolicyWindow.hitRatio = 0.0f;
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-  cudaDeviceProp prop{};
-  size_t carve = 0, window = 0;
-  if (mb > 0 && cudaGetDeviceProperties(&prop, r->cfg.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-    carve = std::min((size_t)mb << 20, (size_t)prop.persistingL2CacheMaxSize);
-    window = std::min((size_t)r->arena_floats * 4, (size_t)prop.accessPolicyMaxWindowSize);
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess && window > 0) {
-      v.accessPolicyWindow.num_bytes = window;
-      v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
-      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    }
-  }
-  for (cudaStream_t st : {r->compute, r->side})
-    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-  if (mb <= 0) cudaCtxResetPersistingL2Cache();
-  cudaGetLastError();
-  if (getenv("BP_VERBOSE"))
-    fprintf(stderr, "libbpgpu: L2 persistence: %zu MB set aside (device max %d MB), window %zu MB, hit ratio %.2f\n",
-            carve >> 20, prop.persistingL2CacheMaxSize >> 20, v.accessPolicyWindow.num_bytes >> 20,
-            v.accessPolicyWindow.hitRatio);
-}
-
-// CUDA loads kernels lazily, at their first launch, and a load may have to wait for the kernels that are running.  The
-// overlapped data-parallel exchange launches its kernels BESIDE a forward launch that is waiting for them, so every
-// kernel of this translation unit is loaded up front (the GEMM kernels are launched long before they matter).
+// CUDA loads kernels lazily, at their first launch, and a load may have to wait for the kernels that are running — a
+// first launch beside a kernel that waits for it never starts (measured: scripts/probe/coreside_probe.cu,
+// profiles/r2g_coreside_probe_lazy_loading.log).  Nothing on the default path depends on that today, but the kernels of
+// the data-parallel exchange and the update are loaded up front so that no schedule change can run into it.
 int preload_runtime_kernels() {
   cudaFuncAttributes fa;
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_signal_kernel));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_wait_kernel));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_wait2_kernel));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, false>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, false>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, true>));
@@ -471,21 +415,13 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
   r->passes = cfg->math_mode == BP_MATH_3XTF32 ? 3 : 1;
   if (const char* e = getenv("BP_AR_SLICES")) r->ar_slices = std::max(1, atoi(e));
   if (const char* e = getenv("BP_COMM_SMS")) r->comm_sms = std::max(0, std::min(64, atoi(e)));
-  if (const char* e = getenv("BP_PEER_EARLY")) r->peer_early = atoi(e) != 0;
-  if (const char* e = getenv("BP_FUSED_UPDATE")) r->fused_update = atoi(e) != 0;
-  if (const char* e = getenv("BP_FUSED_PREFETCH")) r->fused_prefetch = atoi(e) != 0;
-  if (const char* e = getenv("BP_RELU_MASK")) r->relu_mask = atoi(e) != 0;
   if (const char* e = getenv("BP_CHAIN")) r->use_chain = atoi(e) < 0 ? -1 : atoi(e) != 0;
-  if (const char* e = getenv("BP_PEER_OVERLAP")) r->peer_overlap = atoi(e) != 0;
-  if (const char* e = getenv("BP_CHAIN_PAIRS")) r->chain_pairs_cap = atoi(e);
   int rc = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&r->compute, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_side, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&r->ev_bwd, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&r->ev_exch, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_upper, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_comm_upper, cudaEventDisableTiming));
     for (auto& e : r->ev_d) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -539,7 +475,6 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaMemsetAsync(r->w, 0, off * 4, r->compute));
     CU_TRY(cudaMemsetAsync(r->dw, 0, off * 4, r->compute));  // deltas start at zero every run (BP_GPU.cu:137-138,938)
     CU_TRY(cudaMemsetAsync(r->g, 0, off * 4, r->compute));
-    if (const char* e = getenv("BP_L2_PERSIST")) rank_set_l2_persist(r, atoi(e));
     CU_TRY(cudaMalloc(&r->sqerr_dev, sizeof(double)));
     CU_TRY(cudaMalloc(&r->splitk_ws, sizeof(float) * kMaxSplits * (size_t)cfg->bunchsize * r->layer[r->L].ldN));
 
@@ -558,9 +493,6 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
         ls.ldy = round_up(ls.N + 1, 32);
         CU_TRY(cudaMalloc(&ls.y, rows * ls.ldy * 4));
         CU_TRY(cudaMemsetAsync(ls.y, 0, rows * ls.ldy * 4, r->compute));
-        ls.ldmask = round_up(ls.N, 32);
-        CU_TRY(cudaMalloc(&ls.mask, ((rows + 31) / 32) * ls.ldmask * 4));
-        CU_TRY(cudaMemsetAsync(ls.mask, 0, ((rows + 31) / 32) * ls.ldmask * 4, r->compute));
         if (r->passes == 3) {  // the ones column's low part is 0: 1.0f truncates exactly
           CU_TRY(cudaMalloc(&ls.y_lo, rows * ls.ldy * 4));
           CU_TRY(cudaMemsetAsync(ls.y_lo, 0, rows * ls.ldy * 4, r->compute));
@@ -622,6 +554,7 @@ int rank_upload(Rank* r, int n_frames, const float* in, const float* targ, bool 
     CU_TRY(cudaEventRecord(c.split_done, r->copy));
   }
   c.rows = n_frames;
+  c.masked_rows = 0;
   c.has_targ = targ != nullptr;
   r->cur = nb;
   CU_TRY(cudaStreamWaitEvent(r->compute, r->passes == 3 ? c.split_done : c.uploaded, 0));
@@ -715,6 +648,7 @@ int rank_upload_raw(Rank* r, const bp_raw_chunk* rc, bool all_rows, bool wait_ho
   }
   CU_TRY(cudaEventRecord(c.split_done, r->copy));  // "rows assembled"
   c.rows = rows;
+  c.masked_rows = 0;
   c.has_targ = targ_words != 0;
   r->cur = nbuf;
   CU_TRY(cudaStreamWaitEvent(r->compute, c.split_done, 0));
@@ -820,13 +754,7 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
       p.out_lo = ls.y_lo;
       p.ldo = ls.ldy;
       p.drop_p = (train && drop) ? cf.hid_omit : 0.0f;
-      const bool with_mask = train && r->relu_mask && cf.activation == 0;
-      if (with_mask) {
-        p.relu_mask = ls.mask;
-        p.ldmask = ls.ldmask;
-      }
-      BP_TRY((launch_product(with_mask ? PROD_FWD_HID_MASK : PROD_FWD_HID, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p,
-                             bmap64)));
+      BP_TRY((launch_product(PROD_FWD_HID, r->compute, r->gemm_sms(), ls.w_fwd, *bmap, p, bmap64)));
       if (train) tl_mark(r, r->compute, kFwdLabel[l]);
     } else {
       if (train) {
@@ -1021,47 +949,6 @@ int peer_exchange(Rank* r) {
   return BP_OK;
 }
 
-// BP_PEER_EARLY: the exchange in two parts, each on its own pair of counter groups.  part 0 = arena rows of the layers
-// >= 2 (groups 0/1), issued when their gradient GEMMs are complete and therefore running beside the first layer's;
-// part 1 = the first layer (groups 2/3), followed by the wait for every owner's rows of both parts.  Safe because an
-// owner overwrites a replica's W_l (l >= 2) only after that replica has published its part-0 gradients, which it does
-// in stream order behind its whole dX chain — the last reader of W_l in the bunch.
-int peer_exchange_part(Rank* r, int part, unsigned long long step, long long begin4, long long end4,
-                       int blocks_per_sm) {
-  const bp_config& cf = r->cfg;
-  const int W = cf.world_size, me = cf.rank;
-  const int g_grad = part == 0 ? 0 : 2, g_w = g_grad + 1;
-  PeerFlags fg{}, fw{};
-  PeerArenas pa{};
-  for (int p = 0; p < W; ++p) {
-    fg.slot[p] = r->peer[p].flags + g_grad * kMaxPeers + me;
-    fw.slot[p] = r->peer[p].flags + g_w * kMaxPeers + me;
-    pa.w[p] = (float4*)r->peer[p].w;
-    pa.w_lo[p] = (float4*)r->peer[p].w_lo;
-  }
-  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fg, W, step);
-  const float nf = (float)cf.bunchsize;
-  const float c1 = (1 - cf.momentum) * cf.lrate;
-  const int grid = r->num_sms * blocks_per_sm;
-  const unsigned long long* gf = r->flags + g_grad * kMaxPeers;
-  if (cf.weightcost != 0.0f)
-    bp_peer_sgd_kernel<true, true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
-                                                                 r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
-                                                                 cf.momentum, c1, cf.weightcost, gf, step, begin4, end4);
-  else
-    bp_peer_sgd_kernel<false, true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (const float4*)r->recv,
-                                                                  r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
-                                                                  cf.momentum, c1, 0.0f, gf, step, begin4, end4);
-  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fw, W, step);
-  r->launches += 3;
-  if (part == 1) {
-    bp_peer_wait2_kernel<<<1, 32, 0, r->compute>>>(r->flags + kMaxPeers, r->flags + 3 * kMaxPeers, W, step);
-    r->launches++;
-  }
-  CU_TRY(cudaGetLastError());
-  return BP_OK;
-}
-
 // ------------------------------------------------------------------------------------------------ chained products
 void chain_release(Rank* r) {
   for (Rank::ChainPlan* pl : {&r->chain_fwd, &r->chain_bwd}) {
@@ -1072,15 +959,19 @@ void chain_release(Rank* r) {
   r->chain_built = false;
 }
 
-// Tile width of a product inside a chain: 256-wide pair tiles (shared-memory roof = tensor roof) when they still cover
-// >= 60 % of the pairs, else 128-wide ones (twice the tiles, shorter dependency chain) — the rule of pick_kernel.
-inline int chain_pair_n(int M, int N, int pairs, bool have_narrow_b) {
-  const int mt = (M + 255) / 256;
-  if (!have_narrow_b) return 256;
-  return mt * ((N + 255) / 256) * 10 >= pairs * 6 ? 256 : 128;
-}
-
-int chain_upload_plan(Rank* r, Rank::ChainPlan& pl, std::vector<ChainProd>& prods, std::vector<ChainShape>& shapes) {
+int chain_upload_plan(Rank* r, Rank::ChainPlan& pl, std::vector<ChainProd>& prods, std::vector<ChainShape>& shapes,
+                      int which) {
+  {  // the tables built from the device state must be the ones the host-only planner (and its CPU tests) describe
+    const std::vector<ChainShape> want =
+        chain_shapes(r->cfg.layersizes, r->L, r->local_bunch, r->chain_pairs, r->passes, which);
+    bool same = want.size() == shapes.size();
+    for (size_t i = 0; same && i < want.size(); ++i)
+      same = want[i].m_tiles == shapes[i].m_tiles && want[i].n_tiles == shapes[i].n_tiles &&
+             want[i].n_cols == shapes[i].n_cols && want[i].kb == shapes[i].kb && want[i].pair_n == shapes[i].pair_n &&
+             want[i].dep_prod == shapes[i].dep_prod && want[i].dep_all == shapes[i].dep_all &&
+             want[i].prio == shapes[i].prio;
+    if (!same) return fail(BP_EINVAL, "chain: product table differs from chain_shapes() (which = %d)", which);
+  }
   pl.max_pair_n = 128;
   for (const ChainProd& q : prods) {
     if (q.dep_prod >= 0) prods[q.dep_prod].has_consumer = 1;
@@ -1109,7 +1000,6 @@ int chain_build(Rank* r) {
   const int n = r->local_bunch;
   r->chain_pairs = chain_max_pairs(r->num_sms);
   if (r->chain_pairs <= 0) return fail(BP_ECUDA, "chain: no co-resident CTA pairs");
-  if (r->chain_pairs_cap > 0) r->chain_pairs = std::min(r->chain_pairs, r->chain_pairs_cap);
   if (!r->chain_counters) {
     CU_TRY(cudaMalloc(&r->chain_counters, 2 * Rank::kChainCounters * sizeof(uint32_t)));
     CU_TRY(cudaMemset(r->chain_counters, 0, 2 * Rank::kChainCounters * sizeof(uint32_t)));
@@ -1167,7 +1057,7 @@ int chain_build(Rank* r) {
       p.hint_a = hints ? kEvictLast : 0;
       q.amn = 1;
       q.bmn = 0;
-      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs, true);
+      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs);
       add(ls.w_fwd.full, &q.map_a, &q.map_a_lo);
       if (l == 1) {
         q.map_b = -1;
@@ -1178,10 +1068,6 @@ int chain_build(Rank* r) {
       }
       q.dep_prod = l >= 2 ? l - 2 : -1;
       q.dep_all = 0;
-      if (r->dp_p2p && r->peer_overlap) {  // patched per bunch with the step to wait for (chain_launch)
-        q.ext_flags = r->flags + (size_t)(4 + l) * kMaxPeers;
-        q.ext_n = cf.world_size;
-      }
       if (l < r->L) {
         q.epi = EPI_FWD_HID;
         p.out = ls.y;
@@ -1203,7 +1089,7 @@ int chain_build(Rank* r) {
     }
     if (cnt > Rank::kChainCounters) return fail(BP_EINVAL, "chain: too many tiles per product row (%d counters)", cnt);
     const int pn1 = r->chain_fwd.pair_n_l1;
-    BP_TRY(chain_upload_plan(r, r->chain_fwd, prods, shapes));
+    BP_TRY(chain_upload_plan(r, r->chain_fwd, prods, shapes, 0));
     r->chain_fwd.pair_n_l1 = pn1;
   }
   // ---- back-propagation: dX_L .. dX_2 (the chain) and dW_L .. dW_1 (the filler)
@@ -1232,7 +1118,7 @@ int chain_build(Rank* r) {
       q.epi = EPI_DX;
       q.amn = 0;
       q.bmn = 0;
-      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs, true);
+      q.pair_n = chain_pair_n(p.M, p.N, r->chain_pairs);
       add(ls.w_dx.full, &q.map_a, &q.map_a_lo);
       add(q.pair_n == 256 ? ls.d_dx : ls.d_dx64, &q.map_b, &q.map_b_lo);
       q.dep_prod = l < r->L ? dx_index[l + 1] : -1;  // D_l comes from the product that back-propagated through l+1
@@ -1252,7 +1138,6 @@ int chain_build(Rank* r) {
       p.out = r->g + ls.off;
       p.ldo = ls.ldN;
       p.passes = r->passes;
-      p.stream_out = tunable(TUN_DW_STREAM);
       if (r->dp_p2p) {  // reduce-scatter fused into the epilogue: chunks go straight to their owners' receive slabs
         p.scatter_n = cf.world_size;
         p.chunk_base = r->chunk_base[l];
@@ -1278,7 +1163,7 @@ int chain_build(Rank* r) {
     }
     if (cnt > Rank::kChainCounters) return fail(BP_EINVAL, "chain: too many tiles per product row (%d counters)", cnt);
     if ((int)prods.size() > CHAIN_MAX_PROD) return fail(BP_EINVAL, "chain: %d products", (int)prods.size());
-    BP_TRY(chain_upload_plan(r, r->chain_bwd, prods, shapes));
+    BP_TRY(chain_upload_plan(r, r->chain_bwd, prods, shapes, 1));
   }
   CU_TRY(cudaMalloc(&r->chain_maps, maps.size() * sizeof(CUtensorMap)));
   CU_TRY(cudaMemcpy(r->chain_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -1290,33 +1175,13 @@ int chain_build(Rank* r) {
   return BP_OK;
 }
 
-struct ChainPrefetch {
-  const void* base[6];
-  unsigned long long bytes[6];
-  int n = 0;
-  void add(const void* p, unsigned long long b) {
-    if (n < 6 && p && b >= 16384) { base[n] = p; bytes[n] = b; ++n; }
-  }
-};
-
-int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float* targ, double* sqerr,
-                 const ChainPrefetch& pf) {
+int chain_launch(Rank* r, Rank::ChainPlan& pl, const MapPair& dyn_b, const float* targ, double* sqerr) {
   static thread_local ChainArgs a;   // ~20 KB: keep it off the stack of deep call chains
   memset(&a, 0, sizeof a);
-  if (r->chain_prefetch)
-    for (int i = 0; i < pf.n; ++i) {
-      a.pf_base[i] = pf.base[i];
-      a.pf_bytes[i] = pf.bytes[i];
-      a.n_pf = i + 1;
-    }
   a.n_prods = pl.n_prods;
-  a.spin_limit = 4000000000LL;
   for (int i = 0; i < pl.n_prods; ++i) {
-    if (pl.h_prods[i].ext_n > 0 && r->cfg.world_size > 1)
-      a.spin_limit = 130000000000LL;  // the whole pipeline may wait for a late peer
     a.prods[i] = pl.h_prods[i];
     a.prods[i].p.step = r->step;
-    a.prods[i].ext_target = r->dp_step;  // the exchange of the previous bunch
     if (a.prods[i].per_bunch & 1) {
       a.prods[i].p.aux = targ;
       a.prods[i].p.sqerr = sqerr;
@@ -1364,53 +1229,6 @@ int launch_sgd_range(Rank* r, long long begin4, long long end4, int blocks_per_s
 
 int peer_exchange(Rank* r);
 
-// Overlapped exchange of the chained path.  Compute stream: publish "my partial gradients of step s have landed".
-// Communication stream, behind that: for l = 1..L the owner-side reduce + update + all-gather of layer l's rows
-// (2 blocks per SM: they fit beside a resident bp_chain_kernel CTA), then "my rows of layer l have landed" to every
-// peer.  Nothing waits on the compute stream: the next bunch's forward launch starts at once and ITS products wait,
-// layer by layer, for the owners' counters (ChainProd::ext_flags) — so the all-gather of the layers >= 2 hides under
-// the forward products before them.  Safe: a layer's weights are read by the forward product only after every
-// owner's rows landed; the receive slabs are rewritten by the NEXT back-propagation launch, which starts after that
-// forward launch, i.e. after every owner has published — and therefore finished reading — all its layers.
-int peer_exchange_layered(Rank* r) {
-  const bp_config& cf = r->cfg;
-  const int W = cf.world_size, me = cf.rank;
-  const unsigned long long step = ++r->dp_step;
-  PeerFlags fg{};
-  PeerArenas pa{};
-  for (int p = 0; p < W; ++p) {
-    fg.slot[p] = r->peer[p].flags + me;
-    pa.w[p] = (float4*)r->peer[p].w;
-    pa.w_lo[p] = (float4*)r->peer[p].w_lo;
-  }
-  bp_peer_signal_kernel<<<1, 32, 0, r->compute>>>(fg, W, step);
-  CU_TRY(cudaEventRecord(r->ev_bwd, r->compute));
-  CU_TRY(cudaStreamWaitEvent(r->comm_stream, r->ev_bwd, 0));
-  const float nf = (float)cf.bunchsize;
-  const float c1 = (1 - cf.momentum) * cf.lrate;
-  const int grid = r->num_sms * 2;
-  for (int l = 1; l <= r->L; ++l) {
-    const LayerState& ls = r->layer[l];
-    const long long b4 = ls.off / 4, e4 = (ls.off + ls.size) / 4;
-    if (cf.weightcost != 0.0f)
-      bp_peer_sgd_kernel<true, true><<<grid, 256, 0, r->comm_stream>>>((float4*)r->dw, (const float4*)r->recv,
-                                                                       r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
-                                                                       cf.momentum, c1, cf.weightcost, r->flags, step, b4, e4);
-    else
-      bp_peer_sgd_kernel<false, true><<<grid, 256, 0, r->comm_stream>>>((float4*)r->dw, (const float4*)r->recv,
-                                                                        r->arena_floats / 4, pa, r->peer_layers, W, me, nf,
-                                                                        cf.momentum, c1, 0.0f, r->flags, step, b4, e4);
-    PeerFlags fw{};
-    for (int p = 0; p < W; ++p) fw.slot[p] = r->peer[p].flags + (size_t)(4 + l) * kMaxPeers + me;
-    bp_peer_signal_kernel<<<1, 32, 0, r->comm_stream>>>(fw, W, step);
-  }
-  CU_TRY(cudaGetLastError());
-  CU_TRY(cudaEventRecord(r->ev_exch, r->comm_stream));
-  r->exch_pending = true;
-  r->launches += 1 + 2 * r->L;
-  return BP_OK;
-}
-
 // One train bunch as two chained launches (forward products; dX chain + dW products) and the update.
 int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const int n = r->local_bunch;
@@ -1426,30 +1244,17 @@ int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const float* xlo = c.x_lo ? c.x_lo + (long long)f0 * r->ldx : nullptr;
   MapPair xfwd, xdw;
   BP_TRY(make_map(&xfwd, xb, xlo, r->K0(), n, r->ldx, r->chain_fwd.pair_n_l1 / 2, false));
-  ChainPrefetch pf_fwd, pf_bwd;
-  for (int l = 2; l <= r->L; ++l)  // the weights of the layers after the first, needed 15-60 us into the launch
-    pf_fwd.add(r->w + r->layer[l].off, (unsigned long long)r->layer[l].size * 4);
-  BP_TRY(chain_launch(r, r->chain_fwd, xfwd, c.t + (long long)f0 * r->Nout(), loss_slot, pf_fwd));
+  BP_TRY(chain_launch(r, r->chain_fwd, xfwd, c.t + (long long)f0 * r->Nout(), loss_slot));
   tl_mark(r, r->compute, "forward chain");
   mark();                                               // 1: forward done
-  if (r->chain_fwd_only) {
-    for (int k = 0; k < 5; ++k) mark();
-    r->step++;
-    r->bunches++;
-    if (prof) r->prof_cnt++;
-    return BP_OK;
-  }
   BP_TRY(make_map(&xdw, xb, xlo, r->K0() + 1, n, r->ldx, r->dw_bn, true));
-  if ((long long)f0 + 2LL * n <= c.rows)  // the next bunch's input rows (this chunk), for its first forward product
-    pf_bwd.add(xb + (long long)n * r->ldx, (unsigned long long)n * r->ldx * 4);
-  BP_TRY(chain_launch(r, r->chain_bwd, xdw, nullptr, nullptr, pf_bwd));
+  BP_TRY(chain_launch(r, r->chain_bwd, xdw, nullptr, nullptr));
   tl_mark(r, r->compute, "back-propagation chain");
   mark();                                               // 2: dX chain and all dW done
   mark();                                               // 3
   mark();                                               // 4
   mark();                                               // 5
-  if (r->dp_p2p && r->peer_overlap) BP_TRY(peer_exchange_layered(r));  // ... beside the next bunch's forward launch
-  else if (r->dp_p2p) BP_TRY(peer_exchange(r));         // owner-side reduce + update + all-gather
+  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
   else BP_TRY(launch_sgd_range(r, 0, r->arena_floats / 4, 8));
   tl_mark(r, r->compute, "update / exchange, end of bunch");
   mark();                                               // 6
@@ -1467,7 +1272,7 @@ int train_bunch_chain(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
 int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   const bp_config& cf = r->cfg;
   const bool want_chain = r->use_chain == 1 || (r->use_chain < 0 && r->dp_p2p);
-  if (want_chain && (!r->nccl_comm || r->dp_p2p) && !(r->dp_p2p && r->peer_early))
+  if (want_chain && (!r->nccl_comm || r->dp_p2p))
     return train_bunch_chain(r, c, f0, loss_slot);
   const int n = r->local_bunch;
   const bool prof = r->profiling;
@@ -1483,9 +1288,6 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   // update has not touched it yet).  So dW_l is launched on the side stream as soon as dE/dX_l exists and runs
   // concurrently with the rest of the dX chain, filling the SMs a 128-tile GEMM leaves idle on a 148-SM part.
   // Last layer first, so its all-reduce starts earliest.
-  // Fused update (single GPU, off by default): dW_l's epilogue rewrites W_l in place, so it may only start when the dX
-  // product that reads W_l (the one producing dE/dX_{l-1}) is complete — `after` is then ev_d[l-1] instead of ev_d[l].
-  const bool fused = r->fused_update && !r->nccl_comm && !r->dp_p2p && cf.world_size == 1;
   auto launch_dw = [&](int l, cudaEvent_t after) -> int {
     LayerState& ls = r->layer[l];
     CU_TRY(cudaStreamWaitEvent(r->side, after, 0));
@@ -1496,7 +1298,6 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.out = r->g + ls.off;
     p.ldo = ls.ldN;
     p.passes = r->passes;
-    p.stream_out = tunable(TUN_DW_STREAM);
     MapPair xmap;
     const MapPair* bmap = &ls.yprev_dw;
     if (l == 1) {
@@ -1512,23 +1313,6 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
       p.chunk_base = r->chunk_base[l];
       for (int o = 0; o < cf.world_size; ++o)
         p.scatter[o] = r->peer[o].recv + (long long)cf.rank * r->arena_floats + ls.off;
-    }
-    if (fused) {
-      p.out = nullptr;  // the gradient never reaches memory
-      p.upd_w = r->w + ls.off;
-      p.upd_delta = r->dw + ls.off;
-      p.upd_w_lo = r->w_lo ? r->w_lo + ls.off : nullptr;
-      p.upd_nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
-      p.upd_inv_nf = (cf.bunchsize & (cf.bunchsize - 1)) == 0 ? 1.0f / (float)cf.bunchsize : 0.0f;
-      p.upd_momentum = cf.momentum;
-      p.upd_c1 = (1 - cf.momentum) * cf.lrate;
-      p.upd_wc = cf.weightcost;
-      p.upd_bias_col = ls.K;
-      p.upd_prefetch = r->fused_prefetch;
-      BP_TRY((launch_product(PROD_DW_SGD, r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
-      r->launches++;
-      tl_mark(r, r->side, kDwLabel[l]);
-      return BP_OK;
     }
     const int total = p.N;
     int slices = 1;
@@ -1571,71 +1355,31 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     p.act = cf.activation;
     p.passes = r->passes;
     p.hint_a = kEvictLast;  // A = the weights
-    const bool with_mask = r->relu_mask && cf.activation == 0;  // the forward pass of this bunch left lp.mask
-    if (with_mask) {
-      p.relu_mask = lp.mask;
-      p.ldmask = lp.ldmask;
-    }
-    BP_TRY((launch_product(with_mask ? PROD_DX_MASK : PROD_DX, r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p,
-                           &ls.d_dx64)));
+    BP_TRY((launch_product(PROD_DX, r->compute, r->gemm_sms(), ls.w_dx, ls.d_dx, p, &ls.d_dx64)));
     r->launches++;
     tl_mark(r, r->compute, kDxLabel[l - 1]);
     CU_TRY(cudaEventRecord(r->ev_d[l - 1], r->compute));
     return BP_OK;
   };
   CU_TRY(cudaEventRecord(r->ev_d[r->L], r->compute));  // dE/dX_L comes out of the forward's last epilogue
-  if (fused) {
-    // dW_l (which rewrites W_l) follows the dX product that read W_l; it still overlaps the rest of the dX chain.
-    for (int l = r->L; l >= 2; --l) {
-      BP_TRY(launch_dx(l));
-      BP_TRY(launch_dw(l, r->ev_d[l - 1]));
-    }
-    BP_TRY(launch_dw(1, r->ev_d[1]));
-  } else {
-    BP_TRY(launch_dw(r->L, r->ev_d[r->L]));
-    if (r->L == 2) BP_TRY(mark_upper());
-    for (int l = r->L; l >= 2; --l) {
-      BP_TRY(launch_dx(l));
-      if (l - 1 == 1 && r->L > 2) BP_TRY(mark_upper());  // before dW_1 enters the side stream
-      BP_TRY(launch_dw(l - 1, r->ev_d[l - 1]));
-    }
+  BP_TRY(launch_dw(r->L, r->ev_d[r->L]));
+  if (r->L == 2) BP_TRY(mark_upper());
+  for (int l = r->L; l >= 2; --l) {
+    BP_TRY(launch_dx(l));
+    if (l - 1 == 1 && r->L > 2) BP_TRY(mark_upper());  // before dW_1 enters the side stream
+    BP_TRY(launch_dw(l - 1, r->ev_d[l - 1]));
   }
   mark();                                               // 2: dX chain issued/done on `compute`
-  const float nf = (float)cf.bunchsize;  // `n` of kernUpdatedelta: int promoted to float
-  const float c1 = (1 - cf.momentum) * cf.lrate;
-  const int sgd_stream = tunable(TUN_SGD_STREAM);
-  auto launch_sgd = [&](long long begin4, long long end4, int blocks_per_sm) -> int {
-    const int grid = r->num_sms * blocks_per_sm;
-    if (cf.weightcost != 0.0f)
-      bp_sgd_kernel<true><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4,
-                                                        end4, nf, cf.momentum, c1, cf.weightcost, r->bias_ranges,
-                                                        (float4*)r->w_lo, sgd_stream);
-    else
-      bp_sgd_kernel<false><<<grid, 256, 0, r->compute>>>((float4*)r->dw, (float4*)r->w, (const float4*)r->g, begin4,
-                                                         end4, nf, cf.momentum, c1, 0.0f, r->bias_ranges,
-                                                         (float4*)r->w_lo, sgd_stream);
-    CU_TRY(cudaGetLastError());
-    r->launches++;
-    return BP_OK;
-  };
   // The update is HBM-bound, the first layer's gradient GEMM (the largest, and the last to become computable) is
   // tensor-bound and reads neither weights nor deltas: once the dX chain is done the layers >= 2 are updated while dW_1
   // still runs on the side stream.  The early launch leaves thread slots free so the GEMM's CTAs become resident.
   const int sgd_early_blocks = tunable(TUN_SGD_EARLY);  // 0 = one update launch after all gradients (reference order)
   long long tail_end4 = r->arena_floats / 4;
-  const bool peer_split = r->dp_p2p && r->peer_early && r->L >= 2;
-  unsigned long long peer_step = 0;
-  if (peer_split) {  // exchange of the layers >= 2 beside dW_1 (which the side stream already holds)
-    peer_step = ++r->dp_step;
-    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
-    tail_end4 = r->layer[2].off / 4;
-    BP_TRY(peer_exchange_part(r, 0, peer_step, tail_end4, r->arena_floats / 4, 6));
-  }
-  if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p && !fused) {
+  if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
     if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
     tail_end4 = r->layer[2].off / 4;
-    BP_TRY(launch_sgd(tail_end4, r->arena_floats / 4, sgd_early_blocks));
+    BP_TRY(launch_sgd_range(r, tail_end4, r->arena_floats / 4, sgd_early_blocks));
     tl_mark(r, r->compute, "update, layers >= 2");
   }
   mark();                                               // 3: early update of layers >= 2 done
@@ -1648,9 +1392,8 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm, 0));
   }
   mark();                                               // 5: all-reduce waited
-  if (peer_split) BP_TRY(peer_exchange_part(r, 1, peer_step, 0, tail_end4, 8));
-  else if (r->dp_p2p) BP_TRY(peer_exchange(r));         // owner-side reduce + update + all-gather
-  else if (!fused) BP_TRY(launch_sgd(0, tail_end4, 8)); // fused: the dW epilogues have already applied the update
+  if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
+  else BP_TRY(launch_sgd_range(r, 0, tail_end4, 8));
   tl_mark(r, r->compute, "update / exchange, end of bunch");
   mark();                                               // 6: sgd done
   r->step++;
@@ -1665,6 +1408,10 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
 
 int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   CU_TRY(cudaSetDevice(r->cfg.device));
+  if (r->cfg.world_size > 1 && !r->nccl_comm && !r->dp_p2p)  // would scale by 2/B_global over B/N rows and diverge
+    return fail(BP_ECOMM, "train: rank %d of %d has no communicator (call bp_comm_init first)", r->cfg.rank,
+                r->cfg.world_size);
+  const bool in_drop = r->cfg.dropoutflag == 1 && r->cfg.visible_omit > 0.0f;
   ChunkBuf& c = r->chunk[r->cur];
   if (!c.x || !c.has_targ) return fail(BP_EINVAL, "train_resident: no resident chunk with targets");
   if (first_bunch < 0 || n_bunches < 0 || (long long)(first_bunch + n_bunches) * r->local_bunch > c.rows)
@@ -1682,12 +1429,15 @@ int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   if (n_bunches > 0) CU_TRY(cudaMemsetAsync(r->loss_dev[li], 0, sizeof(double) * n_bunches, r->compute));
   r->loss_n[li] = n_bunches;
   r->loss_cur = li;
+  if (in_drop && n_bunches > 0) {
+    // the input mask zeroes the resident rows themselves: training them again would stack a second mask on the first
+    if (first_bunch * r->local_bunch < c.masked_rows)
+      return fail(BP_EINVAL, "train_resident: rows from %d on were already trained with input dropout (visible_omit), "
+                  "which masks the resident chunk in place — upload the chunk again", first_bunch * r->local_bunch);
+    c.masked_rows = (first_bunch + n_bunches) * r->local_bunch;
+  }
   for (int b = 0; b < n_bunches; ++b)
     BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev[li] + b));
-  if (r->exch_pending) {  // whatever follows this call on the compute stream sees the exchanged weights
-    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_exch, 0));
-    r->exch_pending = false;
-  }
   CU_TRY(cudaEventRecord(r->loss_done[li], r->compute));
   CU_TRY(cudaEventRecord(c.consumed, r->compute));
   c.consumed_valid = true;
@@ -1922,24 +1672,27 @@ int bp_create(bp_handle** h, int gpu_used, int numlayers, const int* layersizes,
 
   bp_handle* hh = new bp_handle();
   hh->ranks.assign(gpu_used, nullptr);
-  char id[128];
-  if (gpu_used > 1) {
-    int rc = bp_comm_unique_id(id);
-    if (rc != BP_OK) { delete hh; return rc; }
-  }
   int rc = for_each_rank(hh, [&](int i) -> int {
     bp_config c = cfg;
     c.rank = i;
     c.device = i;
-    BP_TRY(rank_create(&hh->ranks[i], &c, weights, bias));
-    if (gpu_used > 1) {
-      NcclApi::Id128 uid;
-      memcpy(uid.b, id, 128);
-      NCCL_TRY(g_nccl.CommInitRank(&hh->ranks[i]->nccl_comm, gpu_used, uid, i));
-    }
-    return BP_OK;
+    return rank_create(&hh->ranks[i], &c, weights, bias);
   });
+  // The default exchange runs over peer memory and needs no NCCL at all: try it first, and create the NCCL
+  // communicator (which needs a loadable libnccl) only when BP_DP=nccl asks for it or the devices cannot map each other.
   if (rc == BP_OK) rc = group_p2p_connect(hh);
+  if (rc == BP_OK && gpu_used > 1 && !hh->ranks[0]->dp_p2p) {
+    char id[128];
+    rc = bp_comm_unique_id(id);
+    if (rc == BP_OK)
+      rc = for_each_rank(hh, [&](int i) -> int {
+        CU_TRY(cudaSetDevice(hh->ranks[i]->cfg.device));
+        NcclApi::Id128 uid;
+        memcpy(uid.b, id, 128);
+        NCCL_TRY(g_nccl.CommInitRank(&hh->ranks[i]->nccl_comm, gpu_used, uid, i));
+        return BP_OK;
+      });
+  }
   if (rc != BP_OK) {
     std::string keep = g_err;
     bp_destroy(hh);
@@ -2045,7 +1798,7 @@ int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
   const int nb = rc->n_samples / B;
   if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
-  if (h->ranks.size() == 1 && !tunable(TUN_UPLOAD_WAIT_FIRST)) {
+  if (h->ranks.size() == 1) {
     // queue the bunches while the records are still in flight; wait for the DMA last
     BP_TRY(check_raw_chunk(h, rc));
     Rank* r = h->ranks[0];
@@ -2095,7 +1848,7 @@ int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
   if (n_frames % per_call_bunch)
     printf("this bunch has only %d samples and is ignored.\n", n_frames % per_call_bunch);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
-  if (h->ranks.size() == 1 && !tunable(TUN_UPLOAD_WAIT_FIRST)) {
+  if (h->ranks.size() == 1) {
     // queue the bunches while the chunk is still in flight; wait for the DMA last
     BP_TRY(rank_upload(r0, n_frames, in, targ, false));
     const int rc_train = rank_train_resident(r0, 0, nb);
@@ -2106,6 +1859,15 @@ int bp_train(bp_handle* h, int n_frames, const float* in, const float* targ) {
   }
   BP_TRY(bp_upload_chunk(h, n_frames, in, targ));
   return bp_train_resident(h, 0, nb);
+}
+
+int bp_set_dropout_seed(bp_handle* h, uint64_t seed) {
+  if (!h) return fail(BP_EINVAL, "null handle");
+  for (Rank* r : h->ranks) {
+    r->cfg.seed = seed;
+    r->chain_built = false;  // the chained launches' product tables carry the seed
+  }
+  return BP_OK;
 }
 
 int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, int reset_dropout_step) {
@@ -2154,20 +1916,8 @@ int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias) {
 int bp_set_option(bp_handle* h, const char* name, int value) {
   if (!h || !name) return fail(BP_EINVAL, "bp_set_option: null argument");
   for (Rank* r : h->ranks) {
-    if (strcmp(name, "fused_update") == 0) r->fused_update = value != 0;
-    else if (strcmp(name, "fused_prefetch") == 0) r->fused_prefetch = value != 0;
-    else if (strcmp(name, "peer_early") == 0) r->peer_early = value != 0;  // every rank must be given the same value
-    else if (strcmp(name, "relu_mask") == 0) r->relu_mask = value != 0;    // between bunches only (bp_train* has returned)
-    else if (strcmp(name, "chain") == 0) r->use_chain = value < 0 ? -1 : value != 0;  // -1 auto, 0 per product, 1 chained
+    if (strcmp(name, "chain") == 0) r->use_chain = value < 0 ? -1 : value != 0;  // -1 auto, 0 per product, 1 chained
     else if (strcmp(name, "chain_trace") == 0) r->chain_trace_on = value != 0;
-    else if (strcmp(name, "chain_prefetch") == 0) r->chain_prefetch = value != 0;
-    else if (strcmp(name, "peer_overlap") == 0) {  // every rank the same value, and only before the first bunch: the
-      if (r->dp_step > 0)                          // per-layer counters of the two modes are not kept in step
-        return fail(BP_EINVAL, "bp_set_option: peer_overlap can only be changed before the first train bunch");
-      r->peer_overlap = value != 0;
-    }
-    else if (strcmp(name, "chain_fwd_only") == 0) r->chain_fwd_only = value != 0;
-    else if (strcmp(name, "l2_persist") == 0) rank_set_l2_persist(r, value);   // value = MB, <= 0 removes the window
     else if (set_tunable(name, value) != BP_OK)                            // process-wide switches (bp_internal.h)
       return fail(BP_EINVAL, "bp_set_option: unknown option '%s'", name);
     r->chain_built = false;  // the product tables capture the switches (hints, streaming stores): rebuild lazily
@@ -2209,87 +1959,45 @@ int bp_get_option(bp_handle* h, const char* name, int* value) {
     *value = hv[1] ? (int)(1000.0 * (double)hv[0] / (double)hv[1] + 0.5) : 0;
     return BP_OK;
   }
-  if (strcmp(name, "peer_early") == 0) { *value = r->peer_early; return BP_OK; }
-  if (strcmp(name, "relu_mask") == 0) { *value = r->relu_mask; return BP_OK; }
   if (strcmp(name, "chain") == 0) { *value = r->use_chain; return BP_OK; }
-  if (strcmp(name, "peer_overlap") == 0) { *value = r->peer_overlap; return BP_OK; }
   if (get_tunable(name, value) == BP_OK) return BP_OK;
   return fail(BP_EINVAL, "bp_get_option: unknown option '%s'", name);
 }
 
-// Bring-up aid: can a small kernel become resident BESIDE a running bp_chain_kernel?  The forward launch of one bunch
-// is made to wait (all products) for a counter that only a later launch on another stream sets: `blocks_per_sm` x
-// `threads` filler blocks spinning ~20 us, then a one-thread kernel that releases the counter.  Returns BP_OK and the
-// elapsed ms if the forward launch completed, a CUDA error (its waits trap after ~2 s) if the two cannot co-reside.
-__global__ void bp_coreside_filler_kernel(unsigned long long* sink) {
-  const long long t0 = clock64();
-  while (clock64() - t0 < 40000) {}
-  if (threadIdx.x == 0 && blockIdx.x == 0) sink[1] = (unsigned long long)clock64();
-}
-__global__ void bp_coreside_release_kernel(unsigned long long* flag) {
-  __threadfence_system();
-  st_release_sys(flag, 1ull);
-}
-int bp_debug_coresidency(bp_handle* h, int blocks_per_sm, int threads, float* ms) {
-  if (!h || !ms) return fail(BP_EINVAL, "bp_debug_coresidency: null argument");
-  Rank* r = h->ranks[0];
-  CU_TRY(cudaSetDevice(r->cfg.device));
-  {  // kernels are loaded lazily and loading may synchronise with running kernels: load these two now
-    cudaFuncAttributes fa;
-    CU_TRY(cudaFuncGetAttributes(&fa, bp_coreside_filler_kernel));
-    CU_TRY(cudaFuncGetAttributes(&fa, bp_coreside_release_kernel));
-  }
-  ChunkBuf& c = r->chunk[r->cur];
-  if (!c.x || !c.has_targ || c.rows < r->local_bunch) return fail(BP_EINVAL, "bp_debug_coresidency: upload a chunk first");
-  if (!r->chain_built) BP_TRY(chain_build(r));
-  unsigned long long* flag = nullptr;
-  CU_TRY(cudaMalloc(&flag, 64));
-  CU_TRY(cudaMemset(flag, 0, 64));
-  std::vector<ChainProd> keep = r->chain_fwd.h_prods;
-  for (ChainProd& q : r->chain_fwd.h_prods) {
-    q.ext_flags = flag;
-    q.ext_n = 1;
-  }
-  const unsigned long long keep_step = r->dp_step;
-  r->dp_step = 1;  // ext_target
-  MapPair xfwd;
-  int rc = make_map(&xfwd, c.x, c.x_lo, r->K0(), r->local_bunch, r->ldx, r->chain_fwd.pair_n_l1 / 2, false);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  if (rc == BP_OK) {
-    cudaStreamSynchronize(r->compute);
-    cudaEventRecord(e0, r->compute);
-    ChainPrefetch pf;
-    rc = chain_launch(r, r->chain_fwd, xfwd, c.t, r->sqerr_dev, pf);
-    // NB chain_launch sets the ~65 s limit because of ext_n; a failure shows as a long stall, so keep the box safe:
-    cudaEventRecord(e1, r->compute);
-    if (getenv("BP_CORESIDE_CARVEOUT")) {  // same shared-memory carve-out as the resident kernel's SMs
-      cudaFuncSetAttribute(bp_coreside_filler_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(bp_coreside_release_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
+// Host-only: the schedule of the chained launches for a net / bunch / pair count (include/bp_gpu_debug.h).
+int bp_debug_chain_plan(int numlayers, const int* layersizes, int rows, int pairs, int which, int passes,
+                        int max_items, int* n_items, int* pair, int* prod, int* mt, int* nt, int max_prods, int* n_prods,
+                        int* dep_prod, int* dep_all, int* m_tiles, int* n_tiles, int* pair_n, int* n_cols,
+                        long long* makespan_cycles) {
+  if (numlayers < 2 || numlayers > BP_MAXLAYER || !layersizes || rows <= 0 || pairs <= 0 || pairs > CHAIN_MAX_PAIRS ||
+      !n_items || !n_prods)
+    return fail(BP_EINVAL, "bp_debug_chain_plan: bad argument");
+  const std::vector<ChainShape> shapes = chain_shapes(layersizes, numlayers - 1, rows, pairs, passes, which);
+  std::vector<ChainItem> items;
+  std::vector<int> pair_off;
+  const long long ms = chain_schedule(shapes, pairs, items, pair_off);
+  if (ms < 0) return fail(BP_EINVAL, "bp_debug_chain_plan: dependency cycle");
+  if (makespan_cycles) *makespan_cycles = ms;
+  *n_items = (int)items.size();
+  *n_prods = (int)shapes.size();
+  if ((int)items.size() > max_items || (int)shapes.size() > max_prods)
+    return fail(BP_EINVAL, "bp_debug_chain_plan: %d items / %d products exceed the buffers", (int)items.size(),
+                (int)shapes.size());
+  for (int p = 0; p < pairs; ++p)
+    for (int i = pair_off[p]; i < pair_off[p + 1]; ++i) {
+      if (pair) pair[i] = p;
+      if (prod) prod[i] = items[i].prod;
+      if (mt) mt[i] = items[i].mt;
+      if (nt) nt[i] = items[i].nt;
     }
-    size_t dyn = 0;
-    if (const char* e = getenv("BP_CORESIDE_SMEM")) {  // same carve-out CLASS as the resident kernel: same dynamic size
-      dyn = (size_t)atoi(e) * 1024;
-      cudaFuncSetAttribute(bp_coreside_filler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      cudaFuncSetAttribute(bp_coreside_release_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    }
-    if (blocks_per_sm > 0) bp_coreside_filler_kernel<<<blocks_per_sm, threads, dyn, r->comm_stream>>>(flag + 2);
-    bp_coreside_release_kernel<<<1, 1, dyn, r->comm_stream>>>(flag);
-    if (cudaGetLastError() != cudaSuccess) fprintf(stderr, "coreside: launch of the small kernels failed\n");
+  for (size_t q = 0; q < shapes.size(); ++q) {
+    if (dep_prod) dep_prod[q] = shapes[q].dep_prod;
+    if (dep_all) dep_all[q] = shapes[q].dep_all;
+    if (m_tiles) m_tiles[q] = shapes[q].m_tiles;
+    if (n_tiles) n_tiles[q] = shapes[q].n_tiles;
+    if (pair_n) pair_n[q] = shapes[q].pair_n;
+    if (n_cols) n_cols[q] = shapes[q].n_cols;
   }
-  r->chain_fwd.h_prods = keep;
-  r->dp_step = keep_step;
-  cudaError_t e = cudaStreamSynchronize(r->compute);
-  cudaStreamSynchronize(r->comm_stream);
-  if (rc == BP_OK && e == cudaSuccess) cudaEventElapsedTime(ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(flag);
-  if (rc != BP_OK) return rc;
-  CU_TRY(e);
   return BP_OK;
 }
 
@@ -2500,18 +2208,15 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
   long long a_rows, a_cols, b_rows, b_cols;
   bool amn, bmn;
   switch (kind) {
-    case 0: case 3: case 7: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
-    case 1: case 4: case 6: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
+    case 0: case 3: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
+    case 1: a_rows = M; a_cols = K; b_rows = N; b_cols = K; amn = false; bmn = false; break;
     case 2: a_rows = K; a_cols = M; b_rows = K; b_cols = N; amn = true; bmn = true; break;
-    case 5: a_rows = K; a_cols = M; b_rows = N; b_cols = K; amn = true; bmn = false; break;
     default: return fail(BP_EINVAL, "bp_debug_gemm: kind %d", kind);
   }
   const long long dlda = round_up(a_cols, 32), dldb = round_up(b_cols, 32), dldo = round_up(M, 32),
                   dldaux = round_up(M, 32);
   float *dA = nullptr, *dB = nullptr, *dO = nullptr, *dBias = nullptr, *dAux = nullptr, *dAlo = nullptr,
         *dBlo = nullptr;
-  uint32_t* dMask = nullptr;  // kinds 6 / 7: ReLU bit mask, ceil(N/32) x dldo words
-  const long long mask_words = (long long)((N + 31) / 32) * dldo;
   cudaStream_t st;
   cudaEvent_t e0, e1;
   int rc = [&]() -> int {
@@ -2556,45 +2261,17 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
     p.aux = dAux; p.ldaux = dldaux;
     p.scale = scale;
     p.act = act < 0 ? 0 : act;
-    if (const char* e = getenv("BP_DBG_FLAGS")) p.dbg_flags = (uint32_t)atoi(e);
-    long long* dtrace = nullptr;
-    if (getenv("BP_DBG_TRACE")) {
-      CU_TRY(cudaMalloc(&dtrace, 2048 * sizeof(long long)));
-      CU_TRY(cudaMemset(dtrace, 0, 2048 * sizeof(long long)));
-      p.dbg_trace = dtrace;
-    }
     int reps = 1;
     if (const char* e = getenv("BP_DBG_REPS")) reps = std::max(1, atoi(e));
     const int sms = prop.multiProcessorCount;
-    if ((kind == 0 || kind == 7) && !bias) return fail(BP_EINVAL, "kind 0 / 7 needs bias");
-    if ((kind == 1 || kind == 5 || kind == 6) && !aux) return fail(BP_EINVAL, "kind 1 / 5 / 6 needs aux (Y)");
-    if (kind == 6 || kind == 7) {
-      CU_TRY(cudaMalloc(&dMask, mask_words * 4));
-      CU_TRY(cudaMemset(dMask, 0, mask_words * 4));
-      p.relu_mask = dMask;
-      p.ldmask = dldo;
-      p.act = 0;  // the mask is the ReLU derivative
-      if (kind == 6) {  // what the forward epilogue would have left for this Y
-        std::vector<uint32_t> hm((size_t)mask_words, 0u);
-        for (int n = 0; n < N; ++n)
-          for (int m = 0; m < M; ++m)
-            if (aux[(size_t)n * ldaux + m] > 0.0f) hm[(size_t)(n >> 5) * dldo + m] |= 1u << (n & 31);
-        CU_TRY(cudaMemcpy(dMask, hm.data(), mask_words * 4, cudaMemcpyHostToDevice));
-      }
-    }
+    if (kind == 0 && !bias) return fail(BP_EINVAL, "kind 0 needs bias");
+    if (kind == 1 && !aux) return fail(BP_EINVAL, "kind 1 needs aux (Y)");
     for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is an untimed warm-up when reps > 1
       if (rep == (reps > 1 ? 1 : 0)) CU_TRY(cudaEventRecord(e0, st));
       if (reps == 1 && rep == 1) break;
       if (kind == 0) BP_TRY((launch_product(PROD_FWD_HID, st, sms, ma, mb, p, &mb64)));
       else if (kind == 3) BP_TRY((launch_product(PROD_FWD_PLAIN, st, sms, ma, mb, p, &mb64)));
       else if (kind == 1) BP_TRY((launch_product(PROD_DX, st, sms, ma, mb, p, &mb64)));
-      // diagnostics for the dX-vs-forward gap: the dX operand majors with the plain epilogue / the forward majors with
-      // the dX epilogue
-      else if (kind == 4) BP_TRY((launch_product(PROD_DX_PLAIN, st, sms, ma, mb, p, &mb64)));
-      else if (kind == 5) BP_TRY((launch_product(PROD_FWD_DXEPI, st, sms, ma, mb, p, &mb64)));
-      // ReLU bit mask: the dX product reading the mask instead of Y / the forward product leaving the mask
-      else if (kind == 6) BP_TRY((launch_product(PROD_DX_MASK, st, sms, ma, mb, p, &mb64)));
-      else if (kind == 7) BP_TRY((launch_product(PROD_FWD_HID_MASK, st, sms, ma, mb, p, &mb64)));
       else BP_TRY((launch_product(PROD_DW, st, sms, ma, mb, p, &mb64)));
     }
     CU_TRY(cudaEventRecord(e1, st));
@@ -2604,40 +2281,9 @@ int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const 
       *elapsed_ms /= (float)reps;
     }
     CU_TRY(cudaMemcpy2D(out, size_t(ldo) * 4, dO, dldo * 4, size_t(M) * 4, N, cudaMemcpyDeviceToHost));
-    if (kind == 7) {  // self-check: every bit of the mask the epilogue left equals (stored y > 0)
-      std::vector<uint32_t> hm((size_t)mask_words);
-      CU_TRY(cudaMemcpy(hm.data(), dMask, mask_words * 4, cudaMemcpyDeviceToHost));
-      for (int n = 0; n < N; ++n)
-        for (int m = 0; m < M; ++m) {
-          const bool bit = (hm[(size_t)(n >> 5) * dldo + m] >> (n & 31)) & 1u;
-          if (bit != (out[(size_t)n * ldo + m] > 0.0f))
-            return fail(BP_ECUDA, "kind 7: mask bit of (unit %d, frame %d) is %d but y = %g", m, n, (int)bit,
-                        out[(size_t)n * ldo + m]);
-        }
-      for (long long i = 0; i < mask_words; ++i) {  // bits of frames >= N stay clear
-        const int c = (int)(i / dldo);
-        const int valid = std::min(32, N - c * 32);
-        if (valid < 32 && (hm[(size_t)i] >> valid) != 0u) return fail(BP_ECUDA, "kind 7: mask bits set beyond frame %d", N);
-      }
-    }
-    if (dtrace) {  // bring-up aid: print CTA 0's timeline of the last launch (cycles relative to kernel start)
-      std::vector<long long> t(2048);
-      CU_TRY(cudaMemcpy(t.data(), dtrace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      cudaFree(dtrace);
-      const long long t0 = t[1026];
-      const int nkb = std::min(256, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
-      printf("trace (cycles since CTA start): kb | slot_free  loads_issued  full_seen  mma_issued\n");
-      for (int kb = 0; kb < nkb; ++kb)
-        if (kb < 24 || kb >= nkb - 4)
-          printf("  %3d | %9lld %9lld %9lld %9lld\n", kb, t[kb] - t0, t[256 + kb] - t0, t[512 + kb] - t0,
-                 t[768 + kb] - t0);
-      printf("  accumulator ready seen %lld, epilogue done %lld\n", t[1024] - t0, t[1025] - t0);
-      fflush(stdout);
-    }
     return BP_OK;
   }();
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dBias); cudaFree(dAux); cudaFree(dAlo); cudaFree(dBlo);
-  cudaFree(dMask);
   return rc;
 }
 

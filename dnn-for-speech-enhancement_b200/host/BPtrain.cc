@@ -161,6 +161,16 @@ static void run_epoch(Interface* io, bp_handle* trainer, double t_epoch0) {
   fflush(io->fp_log);
 }
 
+// Dropout key of the epoch this process (or this pass of the in-process loop) trains: seed= mixed with
+// init_randem_seed, which the Perl driver advances by 345 per epoch (.pl:136) — so every epoch draws different masks,
+// as the reference's time(NULL)-seeded cuRAND does (BP_GPU.cu:77-78), yet a run is reproducible from its command line.
+static unsigned long long epoch_dropout_seed(const WorkPara* para) {
+  unsigned long long z = para->seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(unsigned)para->init_randem_seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;   // splitmix64 finaliser
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
 int main(int argc, char* argv[]) {
   const double t_start = now_s();
 
@@ -173,7 +183,7 @@ int main(int argc, char* argv[]) {
   if (para->activation == 1) setenv("BP_ACTIVATION", "sigmoid", 1);
   {
     char buf[64];
-    snprintf(buf, sizeof buf, "%llu", para->seed);
+    snprintf(buf, sizeof buf, "%llu", epoch_dropout_seed(para));
     setenv("BP_SEED", buf, 1);
   }
   bp_handle* trainer = nullptr;
@@ -191,6 +201,7 @@ int main(int argc, char* argv[]) {
     const double t0 = now_s();
     const float m = io->begin_epoch(epoch);
     if (bp_begin_epoch(trainer, para->lrate, m, para->weightcost, 1) != BP_OK) die(io, "begin_epoch failed");
+    if (bp_set_dropout_seed(trainer, epoch_dropout_seed(para)) != BP_OK) die(io, "set_dropout_seed failed");
     run_epoch(io, trainer, t0);
   }
 

@@ -91,6 +91,12 @@ int bp_return_weights(bp_handle* h, float* const* weights, float* const* bias);
  * the three hyper-parameters are replaced, and the dropout step counter restarts iff reset_dropout_step != 0. */
 int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, int reset_dropout_step);
 
+/* Re-keys the dropout masks (Philox key) from the next bunch on.  The reference seeds cuRAND from time(NULL) in every
+ * process (BP_GPU.cu:77-78), so its masks differ from epoch to epoch; BPtrain derives the key from seed= and
+ * init_randem_seed (which the Perl driver advances by 345 per epoch, .pl:136) and calls this at every in-process epoch
+ * boundary, so that an epoch draws the masks a fresh process started for it would draw. */
+int bp_set_dropout_seed(bp_handle* h, uint64_t seed);
+
 /* Run-time switches of experimental / measurement code paths (defaults come from the environment variable of the same
  * meaning at bp_create time).  Results are unaffected; only scheduling and fusion change.  Known names:
  *   "fused_update"   1: on a single GPU the weight-gradient GEMM's epilogue applies kernUpdatedelta + kernAccSum
@@ -127,6 +133,9 @@ const char* bp_last_error(void);
  * already in HBM, and a reader thread can overlap the next upload.
  * ------------------------------------------------------------------------------------------------------------- */
 int bp_upload_chunk(bp_handle* h, int n_frames, const float* in, const float* targ /* may be NULL */);
+/* NB with dropoutflag = 1 and visible_omit > 0 the input mask is applied IN PLACE to the resident rows, as the
+ * reference does to its device copy (BP_GPU.cu:536-540): a row can be trained once per upload; training it again is
+ * refused (BP_EINVAL) instead of silently stacking masks. */
 int bp_train_resident(bp_handle* h, int first_bunch, int n_bunches);
 int bp_forward_resident(bp_handle* h, int first_frame, int n_frames, float* out_host /* may be NULL */,
                         double* sum_sq_err /* may be NULL; needs resident targets */);
@@ -219,45 +228,6 @@ int bp_comm_init(bp_handle* h, const char id128[128]);
 /* Mask that the fused dropout draws for (activation tensor `layer`, global frame, unit) at bunch `step`;
  * exposed so tests can replay masks against the oracle.  Returns 1 = dropped, 0 = kept. */
 int bp_dropout_mask(uint64_t seed, uint32_t step, uint32_t layer, uint32_t frame, uint32_t unit, float p);
-
-/* Host-only (no GPU needed): the kernel the library would pick for an M x N x K product on a device with num_sms SMs —
- * *pair_n = 0 (128 x 128 tiles on lone CTAs), 128 or 256 (256 x pair_n tiles on CTA pairs) — the number of output
- * tiles, the CTAs launched (persistent, <= one per SM) and the 64-deep k-blocks per tile.  have_b64: the B operand
- * also has a 64-row-box tensor map (hidden-layer forward and dX products); max_pairs <= 0 assumes num_sms / 2. */
-int bp_debug_plan(int M, int N, int K, int have_b64, int num_sms, int max_pairs, int* pair_n, int* tiles, int* ctas,
-                  int* k_blocks);
-/* Stand-alone launch of one fused GEMM (host operands, testing only).
- *  kind 0: fwd  out[n*ldo+m] = act(scale * sum_k W[k*ldw+m] * X[n*ldx+k] + bias[m])     A=W (K x M), B=X (N x K)
- *  kind 1: dX   out[n*ldo+m] = act'(Y[n*ldy+m]) * sum_k W[m*ldw+k] * D[n*ldd+k]         A=W (M x K), B=D (N x K)
- *  kind 2: dW   out[n*ldo+m] = sum_k D[k*ldd+m] * X[k*ldx+n]                            A=D (K x M), B=X (K x N)
- *  kind 3: plain fwd (no bias/activation).   act < 0 means "no activation" for kind 0.
- *  kind 4: kind 1's operands (A = W, M x K) with the plain epilogue;  kind 5: kind 0's operands (A = W, K x M) with
- *          kind 1's epilogue (act'(Y) * acc) — diagnostics that separate operand layout from epilogue cost.
- *  kind 6: kind 1 for ReLU with the bit mask of Y > 0 (built here from aux) instead of Y — must equal kind 1's output
- *          bit for bit;  kind 7: kind 0 for ReLU that also leaves the mask; the call fails if any mask bit differs
- *          from (out > 0) or a bit beyond frame N is set. */
-int bp_debug_gemm(int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* out,
-                  int ldo, const float* bias, const float* aux, int ldaux, float scale, int act, int math_mode,
-                  float* elapsed_ms);
-
-/* Stand-alone fused SGD update on host arrays of length n (testing only): kernUpdatedelta + kernAccSum
- * (DevFunc.cu:313-318, 270-277). */
-int bp_debug_sgd(int n, float* delta, float* weights, const float* grad, int bunch, float momentum, float lrate,
-                 float weightcost);
-
-/* Bring-up microbenchmark (testing only): cycles per 128 x bn x 8 TF32 tcgen05.mma on one SM with both operands in
- * shared memory.  combo 0 = A MN-major/B K-major, 1 = K/K, 2 = MN/MN, 3 = K/MN. */
-int bp_debug_mma_rate(int combo, int bn, int iters, int mode, double* cyc_issue, double* cyc_total);
-
-/* Bring-up aid of the chained launches (bp_set_option(h, "chain_trace", 1) first): per-tile timestamps of the most
- * recent forward (which = 0) or back-propagation (which = 1) launch, CSV text. */
-int bp_debug_chain_trace(bp_handle* h, int which, char* buf, int len);
-
-/* Bring-up aid: GB/s of the GEMM epilogues' store pattern (layout 0: tiles of a row-major matrix, 1: contiguous tiles). */
-int bp_debug_store_pattern(int layout, int ld, int mb, int reps, int ctas, double* gbs);
-
-/* Bring-up aid: does a kernel of blocks_per_sm x threads become resident beside a running chained forward launch? */
-int bp_debug_coresidency(bp_handle* h, int blocks_per_sm, int threads, float* ms);
 
 int bp_version(void);
 

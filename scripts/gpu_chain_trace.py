@@ -31,14 +31,20 @@ def main():
     g.set_option("chain", 1)
     for k, v in opts.items():
         g.set_option(k, int(v))
-    g.train_resident(0, cb)
-    g.sync()
-    g.timer_start()
-    for _ in range(4):
+    fresh = dflag == 1 and vo > 0   # input dropout masks the resident rows in place: fresh upload per pass
+    ms = 0.0
+    for i in range(5):
+        if fresh:
+            g.upload_chunk(cb * lb, px.array, pt.array)
+        g.sync()
+        g.timer_start()
         g.train_resident(0, cb)
-    ms = g.timer_stop() / (4 * cb)
+        ms += g.timer_stop() if i else 0.0
+    ms /= 4 * cb
     print(f"#### {wl} {opts}: {ms:.4f} ms per bunch")
     g.set_option("chain_trace", 1)
+    if fresh:
+        g.upload_chunk(cb * lb, px.array, pt.array)
     g.train_resident(0, cb)
     g.sync()
     lib = bp.load_library()

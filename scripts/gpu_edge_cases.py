@@ -3,7 +3,7 @@
 tests/test_gpu_parity.py (the round-end suite runs with -x, so unproven cases wait here):
   odd bunch sizes (37, 1), a one-layer net, the deepest net the ABI allows (9 weight layers), a 1-unit output,
   a chunk shorter than one bunch (train is a no-op, like BP_GPU.cu:297-318), forward of 1 frame, CV of a ragged tail,
-  weight cost with odd sizes, the same cases through the fused update (bp_set_option).
+  weight cost with odd sizes, the same cases through the chained launches (bp_set_option "chain").
 Prints one line per case; exit status 1 if any fails."""
 import importlib
 import os
@@ -29,14 +29,14 @@ def close(got, want, tol):
     return bool(np.isfinite(got).all()) and float(np.max(np.abs(got.astype(np.float64) - want))) <= tol * rms(want)
 
 
-def case(name, sizes, bunch, n_frames, fused=0, **kw):
+def case(name, sizes, bunch, n_frames, chain=0, **kw):
     w, b = O.glorot_init(sizes, seed=3)
     x, t = O.synth_data(max(n_frames, 1), sizes[0], sizes[-1], seed=9)
     x, t = x[:n_frames], t[:n_frames]
     o = O.Net(sizes, bunch, tf32=1, weights=w, bias=b, **kw)
     g = bp.BP_GPU(1, len(sizes), sizes, bunch, kw.get("lrate", 1.0), kw.get("momentum", 0.0), kw.get("weightcost", 0.0),
                   w, b, 0, 0.0, 0.0, activation=kw.get("activation", 0), device=0)
-    g.set_option("fused_update", fused)
+    g.set_option("chain", chain)
     ok = True
     if n_frames > 0:
         g.train(n_frames, x, t)
@@ -52,13 +52,13 @@ def case(name, sizes, bunch, n_frames, fused=0, **kw):
     ok &= abs(cv - ref) <= 4 * TOL * abs(ref) + 1e-6
     ok &= close(g.forward(1, xf[:1]), o.forward(xf[:1]).astype(np.float64), 2 * TOL)
     g.close()
-    print(f"[{'OK ' if ok else 'BAD'}] {name}{' (fused update)' if fused else ''}")
+    print(f"[{'OK ' if ok else 'BAD'}] {name}{' (chained launches)' if chain else ''}")
     return ok
 
 
 def main():
     ok = True
-    for fused in (0, 1):
+    for chain in (0, 1):
         for args in (("bunch 37, ragged tail", [75, 96, 33], 37, 3 * 37 + 5, dict(lrate=0.7, momentum=0.9)),
                      ("bunch 1", [40, 24, 8], 1, 5, dict(lrate=0.1, momentum=0.5)),
                      ("one weight layer", [129, 65], 32, 96, dict(momentum=0.9)),
@@ -68,10 +68,10 @@ def main():
                      ("weight cost, odd sizes", [257, 131, 67, 3], 40, 120, dict(lrate=0.5, momentum=0.9, weightcost=1e-3)),
                      ("sigmoid, odd sizes", [61, 45, 29], 24, 72, dict(activation=1, momentum=0.9))):
             try:
-                ok &= case(args[0], args[1], args[2], args[3], fused, **args[4])
+                ok &= case(args[0], args[1], args[2], args[3], chain, **args[4])
             except Exception:
                 ok = False
-                print(f"[EXC] {args[0]}{' (fused update)' if fused else ''}")
+                print(f"[EXC] {args[0]}{' (chained launches)' if chain else ''}")
                 traceback.print_exc()
     print("EDGE CASES", "ALL OK" if ok else "FAILED")
     return 0 if ok else 1

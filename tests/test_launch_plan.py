@@ -44,25 +44,3 @@ def test_plans_of_the_baseline_configs(bp, name, M, N, K, b64, want):
 def test_plan_rejects_bad_arguments(bp):
     lib = bp.load_library()
     assert lib.bp_debug_plan(0, 1, 1, 0, SMS, 0, None, None, None, None) != 0
-
-
-def test_small_pairs_switch_changes_only_small_products():
-    """BP_SMALL_PAIRS=1 (gated experiment): 128-wide pairs for small products whose unit count is a multiple of 256;
-    the plans of C2 / C3 / C5 stay as they are.  The switch is read once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import importlib, ctypes as C\n"
-        "bp = importlib.import_module('dnn-for-speech-enhancement_b200'); lib = bp.load_library()\n"
-        "lib.bp_debug_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_int)] * 4\n"
-        "def plan(M, N, K, b64):\n"
-        "    v = [C.c_int(0) for _ in range(4)]\n"
-        "    assert lib.bp_debug_plan(M, N, K, b64, 148, 0, *[C.byref(x) for x in v]) == 0\n"
-        "    return [x.value for x in v]\n"
-        "print(plan(2048, 512, 2048, 1), plan(2048, 128, 2048, 1), plan(2048, 1024, 2048, 1), plan(257, 512, 2048, 1),"
-        " plan(2048, 2049, 1024, 0))\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, BP_SMALL_PAIRS="1"),
-                         capture_output=True, text=True, check=True).stdout.strip()
-    assert out == "[128, 32, 64, 32] [128, 8, 16, 32] [128, 64, 128, 32] [0, 12, 12, 32] [256, 72, 144, 16]", out

@@ -1,10 +1,9 @@
-"""GPU tests added after the last GPU call of round 1 (they have not run on a B200 yet) — this file sorts last so that
-`-x` cannot mask the proven tests behind them.
+"""GPU tests of the decode pipeline, the chunk prefetch thread, edge shapes and the chained launches:
   * decode straight from raw Pfile records without targets (BP_GPU.decode_raw = bp_crossvalid_raw with a null score
     pointer and no target records): bit-identical with bp_forward on the rows the host reader assembles;
   * the pipelined decode (bp_decode_raw_submit / _wait, two chunks in flight) against the synchronous one;
-  * the ReLU bit mask (EPI_FWD_HID_MASK / EPI_DX_MASK): the two epilogues in isolation, and training with
-    bp_set_option("relu_mask", 1) bit-identical with the default;
+  * edge shapes against the oracle, with one launch per product and with the chained launches; the chained launches
+    bit-identical with the per-product kernels at the BASELINE shapes;
   * BPtrain's chunk prefetch thread (prefetch=1, the default) trains the very same epoch as the serial loop
     (prefetch=0), for both readers: byte-identical .wts, identical CV score."""
 import importlib
@@ -110,63 +109,6 @@ def test_bptrain_prefetch_thread_trains_the_same_epoch(reader):
         assert _cv(f"{d}/pf0.log") == _cv(f"{d}/pf1.log")
 
 
-@pytest.mark.parametrize("shape", [(128, 128, 64), (257, 100, 96), (64, 37, 40), (300, 1030, 515), (2048, 1024, 257)])
-def test_relu_mask_epilogues_in_isolation(shape):
-    """kind 6 (dX product reading the bit mask) == kind 1 (reading Y) bit for bit; kind 7 (forward product leaving
-    the mask) == kind 0 bit for bit, with the library checking every mask bit against (y > 0)."""
-    import ctypes as C
-    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
-    lib = bp.load_library()
-    M, N, K = shape
-    rng = np.random.default_rng(M + 3 * N + 7 * K)
-    fp = C.POINTER(C.c_float)
-
-    def run(kind, A, B, bias, aux):
-        out = np.full((N, M), np.nan, dtype=np.float32)
-        rc = lib.bp_debug_gemm(kind, M, N, K, A.ctypes.data_as(fp), A.shape[1], B.ctypes.data_as(fp), B.shape[1],
-                               out.ctypes.data_as(fp), M, None if bias is None else bias.ctypes.data_as(fp),
-                               None if aux is None else aux.ctypes.data_as(fp), M, 1.0, 0, 0, None)
-        assert rc == 0, lib.bp_last_error().decode()
-        return out
-
-    # dX: A = W (M x K), B = D (N x K), aux = Y with zeros, negatives and -0.0 in it
-    A = rng.standard_normal((M, K), dtype=np.float32)
-    B = rng.standard_normal((N, K), dtype=np.float32)
-    Y = rng.standard_normal((N, M), dtype=np.float32)
-    Y[rng.random((N, M)) < 0.3] = 0.0
-    Y[0, 0] = -0.0
-    with_y, with_mask = run(1, A, B, None, Y), run(6, A, B, None, Y)
-    assert np.array_equal(with_y.view(np.uint32), with_mask.view(np.uint32))
-    assert np.all(with_mask[Y <= 0] == 0)
-    # forward: A = W (K x M), B = X (N x K)
-    A = rng.standard_normal((K, M), dtype=np.float32)
-    bias = rng.standard_normal(M).astype(np.float32)
-    plain, masked = run(0, A, B, bias, None), run(7, A, B, bias, None)
-    assert np.array_equal(plain.view(np.uint32), masked.view(np.uint32))
-
-
-@pytest.mark.parametrize("case", ["ragged", "pairs", "dropout"])
-def test_relu_mask_training_is_bit_identical(case):
-    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
-    import oracle_py as O
-    sizes, bunch, nb, kw = {"ragged": ([75, 96, 70, 33], 37, 4, {}),
-                            "pairs": ([300, 2048, 512, 33], 1024, 2, {}),
-                            "dropout": ([129, 70, 50, 20], 48, 5, dict(dropoutflag=1, visible_omit=0.1, hid_omit=0.3))}[case]
-    w, b = O.glorot_init(sizes, seed=3)
-    x, t = O.synth_data(bunch * nb, sizes[0], sizes[-1], seed=11)
-    res = []
-    for mask in (0, 1):
-        g = bp.BP_GPU(1, len(sizes), sizes, bunch, 1.0, 0.9, 0.0, w, b, kw.get("dropoutflag", 0),
-                      kw.get("visible_omit", 0.0), kw.get("hid_omit", 0.0), device=0, seed=777)
-        g.set_option("relu_mask", mask)
-        g.train(bunch * nb, x, t)
-        res.append(g.returnWeights())
-        g.close()
-    for l in range(1, len(sizes)):
-        assert np.array_equal(res[0][0][l], res[1][0][l]) and np.array_equal(res[0][1][l], res[1][1][l]), f"layer {l}"
-        assert not np.array_equal(res[0][0][l], w[l])   # it did train
-
-
 EDGE_CASES = [("bunch 37, ragged tail", [75, 96, 33], 37, 3 * 37 + 5, dict(lrate=0.7, momentum=0.9)),
               ("bunch 1", [40, 24, 8], 1, 5, dict(lrate=0.1, momentum=0.5)),
               ("one weight layer", [129, 65], 32, 96, dict(momentum=0.9)),
@@ -177,14 +119,52 @@ EDGE_CASES = [("bunch 37, ragged tail", [75, 96, 33], 37, 3 * 37 + 5, dict(lrate
               ("sigmoid, odd sizes", [61, 45, 29], 24, 72, dict(activation=1, momentum=0.9))]
 
 
-@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("chain", [0, 1], ids=["per-product", "chained"])
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
-def test_edge_shapes_against_the_oracle(case, fused):
-    """The shapes of scripts/gpu_edge_cases.py (odd and unit bunches, 1 and 9 weight layers, a 1-unit output, a chunk
-    shorter than a bunch = no-op like BP_GPU.cu:297-318, forward of 1 frame, CV of a ragged tail) against the
-    tf32-conditioned oracle, with the separate and the fused update."""
+def test_edge_shapes_against_the_oracle(case, chain):
+    """Odd and unit bunches, 1 and 9 weight layers, a 1-unit output, a chunk shorter than a bunch (= no-op like
+    BP_GPU.cu:297-318), forward of 1 frame, CV of a ragged tail — against the tf32-conditioned oracle, with one launch
+    per product and with the chained launches (csrc/bp_chain.cuh)."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
     import gpu_edge_cases as E
     name, sizes, bunch, n_frames, kw = case
-    assert E.case(name, sizes, bunch, n_frames, fused, **kw)
+    assert E.case(name, sizes, bunch, n_frames, chain, **kw)
+
+
+CHAIN_CASES = [("tiny ragged", [75, 96, 33], 37, 4, {}),
+               ("one layer", [129, 65], 32, 3, {}),
+               ("nine layers", [64, 72, 40, 96, 33, 80, 48, 56, 64, 20], 32, 2, {}),
+               ("odd sizes, weight cost", [300, 261, 131, 33], 96, 3, dict(weightcost=1e-3)),
+               ("dropout", [129, 70, 50, 20], 48, 4, dict(dropoutflag=1, visible_omit=0.1, hid_omit=0.3)),
+               ("sigmoid", [61, 45, 29], 24, 3, dict(activation=1)),
+               ("3xTF32", [300, 512, 129], 256, 2, dict(math_mode=1)),
+               ("C2, 3 bunches", [2827, 2048, 2048, 2048, 257], 1024, 3, {}),
+               ("C3 dropout", [3084, 2048, 2048, 2048, 257], 2048, 2, dict(dropoutflag=1, visible_omit=0.2, hid_omit=0.2)),
+               ("C4 per-GPU share", [2827, 2048, 2048, 2048, 2048, 2048, 257], 512, 2, {})]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_chained_launches_are_bit_identical_with_one_launch_per_product(case):
+    """bp_chain_kernel (the forward products of a bunch in one launch, the dX chain + all dW products in a second one)
+    runs the same tiles with the same k order and the same epilogues as the per-product kernels: the trained weights
+    must be IDENTICAL (with the output layer's split-K off on the per-product side, which the chain does not use)."""
+    import oracle_py as O
+    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
+    _name, sizes, bunch, nb, kw = case
+    w, b = O.glorot_init(sizes, seed=3)
+    x, t = O.synth_data(bunch * nb + 3, sizes[0], sizes[-1], seed=11)
+    res = []
+    for chain in (0, 1):
+        g = bp.BP_GPU(1, len(sizes), sizes, bunch, 1.0, 0.9, kw.get("weightcost", 0.0), w, b, kw.get("dropoutflag", 0),
+                      kw.get("visible_omit", 0.0), kw.get("hid_omit", 0.0), device=0, seed=777,
+                      activation=kw.get("activation", 0), math_mode=kw.get("math_mode", 0))
+        g.set_option("chain", chain)
+        g.set_option("splitk", 0)
+        assert g.get_option("chain") == chain
+        g.train(x.shape[0], x, t)
+        res.append(g.returnWeights())
+        g.close()
+    for l in range(1, len(sizes)):
+        assert np.array_equal(res[0][0][l], res[1][0][l]) and np.array_equal(res[0][1][l], res[1][1][l]), f"layer {l}"
+        assert np.isfinite(res[1][0][l]).all() and not np.array_equal(res[1][0][l], w[l])
