@@ -229,7 +229,7 @@ def isolated_dominant_gemm(bp, sizes, lb, reps=2000, sampler=None):
             "clocks": sampler.region("isolated") if sampler is not None else None}
 
 
-TRAFFIC_FILE = "r1d_traffic.json"
+TRAFFIC_FILE = "r2_traffic.json"
 
 
 class Ctx:
@@ -767,7 +767,7 @@ def main():
     extras = {}
     if world > 1:
         extras["exchange"] = {0: "none", 1: "nccl", 2: "p2p"}[g.get_option("dp_exchange")]
-        extras["peer_early"] = g.get_option("peer_early")
+        extras["schedule"] = "chained launches" if g.get_option("chain") != 0 else "one launch per product"
     g.close()
     px.free()
     pt.free()

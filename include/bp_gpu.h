@@ -97,22 +97,15 @@ int bp_begin_epoch(bp_handle* h, float lrate, float momentum, float weightcost, 
  * boundary, so that an epoch draws the masks a fresh process started for it would draw. */
 int bp_set_dropout_seed(bp_handle* h, uint64_t seed);
 
-/* Run-time switches of experimental / measurement code paths (defaults come from the environment variable of the same
- * meaning at bp_create time).  Results are unaffected; only scheduling and fusion change.  Known names:
- *   "fused_update"   1: on a single GPU the weight-gradient GEMM's epilogue applies kernUpdatedelta + kernAccSum
- *                       (DevFunc.cu:313-318, 270-277) to its own tile instead of storing the gradient for a separate
- *                       update kernel — bit-identical weights, 16 instead of 24 B/parameter (BP_FUSED_UPDATE)
- *   "fused_prefetch" 1: ... with the tile's delta/weight lines prefetched into L2 under the main loop (default 1)
- *   "peer_early"     1: data-parallel peer-memory exchange in two parts — the layers >= 2 are reduced, updated and
- *                       all-gathered while the first layer's gradient GEMM still runs (BP_PEER_EARLY); every rank
- *                       must be given the same value
- *   "relu_mask"      1: ReLU nets — the hidden layers' forward epilogues also leave a bit mask of Y > 0 and the
- *                       back-propagation epilogues read that mask instead of Y (kernDsigmoid's ReLU' is the predicate
- *                       y > 0, DevFunc.cu:81-97): 1/32 of the bytes, bit-identical results (BP_RELU_MASK)
- *   "l2_persist"     MB of persisting L2 with an access-policy window over the weight arena (<= 0 removes it)
- *   process-wide scheduling switches (each starts from its environment variable, scripts/SWITCHES.md): "pdl",
- *   "tma_hint", "l2_prefetch", "stages", "pairs", "mc", "small_pairs", "dw_stream", "sgd_stream", "sgd_early", "splitk"
- *   — changeable between calls so that alternatives are A/B-timed inside one process (scripts/gpu_ab_inproc.py)
+/* Run-time scheduling switches (defaults come from the environment variable of the same meaning at bp_create time;
+ * scripts/SWITCHES.md lists them with their measured effect).  Results are unaffected — bit for bit, except "splitk",
+ * which changes the summation order of the output layer.  Known names:
+ *   "chain"          -1 automatic / 0 one launch per matrix product / 1 chained launches: all forward products of a bunch
+ *                    in one persistent launch, the dX chain + every dW product in a second one (csrc/bp_chain.cuh).
+ *                    Automatic = chained for data-parallel ranks on peer memory, per product on a single GPU (BP_CHAIN)
+ *   "chain_trace"    1: bring-up aid, per-tile timestamps of the chained launches (bp_debug_chain_trace)
+ *   process-wide switches: "pdl", "tma_hint", "pairs", "sgd_stream", "sgd_early", "splitk" — changeable between calls so
+ *   that alternatives are A/B-timed inside one process (scripts/gpu_ab_quick.py)
  * Returns BP_EINVAL for an unknown name. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 

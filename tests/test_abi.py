@@ -54,7 +54,7 @@ def test_bad_arguments_are_rejected(bp):
     assert lib.bp_create_ex(C.byref(h), None, None, None) != 0
     assert b"null" in lib.bp_last_error()
     assert lib.bp_train(None, 1, None, None) != 0
-    assert lib.bp_set_option(None, b"fused_update", 1) != 0
+    assert lib.bp_set_option(None, b"chain", 1) != 0
     assert lib.bp_debug_gemm(9, 1, 1, 1, None, 1, None, 1, None, 1, None, None, 1, 1.0, 0, 0, None) != 0
 
 

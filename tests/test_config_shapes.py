@@ -64,8 +64,11 @@ def test_c5_shape_forward_vs_oracle(bp, oracle, parity_log):
     g.close()
     ref_tf, ref_fp = o_tf.forward(x), o_fp.forward(x)
     assert np.isfinite(out).all()
-    parity_log("C5 decode vs tf32 oracle (max/rms)", np.abs(out - ref_tf).max() / rms(ref_tf), BOUND["c5_tf32"])
-    parity_log("C5 decode vs literal-fp32 oracle (max/rms)", np.abs(out - ref_fp).max() / rms(ref_fp), BOUND["c5_fp32"])
+    e_tf, e_fp = np.abs(out - ref_tf).max() / rms(ref_tf), np.abs(out - ref_fp).max() / rms(ref_fp)
+    print(f"[parity] C5 decode: vs tf32 oracle {e_tf:.3e}, vs literal-fp32 oracle {e_fp:.3e} (max |err| / rms)")
+    parity_log("C5 decode vs tf32 oracle (max/rms)", e_tf, BOUND["c5_tf32"])
+    parity_log("C5 decode vs literal-fp32 oracle (max/rms)", e_fp, BOUND["c5_fp32"])
+    parity_log("C5 decode vs literal-fp32 oracle (rel. Frobenius)", fro(out - ref_fp) / fro(ref_fp), BOUND["c5_fp32_fro"])
 
 
 def test_c4_shape_local_bunch_vs_oracle(bp, oracle, parity_log):
@@ -116,7 +119,7 @@ def test_c2_size_vs_reference_cuda_binary(bp, oracle, parity_log, math):
 # <= 2x the achieved values recorded in profiles/r2_parity_errors.json.
 BOUND = {
     "c3_dw": 4e-2, "c3_w": 5e-6,          # achieved 2.0e-2 (layer 1) / 1.3e-6
-    "c5_tf32": 3.5e-3, "c5_fp32": 1e-2,   # achieved 1.7e-3
+    "c5_tf32": 3.5e-3, "c5_fp32": 3e-2, "c5_fp32_fro": 5e-3,   # achieved 1.7e-3 / (max over 2.1 M outputs) / -
     "c4_dw": 5e-2,                        # achieved 2.6e-2 (layer 1 of 6)
     "c2_ref_dw_tf32": 5e-2, "c2_ref_w_tf32": 2.5e-5, "c2_ref_cv_tf32": 1e-4,        # achieved 2.8e-2 / 1.1e-5 / 3.5e-5
     "c2_ref_dw_3xtf32": 6e-3, "c2_ref_w_3xtf32": 1e-5, "c2_ref_cv_3xtf32": 1e-4,    # achieved 2.9e-3 / 4.3e-6 / 4.9e-5

@@ -168,3 +168,4 @@ def test_chained_launches_are_bit_identical_with_one_launch_per_product(case):
     for l in range(1, len(sizes)):
         assert np.array_equal(res[0][0][l], res[1][0][l]) and np.array_equal(res[0][1][l], res[1][1][l]), f"layer {l}"
         assert np.isfinite(res[1][0][l]).all() and not np.array_equal(res[1][0][l], w[l])
+

@@ -56,9 +56,16 @@ def test_reference_main_with_our_trainer_equals_our_cli(dropout):
         T.write_norm(f"{d}/fea.norm", mu, ivar)
         extra = ["traincache=700"] + (["dropoutflag=1", "visible_omit=0.1", "hid_omit=0.2"] if dropout else [])
         drop = ("traincache=3000",) + (("dropoutflag=0", "visible_omit=0", "hid_omit=0") if dropout else ())
+        # Our CLI keys the dropout masks on seed= mixed with init_randem_seed (host/BPtrain.cc: epoch_dropout_seed); the
+        # reference's main knows nothing of seeds, so the library takes BP_SEED from the environment: same key here.
+        z = (0x5EED5EED + 0x9E3779B97F4A7C15 * 7) & (2 ** 64 - 1)          # seed default, init_randem_seed=7 (_args)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        env = dict(os.environ, BP_SEED=str(z ^ (z >> 31)))
         for tag, exe in (("shim", SHIM), ("ours", OURS)):
             a = [x for x in _args(d, tag, extra) if x not in drop]
-            o = subprocess.run([exe] + a, cwd=d, capture_output=True, text=True, timeout=600)
+            o = subprocess.run([exe] + a, cwd=d, capture_output=True, text=True, timeout=600,
+                               env=env if tag == "shim" else None)
             assert o.returncode == 1, o.stdout + o.stderr          # success exit status is 1 (BPtrain.cc:100)
         assert open(f"{d}/shim.wts", "rb").read() == open(f"{d}/ours.wts", "rb").read()
         assert _cv(f"{d}/shim.log") == _cv(f"{d}/ours.log")
