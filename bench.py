@@ -743,7 +743,7 @@ def main():
             try:
                 fea_dim, ctx_w, n_s = 257, 11, e2e_cb * lb
                 n_rec = n_s + ctx_w - 1
-                rng = np.random.default_rng(11 + rank)
+                rng = np.random.default_rng(11)            # the same records on every rank
                 pf, ptg = bp.PinnedArray((n_rec, fea_dim + 2)), bp.PinnedArray((n_rec, sizes[-1] + 2))
                 for pa, scale in ((pf, 1.0), (ptg, 0.5)):
                     words = rng.standard_normal(pa.array.shape, dtype=np.float32) * np.float32(scale)
@@ -754,8 +754,10 @@ def main():
                                   np.ones(fea_dim, np.float32), frames,
                                   (frames // 300) * 300 if nat else None)   # "sentences" of 300 frames for the NAT mean
                 dt_raw, _ = e2e_loop(lambda c: g.train_raw(raw), n_calls)
-                e2e["raw_reader"] = {"value": n_calls * n_s * world / dt_raw, "unit": "frames/s",
-                                     "h2d_bytes_per_step": 4 * n_rec * (fea_dim + sizes[-1] + 4) // e2e_cb * world,
+                # a raw chunk is the GLOBAL chunk: every rank is handed the same n_s samples and assembles its own
+                # rows of each global bunch on its device, so one call trains n_s frames in total
+                e2e["raw_reader"] = {"value": n_calls * n_s / dt_raw, "unit": "frames/s",
+                                     "h2d_bytes_per_step": 4 * n_rec * (fea_dim + sizes[-1] + 4) * world * gb // n_s,
                                      "d2h_bytes_per_step": 8 * world,
                                      "api": f"bp_train_raw() on pinned raw-record chunks of {e2e_cb} bunches "
                                             "(device-side splice, BPtrain reader=gpu)"}

@@ -1793,8 +1793,10 @@ int bp_decode_raw_wait(bp_handle* h) {
 int bp_train_raw(bp_handle* h, const bp_raw_chunk* rc) {
   if (!h || !rc) return fail(BP_EINVAL, "null argument");
   if (!rc->targ_records) return fail(BP_EINVAL, "bp_train_raw: no target records");
-  // a rank handle (one process per GPU) is given ITS rows of every global bunch, as in bp_train
-  const int B = (h->ranks.size() == 1) ? h->ranks[0]->local_bunch : h->ranks[0]->cfg.bunchsize;
+  // NB unlike bp_train, a raw chunk is the GLOBAL chunk for every kind of handle: each rank (thread of a group, or
+  // process with its own rank handle) is given the same records and sample table and assembles ITS rows of every
+  // global bunch on its device (rank_upload_raw), so the bunch count divides by the global bunch size
+  const int B = h->ranks[0]->cfg.bunchsize;
   const int nb = rc->n_samples / B;
   if (rc->n_samples % B) printf("this bunch has only %d samples and is ignored.\n", rc->n_samples % B);  // BP_GPU.cu:317
   if (nb == 0) return BP_OK;
