@@ -23,43 +23,6 @@ struct SgdBiasRanges {
 // L2 policy: the momentum deltas and the gradients are touched by nobody else until the next update, so they are
 // streamed (evict-first loads/stores) and do not push the weights — which the next bunch's forward and dX GEMMs read —
 // out of the 126 MB L2 (the three arenas of the C2 net are 176 MB).
-// One float4 of the update, shared by the two kernels below so that they cannot drift apart: same operations, same order.
-template <bool kHasWC>
-__device__ __forceinline__ void sgd_apply4(const float4& g, float4& d, float4& x, float nf, float momentum,
-                                           float one_minus_m_lr, float wc) {
-  const float gv[4] = {g.x, g.y, g.z, g.w};
-  float dv[4] = {d.x, d.y, d.z, d.w};
-  float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float t = __fdiv_rn(gv[k], nf);
-    if (kHasWC) t = __fadd_rn(t, __fmul_rn(wc, xv[k]));
-    const float nd = __fsub_rn(__fmul_rn(momentum, dv[k]), __fmul_rn(one_minus_m_lr, t));
-    dv[k] = nd;
-    xv[k] = __fadd_rn(nd, xv[k]);
-  }
-  d = make_float4(dv[0], dv[1], dv[2], dv[3]);
-  x = make_float4(xv[0], xv[1], xv[2], xv[3]);
-}
-__device__ __forceinline__ float4 tf32_lo4(const float4& x) {
-  float4 lo;
-  lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-  lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-  lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-  lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-  return lo;
-}
-template <bool kHasWC>
-__device__ __forceinline__ float sgd_weightcost_at(long long i, float weightcost, const SgdBiasRanges& br) {
-  float wc = weightcost;
-  if (kHasWC) {
-#pragma unroll 1
-    for (int r = 0; r < br.n; ++r)
-      if (i >= br.begin4[r] && i < br.end4[r]) wc = 0.0f;
-  }
-  return wc;
-}
-
 template <bool kHasWC>
 __global__ void __launch_bounds__(256)
 bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad, long long begin4,
@@ -72,54 +35,32 @@ bp_sgd_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* 
     const float4 g = __ldcs(grad + i);  // gradient is dead after this read: streaming load
     float4 d = stream_delta ? __ldcs(delta + i) : delta[i];
     float4 x = w[i];
-    sgd_apply4<kHasWC>(g, d, x, nf, momentum, one_minus_m_lr, sgd_weightcost_at<kHasWC>(i, weightcost, br));
-    if (stream_delta) __stcs(delta + i, d);
-    else delta[i] = d;
-    w[i] = x;
-    if (w_lo != nullptr) w_lo[i] = tf32_lo4(x);
-  }
-}
-
-// The same update for a launch that must stay on a FEW SMs (train_bunch, "side-car update"): blocks of 1024 threads in
-// clusters of two, so that each cluster fills one TPC (both SMs) and leaves every other TPC whole for the CTA pairs of
-// the GEMMs running beside it; three elements per thread in flight (9 independent 16-byte loads; four spill at the 64-register cap of a 1024-thread block) because 20 SMs, not
-// 148, have to pull the stream.  Same arithmetic (sgd_apply4), element by element: results are bit-identical.
-template <bool kHasWC>
-__global__ void __launch_bounds__(1024)
-bp_sgd_sidecar_kernel(float4* __restrict__ delta, float4* __restrict__ w, const float4* __restrict__ grad,
-                      long long begin4, long long n4, float nf, float momentum, float one_minus_m_lr, float weightcost,
-                      SgdBiasRanges br, float4* __restrict__ w_lo, int stream_delta) {
-  constexpr int kIlp = 3;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  long long i = begin4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + (kIlp - 1) * stride < n4; i += kIlp * stride) {
-    float4 g[kIlp], d[kIlp], x[kIlp];
-#pragma unroll
-    for (int u = 0; u < kIlp; ++u) {
-      const long long j = i + u * stride;
-      g[u] = __ldcs(grad + j);
-      d[u] = stream_delta ? __ldcs(delta + j) : delta[j];
-      x[u] = w[j];
+    float wc = weightcost;
+    if (kHasWC) {
+#pragma unroll 1
+      for (int r = 0; r < br.n; ++r)
+        if (i >= br.begin4[r] && i < br.end4[r]) wc = 0.0f;
     }
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    float dv[4] = {d.x, d.y, d.z, d.w};
+    float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-    for (int u = 0; u < kIlp; ++u) {
-      const long long j = i + u * stride;
-      sgd_apply4<kHasWC>(g[u], d[u], x[u], nf, momentum, one_minus_m_lr, sgd_weightcost_at<kHasWC>(j, weightcost, br));
-      if (stream_delta) __stcs(delta + j, d[u]);
-      else delta[j] = d[u];
-      w[j] = x[u];
-      if (w_lo != nullptr) w_lo[j] = tf32_lo4(x[u]);
+    for (int k = 0; k < 4; ++k) {
+      float t = __fdiv_rn(gv[k], nf);
+      if (kHasWC) t = __fadd_rn(t, __fmul_rn(wc, xv[k]));
+      const float nd = __fsub_rn(__fmul_rn(momentum, dv[k]), __fmul_rn(one_minus_m_lr, t));
+      dv[k] = nd;
+      xv[k] = __fadd_rn(nd, xv[k]);
     }
-  }
-  for (; i < n4; i += stride) {
-    const float4 g = __ldcs(grad + i);
-    float4 d = stream_delta ? __ldcs(delta + i) : delta[i];
-    float4 x = w[i];
-    sgd_apply4<kHasWC>(g, d, x, nf, momentum, one_minus_m_lr, sgd_weightcost_at<kHasWC>(i, weightcost, br));
-    if (stream_delta) __stcs(delta + i, d);
-    else delta[i] = d;
-    w[i] = x;
-    if (w_lo != nullptr) w_lo[i] = tf32_lo4(x);
+    if (stream_delta) __stcs(delta + i, make_float4(dv[0], dv[1], dv[2], dv[3]));
+    else delta[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    w[i] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    if (w_lo != nullptr) {
+      float lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo[k] = xv[k] - __uint_as_float(__float_as_uint(xv[k]) & 0xFFFFE000u);
+      w_lo[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 

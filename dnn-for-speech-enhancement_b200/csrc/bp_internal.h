@@ -85,12 +85,6 @@ enum Tunable : int {
   TUN_SGD_STREAM,   // "sgd_stream"   BP_SGD_STREAM   1   streaming access to the momentum deltas in the update
   TUN_SGD_EARLY,    // "sgd_early"    BP_SGD_EARLY    6   blocks per SM of the early update of layers >= 2 (0 = off)
   TUN_SPLITK,       // "splitk"       BP_SPLITK      -1   output-layer K slices: -1 automatic, 0 never, N force
-  TUN_SGD_DEFER,    // "sgd_defer"    BP_SGD_DEFER    0   side-car update: layers >= this are updated on a few TPCs beside
-                    //                                    the next GEMMs (0 = off; single GPU, per-product launches)
-  TUN_SGD_DEFER_TPCS,  // "sgd_defer_tpcs" BP_SGD_DEFER_TPCS 10  TPCs (clusters of two 1024-thread blocks) of the side-car
-  TUN_SGD_DEFER_AT,    // "sgd_defer_at"   BP_SGD_DEFER_AT    0  side-car starts 0 after the dX chain, 1 after the bunch's last update
-  TUN_DW1_SPLIT,       // "dw1_split"      BP_DW1_SPLIT       0  first layer's gradient in two launches, the first over this
-                       //                                        many 256-row slices of the block, updated under the second
   TUN_COUNT
 };
 int tunable(Tunable t);

@@ -28,11 +28,7 @@ struct TunableDef {
 };
 const TunableDef kTunables[TUN_COUNT] = {{"pdl", "BP_PDL", 1},         {"tma_hint", "BP_TMA_HINT", 1},
                                             {"pairs", "BP_PAIRS", 1},     {"sgd_stream", "BP_SGD_STREAM", 1},
-                                            {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1},
-                                            {"sgd_defer", "BP_SGD_DEFER", 0},
-                                            {"sgd_defer_tpcs", "BP_SGD_DEFER_TPCS", 10},
-                                            {"sgd_defer_at", "BP_SGD_DEFER_AT", 0},
-                                            {"dw1_split", "BP_DW1_SPLIT", 0}};
+                                            {"sgd_early", "BP_SGD_EARLY", 6}, {"splitk", "BP_SPLITK", -1}};
 std::atomic<int> g_tunable[TUN_COUNT];
 std::once_flag g_tunable_once;
 void init_tunables() {

@@ -151,13 +151,6 @@ struct Rank {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_grad = nullptr, ev_comm = nullptr, ev_side = nullptr;
   cudaEvent_t ev_upper = nullptr, ev_comm_upper = nullptr;  // dW / all-reduce of layers >= 2 complete
   cudaEvent_t ev_d[BP_MAXLAYER] = {};  // ev_d[l]: dE/dX_l is complete (recorded on `compute`)
-  // Side-car update (option "sgd_defer"): the layers >= upd_from of the bunch just trained are updated by a launch that
-  // occupies a few TPCs of its own on the stream `upd`; the next forward pass waits for ev_upd[l] before it reads W_l.
-  cudaStream_t upd = nullptr;
-  cudaEvent_t ev_upd[BP_MAXLAYER] = {};
-  cudaEvent_t ev_upd_go = nullptr;     // what the side-car waits for on `compute`
-  cudaEvent_t ev_dw1a = nullptr;       // option "dw1_split": the first slice of the first layer's gradient is complete
-  int upd_from = 0;                    // > 0: updates of the layers >= upd_from are in flight on `upd`
   float *w = nullptr, *dw = nullptr, *g = nullptr;
   float* w_lo = nullptr;   // split-precision low part of the weights (3xTF32 mode only)
   int passes = 1;          // 1 = TF32, 3 = 3xTF32
@@ -326,10 +319,6 @@ int rank_destroy(Rank* r) {
     if (e) cudaEventDestroy(e);
   for (auto e : r->ev_d)
     if (e) cudaEventDestroy(e);
-  for (auto e : r->ev_upd)
-    if (e) cudaEventDestroy(e);
-  if (r->ev_upd_go) cudaEventDestroy(r->ev_upd_go);
-  if (r->ev_dw1a) cudaEventDestroy(r->ev_dw1a);
   for (auto e : r->pev)
     if (e) cudaEventDestroy(e);
   for (auto e : r->tev)
@@ -343,7 +332,7 @@ int rank_destroy(Rank* r) {
     if (ds.fwd_done) cudaEventDestroy(ds.fwd_done);
     if (ds.out_done) cudaEventDestroy(ds.out_done);
   }
-  for (auto s : {r->compute, r->copy, r->comm_stream, r->side, r->d2h, r->upd})
+  for (auto s : {r->compute, r->copy, r->comm_stream, r->side, r->d2h})
     if (s) cudaStreamDestroy(s);
   delete r;
   return BP_OK;
@@ -381,8 +370,6 @@ int preload_runtime_kernels() {
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, true>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<false>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<true>));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_sidecar_kernel<false>));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_sidecar_kernel<true>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_input_dropout_kernel));
   return BP_OK;
 }
@@ -438,10 +425,6 @@ int rank_create(Rank** out, const bp_config* cfg, float* const* weights, float* 
     CU_TRY(cudaEventCreateWithFlags(&r->ev_upper, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_comm_upper, cudaEventDisableTiming));
     for (auto& e : r->ev_d) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU_TRY(cudaStreamCreateWithFlags(&r->upd, cudaStreamNonBlocking));
-    for (auto& e : r->ev_upd) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&r->ev_upd_go, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&r->ev_dw1a, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&r->ev_t0));
     CU_TRY(cudaEventCreate(&r->ev_t1));
     CU_TRY(cudaEventCreateWithFlags(&r->ev_grad, cudaEventDisableTiming));
@@ -741,8 +724,6 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
   if (train) BP_TRY(input_dropout(r, c, f0, n));
   for (int l = 1; l <= r->L; ++l) {
     LayerState& ls = r->layer[l];
-    // side-car update of the previous bunch (train_bunch): W_l is final once ev_upd[l] has fired
-    if (r->upd_from > 0 && l >= r->upd_from) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upd[l], 0));
     GemmParams p{};
     p.M = ls.N;
     p.N = n;
@@ -819,7 +800,6 @@ int forward_rows(Rank* r, ChunkBuf& c, int f0, int n, bool train, float* out2, l
     }
     r->launches++;
   }
-  r->upd_from = 0;  // every pending layer has been waited for on `compute`
   return BP_OK;
 }
 
@@ -1247,35 +1227,6 @@ int launch_sgd_range(Rank* r, long long begin4, long long end4, int blocks_per_s
   return BP_OK;
 }
 
-// The same update of arena floats [4*begin4, 4*end4) on `tpcs` TPCs only (bp_sgd_sidecar_kernel), on the stream `upd`.
-int launch_sgd_sidecar(Rank* r, long long begin4, long long end4, int tpcs) {
-  const bp_config& cf = r->cfg;
-  const float nf = (float)cf.bunchsize;
-  const float c1 = (1 - cf.momentum) * cf.lrate;
-  const int sgd_stream = tunable(TUN_SGD_STREAM);
-  cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3(2 * std::max(1, std::min(tpcs, r->num_sms / 2)));
-  lc.blockDim = dim3(1024);
-  lc.stream = r->upd;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  lc.attrs = attr;
-  lc.numAttrs = 1;
-  float4 *dw = (float4*)r->dw, *w = (float4*)r->w, *w_lo = (float4*)r->w_lo;
-  const float4* g = (const float4*)r->g;
-  if (cf.weightcost != 0.0f)
-    CU_TRY(cudaLaunchKernelEx(&lc, bp_sgd_sidecar_kernel<true>, dw, w, g, begin4, end4, nf, cf.momentum, c1, cf.weightcost,
-                              r->bias_ranges, w_lo, sgd_stream));
-  else
-    CU_TRY(cudaLaunchKernelEx(&lc, bp_sgd_sidecar_kernel<false>, dw, w, g, begin4, end4, nf, cf.momentum, c1, 0.0f,
-                              r->bias_ranges, w_lo, sgd_stream));
-  r->launches++;
-  return BP_OK;
-}
-
 int peer_exchange(Rank* r);
 
 // One train bunch as two chained launches (forward products; dX chain + dW products) and the update.
@@ -1337,11 +1288,6 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   // update has not touched it yet).  So dW_l is launched on the side stream as soon as dE/dX_l exists and runs
   // concurrently with the rest of the dX chain, filling the SMs a 128-tile GEMM leaves idle on a 148-SM part.
   // Last layer first, so its all-reduce starts earliest.
-  int dw1_rows = 0;  // > 0: rows [0, dw1_rows) of the first layer's gradient block come from a launch of their own
-  if (!r->dp_p2p && !r->nccl_comm && r->L >= 2) {
-    const int t = tunable(TUN_DW1_SPLIT);
-    if (t > 0 && t * 256 < r->layer[1].K + 1) dw1_rows = t * 256;
-  }
   auto launch_dw = [&](int l, cudaEvent_t after) -> int {
     LayerState& ls = r->layer[l];
     CU_TRY(cudaStreamWaitEvent(r->side, after, 0));
@@ -1371,22 +1317,13 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
     const int total = p.N;
     int slices = 1;
     if (r->nccl_comm && !r->dp_p2p) slices = std::max(1, std::min(r->ar_slices, (total + kBlockN - 1) / kBlockN));
-    int per = ((total + slices - 1) / slices + kBlockN - 1) / kBlockN * kBlockN;
-    // Single GPU, first layer (option "dw1_split" = fan-in rows of the first slice / 256): the gradient block is computed
-    // in two launches so that the rows of the first are updated while the second is still computing — only the
-    // second slice's update stays behind the last GEMM of the bunch.  Same tiles, same k order: same bits.
-    if (l == 1 && dw1_rows > 0) per = dw1_rows;
+    const int per = ((total + slices - 1) / slices + kBlockN - 1) / kBlockN * kBlockN;
     for (int b0 = 0; b0 < total; b0 += per) {
       p.n_begin = b0;
       p.N = std::min(total, b0 + per);
-      if (l == 1 && dw1_rows > 0 && b0 > 0) p.N = total;  // two slices: [0, dw1_rows) and the rest
       BP_TRY((launch_product(PROD_DW, r->side, r->gemm_sms(), ls.d_dw, *bmap, p)));
       r->launches++;
       tl_mark(r, r->side, kDwLabel[l]);
-      if (l == 1 && dw1_rows > 0) {
-        if (b0 == 0) CU_TRY(cudaEventRecord(r->ev_dw1a, r->side));
-        else break;
-      }
       if (r->nccl_comm && !r->dp_p2p) {
         float* gs = r->g + ls.off + (long long)b0 * ls.ldN;
         const size_t cnt = (p.N == total) ? (size_t)(ls.size - (long long)b0 * ls.ldN)
@@ -1437,50 +1374,15 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   // tensor-bound and reads neither weights nor deltas: once the dX chain is done the layers >= 2 are updated while dW_1
   // still runs on the side stream.  The early launch leaves thread slots free so the GEMM's CTAs become resident.
   const int sgd_early_blocks = tunable(TUN_SGD_EARLY);  // 0 = one update launch after all gradients (reference order)
-  // Side-car update (single GPU): the layers >= defer_from leave the critical path altogether.  Their update needs only
-  // this bunch's dW_l (all issued before ev_upper) and the end of the dX chain (the last reader of W_l), and its result
-  // is not needed before the NEXT bunch's forward pass reaches layer l; so it runs on `upd`, on a few TPCs of its own,
-  // beside dW_1, the first layer's update and the next bunch's first forward products.
-  int defer_from = 0;
-  if (!r->dp_p2p && !r->nccl_comm && r->L >= 2) {
-    const int d = tunable(TUN_SGD_DEFER);
-    if (d >= 2 && d <= r->L) defer_from = d;
-  }
-  const int defer_at = tunable(TUN_SGD_DEFER_AT);
-  auto launch_deferred = [&]() -> int {
-    CU_TRY(cudaEventRecord(r->ev_upd_go, r->compute));
-    CU_TRY(cudaStreamWaitEvent(r->upd, r->ev_upd_go, 0));
-    CU_TRY(cudaStreamWaitEvent(r->upd, r->ev_upper, 0));
-    const int tpcs = tunable(TUN_SGD_DEFER_TPCS);
-    for (int l = defer_from; l <= r->L; ++l) {
-      const long long b4 = r->layer[l].off / 4;
-      const long long e4 = (l < r->L ? r->layer[l + 1].off : r->arena_floats) / 4;
-      BP_TRY(launch_sgd_sidecar(r, b4, e4, tpcs));
-      CU_TRY(cudaEventRecord(r->ev_upd[l], r->upd));
-    }
-    r->upd_from = defer_from;
-    return BP_OK;
-  };
-  if (defer_from && defer_at == 0) BP_TRY(launch_deferred());
-  const long long compute_end4 = (defer_from ? r->layer[defer_from].off : r->arena_floats) / 4;  // updated on `compute`
-  long long tail_end4 = compute_end4;
+  long long tail_end4 = r->arena_floats / 4;
   if (sgd_early_blocks > 0 && r->L >= 2 && !r->dp_p2p) {
+    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
+    if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
     tail_end4 = r->layer[2].off / 4;
-    if (tail_end4 < compute_end4) {
-      CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upper, 0));
-      if (r->nccl_comm) CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_comm_upper, 0));
-      BP_TRY(launch_sgd_range(r, tail_end4, compute_end4, sgd_early_blocks));
-      tl_mark(r, r->compute, "update, layers >= 2");
-    }
+    BP_TRY(launch_sgd_range(r, tail_end4, r->arena_floats / 4, sgd_early_blocks));
+    tl_mark(r, r->compute, "update, layers >= 2");
   }
   mark();                                               // 3: early update of layers >= 2 done
-  long long head4 = 0;  // [0, head4) has been updated before the join
-  if (dw1_rows > 0 && tail_end4 == r->layer[2].off / 4) {
-    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_dw1a, 0));
-    head4 = (r->layer[1].off + (long long)dw1_rows * r->layer[1].ldN) / 4;
-    BP_TRY(launch_sgd_range(r, r->layer[1].off / 4, head4, sgd_early_blocks > 0 ? sgd_early_blocks : 8));
-    tl_mark(r, r->compute, "update, first slice of layer 1");
-  }
   CU_TRY(cudaEventRecord(r->ev_side, r->side));
   CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_side, 0));
   tl_mark(r, r->compute, "join (all dW done)");
@@ -1491,9 +1393,8 @@ int train_bunch(Rank* r, ChunkBuf& c, int f0, double* loss_slot) {
   }
   mark();                                               // 5: all-reduce waited
   if (r->dp_p2p) BP_TRY(peer_exchange(r));              // owner-side reduce + update + all-gather
-  else BP_TRY(launch_sgd_range(r, head4, tail_end4, 8));
+  else BP_TRY(launch_sgd_range(r, 0, tail_end4, 8));
   tl_mark(r, r->compute, "update / exchange, end of bunch");
-  if (defer_from && defer_at != 0) BP_TRY(launch_deferred());
   mark();                                               // 6: sgd done
   r->step++;
   r->bunches++;
@@ -1537,10 +1438,6 @@ int rank_train_resident(Rank* r, int first_bunch, int n_bunches) {
   }
   for (int b = 0; b < n_bunches; ++b)
     BP_TRY(train_bunch(r, c, (first_bunch + b) * r->local_bunch, r->loss_dev[li] + b));
-  if (r->upd_from > 0) {  // side-car update of the last bunch: everything queued on `compute` from here on sees it
-    CU_TRY(cudaStreamWaitEvent(r->compute, r->ev_upd[r->L], 0));
-    r->upd_from = 0;
-  }
   CU_TRY(cudaEventRecord(r->loss_done[li], r->compute));
   CU_TRY(cudaEventRecord(c.consumed, r->compute));
   c.consumed_valid = true;

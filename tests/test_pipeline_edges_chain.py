@@ -169,48 +169,3 @@ def test_chained_launches_are_bit_identical_with_one_launch_per_product(case):
         assert np.array_equal(res[0][0][l], res[1][0][l]) and np.array_equal(res[0][1][l], res[1][1][l]), f"layer {l}"
         assert np.isfinite(res[1][0][l]).all() and not np.array_equal(res[1][0][l], w[l])
 
-
-
-SIDECAR_CASES = [c for c in CHAIN_CASES if c[0] in ("tiny ragged", "nine layers", "odd sizes, weight cost", "dropout",
-                                                    "3xTF32", "C2, 3 bunches", "C4 per-GPU share")]
-
-
-@pytest.mark.parametrize("mode", [(2, 0, 0), (3, 0, 0), (2, 1, 0), (0, 0, 1), (2, 0, 8)],
-                         ids=["from2", "from3", "from2-after-the-bunch", "dw1-split", "from2+dw1-split"])
-@pytest.mark.parametrize("case", SIDECAR_CASES, ids=[c[0] for c in SIDECAR_CASES])
-def test_sidecar_update_is_bit_identical(case, mode):
-    """Option sgd_defer (train_bunch, csrc/bp_runtime.cu): the layers >= N are updated by bp_sgd_sidecar_kernel on a few
-    TPCs of their own while dW_1, the first layer's update and the next bunch's first forward products run.  Same
-    arithmetic, same operands, only later: the trained weights and the CV score must be IDENTICAL to the default
-    schedule, over several bunches in one call and over two calls (the pending update is joined at the end of a call).
-    Option dw1_split: the first layer's gradient block in two launches, the first slice updated under the second."""
-    import oracle_py as O
-    bp = importlib.import_module("dnn-for-speech-enhancement_b200")
-    _name, sizes, bunch, nb, kw = case
-    w, b = O.glorot_init(sizes, seed=3)
-    x, t = O.synth_data(bunch * nb + 3, sizes[0], sizes[-1], seed=11)
-    res = []
-    for defer, at, split in ((0, 0, 0), mode):
-        g = bp.BP_GPU(1, len(sizes), sizes, bunch, 1.0, 0.9, kw.get("weightcost", 0.0), w, b, kw.get("dropoutflag", 0),
-                      kw.get("visible_omit", 0.0), kw.get("hid_omit", 0.0), device=0, seed=777,
-                      activation=kw.get("activation", 0), math_mode=kw.get("math_mode", 0))
-        try:   # the scheduling options are process-wide: put them back whatever happens
-            g.set_option("chain", 0)
-            g.set_option("sgd_defer", defer)
-            g.set_option("sgd_defer_at", at)
-            g.set_option("dw1_split", split)
-            assert g.get_option("sgd_defer") == defer and g.get_option("dw1_split") == split
-            g.train(x.shape[0], x, t)
-            g.train(bunch + 1, x[:bunch + 1], t[:bunch + 1])
-            res.append((g.returnWeights(), g.CrossValid(bunch, x[:bunch], t[:bunch])))
-        finally:
-            g.set_option("sgd_defer", 0)
-            g.set_option("sgd_defer_at", 0)
-            g.set_option("dw1_split", 0)
-            g.close()
-    (wa, ba), cva = res[0]
-    (wb, bb), cvb = res[1]
-    for l in range(1, len(sizes)):
-        assert np.array_equal(wa[l], wb[l]) and np.array_equal(ba[l], bb[l]), f"layer {l}"
-        assert np.isfinite(wb[l]).all() and not np.array_equal(wb[l], w[l])
-    assert cva == cvb
