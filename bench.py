@@ -560,7 +560,8 @@ def main():
     gb = lb * world
     metric = "frames_per_sec"
     cfg = {"workload": f"{args.workload}: {'-'.join(map(str, sizes))} {'train (fwd+bwd+SGD)' if train else 'forward decode'}",
-           "bunch_per_gpu": lb, "global_bunch": gb, "parallelism": f"dp{world}",
+           "bunch_per_gpu": lb, "global_bunch": gb,
+           "parallelism": f"dp{world}" if train or world == 1 else f"{world} independent replicas (no exchange)",
            "dropout": [dflag, vo, ho], "activation": "sigmoid" if act else "relu", "l2_policy": "inputs larger than L2 (resident chunk cycles)",
            "math": ("3xTF32 split-precision tensor-core products (fp32 storage, fp32 accumulate, ~fp32 accuracy)"
                     if args.math == "3xtf32" else "tf32 tensor-core products (fp32 storage, fp32 accumulate)")}
@@ -617,7 +618,9 @@ def main():
     ctx = Ctx(bp, dist, rank, local_rank, world)
     w, b = glorot(sizes)
     math_mode = bp.BP_MATH_3XTF32 if args.math == "3xtf32" else bp.BP_MATH_TF32
-    g = ctx.create(sizes, gb, w, b, (dflag, vo, ho), act, math_mode)
+    # Training shards a GLOBAL bunch over the ranks (gradient exchange).  Decode has no exchange step: every rank is an
+    # independent replica decoding its own batches of `lb` frames ("replicas only").
+    g = ctx.create(sizes, gb if train else lb, w, b, (dflag, vo, ho), act, math_mode, world=None if train else 1)
     barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
 
     cb = args.chunk_bunches
