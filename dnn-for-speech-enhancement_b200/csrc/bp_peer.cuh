@@ -59,14 +59,6 @@ __device__ __forceinline__ void peer_wait_all(const unsigned long long* mine, in
 __global__ void bp_peer_wait_kernel(const unsigned long long* mine, int world, unsigned long long value) {
   peer_wait_all(mine, world, value);
 }
-// Same for two counter groups at once (BP_PEER_EARLY: the upper layers' rows and the first layer's rows are published
-// separately).
-__global__ void bp_peer_wait2_kernel(const unsigned long long* a, const unsigned long long* b, int world,
-                                     unsigned long long value) {
-  peer_wait_all(a, world, value);
-  peer_wait_all(b, world, value);
-}
-
 // Layer geometry of the arena for the owner-side update.
 struct PeerLayers {
   int n;
@@ -84,21 +76,16 @@ struct PeerArenas {
 
 // Owner-side reduce + momentum SGD + all-gather.  Same arithmetic, operation for operation, as bp_sgd_kernel
 // (kernUpdatedelta + kernAccSum, DevFunc.cu:313-318, 270-277) on G = recv[0] + recv[1] + ... in rank order.
-// kRange (BP_PEER_EARLY, see train_bunch): the launch covers float4 elements [begin4, end4) of the arena only, so the
-// exchange of the layers >= 2 can run — on its own pair of counters — while the first layer's gradient GEMM is still
-// computing; kRange = false is the whole-arena launch of the default path (begin4 / end4 unused).
-template <bool kHasWC, bool kRange = false>
+template <bool kHasWC>
 __global__ void __launch_bounds__(256)
 bp_peer_sgd_kernel(float4* __restrict__ delta, const float4* __restrict__ recv, long long arena4,
                    const __grid_constant__ PeerArenas pa, const __grid_constant__ PeerLayers pl, int world, int rank,
                    float nf, float momentum, float one_minus_m_lr, float weightcost,
-                   const unsigned long long* grad_flags, unsigned long long step, long long begin4 = 0,
-                   long long end4 = 0) {
+                   const unsigned long long* grad_flags, unsigned long long step) {
   peer_wait_all(grad_flags, world, step);  // every rank's partial gradients of this step have landed in `recv`
   __syncthreads();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long first = kRange ? begin4 : 0, last = kRange ? end4 : arena4;
-  for (long long i = first + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < last; i += stride) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < arena4; i += stride) {
     int l = 0;
 #pragma unroll 1
     while (l < pl.n - 1 && i >= pl.end4[l]) ++l;

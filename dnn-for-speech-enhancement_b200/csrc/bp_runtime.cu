@@ -191,8 +191,7 @@ struct Rank {
   int dp_p2p = 0;
   float* recv = nullptr;                 // world_size slabs of arena_floats: recv + src*arena_floats
   unsigned long long* flags = nullptr;   // kPeerFlagGroups x kMaxPeers counters, group g at flags + g*kMaxPeers:
-                                         // 0 gradients of step s landed from src, 1 weights landed from src;
-                                         // BP_PEER_EARLY: 0/1 = layers >= 2, 2/3 = the same two for layer 1
+                                         // 0 gradients of step s landed from src, 1 weights landed from src
   PeerMem peer[kMaxPeers];
   unsigned long long dp_step = 0;
   PeerLayers peer_layers{};
@@ -364,10 +363,8 @@ int preload_runtime_kernels() {
   cudaFuncAttributes fa;
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_signal_kernel));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_wait_kernel));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, false>));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, false>));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false, true>));
-  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true, true>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<false>));
+  CU_TRY(cudaFuncGetAttributes(&fa, bp_peer_sgd_kernel<true>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<false>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_sgd_kernel<true>));
   CU_TRY(cudaFuncGetAttributes(&fa, bp_input_dropout_kernel));
