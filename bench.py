@@ -880,6 +880,19 @@ def main():
             line["exchange_ms"] = {"exposed_dw_tail": prof["dw"] / nprof, "owner_update_and_all_gather": prof["sgd"] / nprof,
                                    "note": "per-class CUDA events of rank 0; the gradient reduce-scatter runs inside "
                                            "the dW epilogues, the update + all-gather in bp_peer_sgd_kernel"}
+            try:   # NVLink counters are not readable on the pool's boxes: the ALGORITHMIC bytes of the exchange instead
+                arena = 4.0 * n_params_padded(sizes)
+                leg = arena * (world - 1) / world   # what a rank stores into its peers' memory in each leg
+                ag_ms = prof["sgd"] / nprof
+                line["nvlink"] = {"kind": "algorithmic (not a counter)", "arena_bytes": arena,
+                                  "reduce_scatter_bytes_out_per_rank": leg, "all_gather_bytes_out_per_rank": leg,
+                                  "bytes_in_per_rank_per_step": 2 * leg,
+                                  "all_gather_gbs_out_per_rank": leg / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None,
+                                  "note": "reduce-scatter = remote stores of the dW epilogues (under the back-propagation "
+                                          "launch); all-gather = remote stores of bp_peer_sgd_kernel, timed together with "
+                                          "the wait for every rank's partial gradients and the owner's update"}
+            except Exception as e:
+                line["nvlink"] = {"error": str(e)}
     if world == 1 and train and not args.no_ref_gpu:
         rg = ref_gpu_arm(sizes, lb, (dflag, vo, ho))
         if rg and "value" in rg:
