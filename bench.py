@@ -881,16 +881,7 @@ def main():
                                    "note": "per-class CUDA events of rank 0; the gradient reduce-scatter runs inside "
                                            "the dW epilogues, the update + all-gather in bp_peer_sgd_kernel"}
             try:   # NVLink counters are not readable on the pool's boxes: the ALGORITHMIC bytes of the exchange instead
-                arena = 4.0 * n_params_padded(sizes)
-                leg = arena * (world - 1) / world   # what a rank stores into its peers' memory in each leg
-                ag_ms = prof["sgd"] / nprof
-                line["nvlink"] = {"kind": "algorithmic (not a counter)", "arena_bytes": arena,
-                                  "reduce_scatter_bytes_out_per_rank": leg, "all_gather_bytes_out_per_rank": leg,
-                                  "bytes_in_per_rank_per_step": 2 * leg,
-                                  "all_gather_gbs_out_per_rank": leg / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None,
-                                  "note": "reduce-scatter = remote stores of the dW epilogues (under the back-propagation "
-                                          "launch); all-gather = remote stores of bp_peer_sgd_kernel, timed together with "
-                                          "the wait for every rank's partial gradients and the owner's update"}
+                line["nvlink"] = nvlink_algorithmic(sizes, world, prof["sgd"] / nprof)
             except Exception as e:
                 line["nvlink"] = {"error": str(e)}
     if world == 1 and train and not args.no_ref_gpu:
@@ -913,6 +904,21 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def nvlink_algorithmic(sizes, world, all_gather_ms):
+    """Bytes a rank stores into its peers' memory per step of the peer-memory exchange (csrc/bp_peer.cuh): the padded
+    parameter arena, minus the 1/world of it the rank owns, once as partial gradients (reduce-scatter, from the dW
+    epilogues) and once as new weights (all-gather, from bp_peer_sgd_kernel); every rank receives the same amounts."""
+    arena = 4.0 * n_params_padded(sizes)
+    leg = arena * (world - 1) / world
+    return {"kind": "algorithmic (not a counter)", "arena_bytes": arena,
+            "reduce_scatter_bytes_out_per_rank": leg, "all_gather_bytes_out_per_rank": leg,
+            "bytes_in_per_rank_per_step": 2 * leg,
+            "all_gather_gbs_out_per_rank": leg / (all_gather_ms * 1e-3) / 1e9 if all_gather_ms > 0 else None,
+            "note": "reduce-scatter = remote stores of the dW epilogues (under the back-propagation launch); all-gather = "
+                    "remote stores of bp_peer_sgd_kernel, timed together with the wait for every rank's partial "
+                    "gradients and the owner's update"}
 
 
 def n_params_padded(sizes):

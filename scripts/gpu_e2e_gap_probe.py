@@ -53,31 +53,35 @@ def bunches(with_copies):
     return ms
 
 
-for rep in range(2):
-    print(f"device ms per bunch: GPU to itself {bunches(False):.4f}   copies streaming beside it {bunches(True):.4f}")
-
 e2e_cb = 8
 n = e2e_cb * lb
-for rep in range(2):
-    g.train(n, px.array[:n], pt.array[:n])
-    g.sync()
-    t_train, t_loss = [], []
-    t_begin = time.perf_counter()
-    for c in range(24):
-        o = (c % (cb // e2e_cb)) * n
-        t0 = time.perf_counter()
-        g.train(n, px.array[o: o + n], pt.array[o: o + n])
-        t1 = time.perf_counter()
-        if c > 0:
-            g.train_losses(age=1, max_n=e2e_cb)
-        t2 = time.perf_counter()
-        t_train.append((t1 - t0) * 1e3)
-        t_loss.append((t2 - t1) * 1e3)
-    g.sync()
-    tot = (time.perf_counter() - t_begin) * 1e3
-    print(f"24 calls of 8 bunches: {tot / 24:.3f} ms per call ({24 * n / tot / 1e3:.3f} M frames/s);  bp_train() median "
-          f"{statistics.median(t_train):.3f} ms (min {min(t_train):.3f}, max {max(t_train):.3f});  bp_train_losses() median "
-          f"{statistics.median(t_loss):.3f} ms (max {max(t_loss):.3f})")
-    print("   bp_train ms:", " ".join(f"{v:.2f}" for v in t_train))
-    print("   losses   ms:", " ".join(f"{v:.2f}" for v in t_loss))
+for chain in (0, 1) if "chain" in sys.argv[1:] else (0,):
+  g.set_option("chain", chain)
+  g.upload_chunk(cb * lb, px.array, pt.array)   # the e2e loop below leaves an 8-bunch chunk resident
+  g.train_resident(0, cb)
+  print(f"--- chain={chain}")
+  for rep in range(2):
+    print(f"device ms per bunch: GPU to itself {bunches(False):.4f}   copies streaming beside it {bunches(True):.4f}")
+  for rep in range(2):
+      g.train(n, px.array[:n], pt.array[:n])
+      g.sync()
+      t_train, t_loss = [], []
+      t_begin = time.perf_counter()
+      for c in range(24):
+          o = (c % (cb // e2e_cb)) * n
+          t0 = time.perf_counter()
+          g.train(n, px.array[o: o + n], pt.array[o: o + n])
+          t1 = time.perf_counter()
+          if c > 0:
+              g.train_losses(age=1, max_n=e2e_cb)
+          t2 = time.perf_counter()
+          t_train.append((t1 - t0) * 1e3)
+          t_loss.append((t2 - t1) * 1e3)
+      g.sync()
+      tot = (time.perf_counter() - t_begin) * 1e3
+      print(f"24 calls of 8 bunches: {tot / 24:.3f} ms per call ({24 * n / tot / 1e3:.3f} M frames/s);  bp_train() median "
+            f"{statistics.median(t_train):.3f} ms (min {min(t_train):.3f}, max {max(t_train):.3f});  bp_train_losses() median "
+            f"{statistics.median(t_loss):.3f} ms (max {max(t_loss):.3f})")
+      print("   bp_train ms:", " ".join(f"{v:.2f}" for v in t_train))
+      print("   losses   ms:", " ".join(f"{v:.2f}" for v in t_loss))
 g.close()

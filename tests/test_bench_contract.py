@@ -59,3 +59,20 @@ def test_flop_and_parameter_bookkeeping_matches_survey_table():
     assert abs(bench.flops_per_frame(c3, True) / 1e6 - 78.75) < 0.005
     assert bench.n_params(c4) == 23093248 + 10497 and abs(bench.flops_per_frame(c4, True) / 1e6 - 126.98) < 0.005
     assert bench.WORKLOADS["C4"][1] * 8 == 4096 and bench.WORKLOADS["C5"][1] == 8192 and not bench.WORKLOADS["C5"][5]
+
+
+def test_exchange_bytes_of_the_peer_memory_step():
+    """`nvlink` of the N > 1 line (algorithmic, the boxes expose no NVLink counters): each leg of the exchange moves the
+    padded arena minus the rank's own 1/N share; the arena is >= the 58.84 MB of SURVEY.md §8(d)'s gradient size."""
+    sys.path.insert(0, ROOT)
+    import bench
+    c2 = bench.WORKLOADS["C2"][0]
+    for world in (2, 4, 8):
+        nv = bench.nvlink_algorithmic(c2, world, 0.114)
+        arena = nv["arena_bytes"]
+        assert 4 * bench.n_params(c2) <= arena <= 1.01 * 4 * bench.n_params(c2)
+        assert nv["all_gather_bytes_out_per_rank"] == arena * (world - 1) / world == nv["reduce_scatter_bytes_out_per_rank"]
+        assert nv["bytes_in_per_rank_per_step"] == 2 * nv["all_gather_bytes_out_per_rank"]
+        assert abs(nv["all_gather_gbs_out_per_rank"] - nv["all_gather_bytes_out_per_rank"] / 0.114e-3 / 1e9) < 1e-6
+    assert bench.nvlink_algorithmic(c2, 8, 0.0)["all_gather_gbs_out_per_rank"] is None
+    json.dumps(bench.nvlink_algorithmic(c2, 8, 0.1))
